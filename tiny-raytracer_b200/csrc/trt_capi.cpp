@@ -1,0 +1,378 @@
+// trt_capi.cpp — the C ABI of include/trt.h over the host scene (trt_scene.cpp) and the sm_100a kernels
+// (trt_kernels.cu). No CPU fallback: every compute entry point needs a CUDA device and fails loudly without one.
+#include "../../include/trt.h"
+#include "trt_kernels.h"
+#include "trt_scene.hpp"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+static int fail_cuda(const char* what, cudaError_t e) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return e == cudaErrorMemoryAllocation ? TRT_ERR_OOM : TRT_ERR_CUDA;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_cuda(#call, e_); } while (0)
+
+struct DeviceCopy {
+    uint64_t version = 0; void* buf = nullptr; size_t bytes = 0; trtk::SceneView view{};
+};
+struct trt_scene {
+    trt::HostScene host;
+    std::map<int, DeviceCopy> on_device;   // device ordinal -> copy
+};
+struct trt_ctx {
+    int device = 0; int sm_count = 0; cudaStream_t stream = nullptr; cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned long long* d_counters = nullptr;   // 8 x u64 (5 used) followed by the u32 work counter
+    unsigned int* d_next_item = nullptr;
+    // scratch reused across calls (grown on demand)
+    void* scratch[4] = {nullptr, nullptr, nullptr, nullptr}; size_t scratch_bytes[4] = {0, 0, 0, 0};
+    char name[256];
+};
+
+static int ensure_scratch(trt_ctx* c, int slot, size_t bytes, void** out) {
+    if (bytes == 0) bytes = 16;
+    if (c->scratch_bytes[slot] < bytes) {
+        if (c->scratch[slot]) { cudaFree(c->scratch[slot]); c->scratch[slot] = nullptr; c->scratch_bytes[slot] = 0; }
+        CU(cudaMalloc(&c->scratch[slot], bytes));
+        c->scratch_bytes[slot] = bytes;
+    }
+    *out = c->scratch[slot];
+    return TRT_OK;
+}
+
+extern "C" {
+
+const char* trt_last_error(void) { return g_last_error.c_str(); }
+uint32_t trt_abi_version(void) { return TRT_ABI_VERSION; }
+
+// ------------------------------------------------------------------ context
+int trt_ctx_create(int device_ordinal, trt_ctx** out) {
+    if (!out) return fail(TRT_ERR_INVALID, "trt_ctx_create: out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(TRT_ERR_CUDA, std::string("trt_ctx_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path");
+    if (device_ordinal < 0 || device_ordinal >= n) return fail(TRT_ERR_INVALID, "trt_ctx_create: device ordinal out of range");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device_ordinal));
+    if (prop.major != 10) return fail(TRT_ERR_UNSUPPORTED, std::string("trt_ctx_create: built for sm_100a only, device is ") + prop.name);
+    CU(cudaSetDevice(device_ordinal));
+    trt_ctx* c = new (std::nothrow) trt_ctx();
+    if (!c) return fail(TRT_ERR_OOM, "trt_ctx_create: host allocation failed");
+    c->device = device_ordinal; c->sm_count = prop.multiProcessorCount;
+    std::snprintf(c->name, sizeof c->name, "%s", prop.name);
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&c->ev[i]));
+    CU(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long) + 64));
+    c->d_next_item = (unsigned int*)(c->d_counters + 8);
+    *out = c;
+    return TRT_OK;
+}
+int trt_ctx_destroy(trt_ctx* c) {
+    if (!c) return TRT_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 4; ++i) if (c->scratch[i]) cudaFree(c->scratch[i]);
+    if (c->d_counters) cudaFree(c->d_counters);
+    for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return TRT_OK;
+}
+int trt_ctx_device_name(trt_ctx* c, char* buf, size_t n) {
+    if (!c || !buf || n == 0) return fail(TRT_ERR_INVALID, "trt_ctx_device_name: bad argument");
+    std::snprintf(buf, n, "%s", c->name); return TRT_OK;
+}
+int trt_ctx_sm_count(trt_ctx* c, int* out) { if (!c || !out) return fail(TRT_ERR_INVALID, "trt_ctx_sm_count: bad argument"); *out = c->sm_count; return TRT_OK; }
+int trt_ctx_synchronize(trt_ctx* c) { if (!c) return fail(TRT_ERR_INVALID, "trt_ctx_synchronize: null ctx"); CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->stream)); return TRT_OK; }
+
+// ------------------------------------------------------------------ scene (host only)
+int trt_scene_create(trt_scene** out) {
+    if (!out) return fail(TRT_ERR_INVALID, "trt_scene_create: out is null");
+    *out = new (std::nothrow) trt_scene();
+    return *out ? TRT_OK : fail(TRT_ERR_OOM, "trt_scene_create: host allocation failed");
+}
+int trt_scene_destroy(trt_scene* s) {
+    if (!s) return TRT_OK;
+    for (auto& kv : s->on_device) if (kv.second.buf) { cudaSetDevice(kv.first); cudaFree(kv.second.buf); }
+    delete s; return TRT_OK;
+}
+static int add_mat(trt_scene* s, uint32_t kind, const float rgb[3], float param, uint32_t* id, const char* who) {
+    if (!s || !rgb) return fail(TRT_ERR_INVALID, std::string(who) + ": null argument");
+    uint32_t m = s->host.add_material(kind, rgb, param);
+    if (id) *id = m;
+    return TRT_OK;
+}
+int trt_add_lambertian(trt_scene* s, const float albedo[3], uint32_t* id) { return add_mat(s, TRT_MAT_LAMBERTIAN, albedo, 0.f, id, "trt_add_lambertian"); }
+int trt_add_metal(trt_scene* s, const float albedo[3], float fuzz, uint32_t* id) { return add_mat(s, TRT_MAT_METAL, albedo, fuzz, id, "trt_add_metal"); }
+int trt_add_dielectric(trt_scene* s, const float albedo[3], float ri, uint32_t* id) { return add_mat(s, TRT_MAT_DIELECTRIC, albedo, ri, id, "trt_add_dielectric"); }
+int trt_add_light(trt_scene* s, const float color[3], uint32_t* id) { return add_mat(s, TRT_MAT_LIGHT, color, 0.f, id, "trt_add_light"); }
+
+int trt_add_sphere(trt_scene* s, const float c[3], float r, uint32_t mat, uint32_t* id) {
+    if (!s || !c) return fail(TRT_ERR_INVALID, "trt_add_sphere: null argument");
+    std::string err; if (!s->host.add_sphere(c, r, mat, id, &err)) return fail(TRT_ERR_INVALID, err);
+    return TRT_OK;
+}
+int trt_add_quad(trt_scene* s, const float corner[3], const float u[3], const float v[3], uint32_t mat, uint32_t* id) {
+    if (!s || !corner || !u || !v) return fail(TRT_ERR_INVALID, "trt_add_quad: null argument");
+    std::string err; if (!s->host.add_quad(corner, u, v, mat, id, &err)) return fail(TRT_ERR_INVALID, err);
+    return TRT_OK;
+}
+int trt_add_prims(trt_scene* s, uint32_t n, const uint32_t* type, const float* data12, const uint32_t* mat) {
+    if (!s || (n && (!type || !data12 || !mat))) return fail(TRT_ERR_INVALID, "trt_add_prims: null argument");
+    s->host.prims.reserve(s->host.prims.size() + n);
+    std::string err;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* d = data12 + 12 * (size_t)i;
+        bool ok = type[i] == 0 ? s->host.add_sphere(d, d[3], mat[i], nullptr, &err)
+                : type[i] == 1 ? s->host.add_quad(d, d + 3, d + 6, mat[i], nullptr, &err)
+                : (err = "trt_add_prims: unknown primitive type", false);
+        if (!ok) return fail(TRT_ERR_INVALID, err);
+    }
+    return TRT_OK;
+}
+int trt_scene_num_prims(trt_scene* s, uint32_t* out) { if (!s || !out) return fail(TRT_ERR_INVALID, "trt_scene_num_prims: null argument"); *out = (uint32_t)s->host.prims.size(); return TRT_OK; }
+
+int trt_scene_commit(trt_scene* s, int bvh_kind) {
+    if (!s) return fail(TRT_ERR_INVALID, "trt_scene_commit: null scene");
+    std::string err;
+    if (!s->host.commit(bvh_kind, &err)) return fail(bvh_kind == 0 || bvh_kind == 1 ? TRT_ERR_UNSUPPORTED : TRT_ERR_INVALID, err);
+    return TRT_OK;
+}
+int trt_scene_leaf_ranks(trt_scene* s, uint32_t* rank) {
+    if (!s || !rank) return fail(TRT_ERR_INVALID, "trt_scene_leaf_ranks: null argument");
+    if (!s->host.committed) return fail(TRT_ERR_INVALID, "trt_scene_leaf_ranks: scene not committed");
+    std::memcpy(rank, s->host.leaf_rank.data(), s->host.leaf_rank.size() * sizeof(uint32_t));
+    return TRT_OK;
+}
+int trt_scene_bvh_info(trt_scene* s, uint32_t* n_nodes, uint32_t* max_depth, float* sah_cost) {
+    if (!s) return fail(TRT_ERR_INVALID, "trt_scene_bvh_info: null scene");
+    if (!s->host.committed) return fail(TRT_ERR_INVALID, "trt_scene_bvh_info: scene not committed");
+    if (n_nodes) *n_nodes = s->host.flat.n_nodes;
+    if (max_depth) *max_depth = s->host.flat.max_depth;
+    if (sah_cost) *sah_cost = s->host.flat.sah_cost;
+    return TRT_OK;
+}
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int trt_scene_upload(trt_ctx* c, trt_scene* s) {
+    if (!c || !s) return fail(TRT_ERR_INVALID, "trt_scene_upload: null argument");
+    if (!s->host.committed) return fail(TRT_ERR_INVALID, "trt_scene_upload: scene not committed (call trt_scene_commit)");
+    CU(cudaSetDevice(c->device));
+    DeviceCopy& dc = s->on_device[c->device];
+    if (dc.buf && dc.version == s->host.version) return TRT_OK;
+    const trt::FlatScene& f = s->host.flat;
+    size_t sz[6] = {f.nodes.size() * 16, f.spheres.size() * 16, f.quads.size() * 16, f.sphere_meta.size() * 16, f.quad_meta.size() * 16, f.materials.size() * 16};
+    const void* src[6] = {f.nodes.data(), f.spheres.data(), f.quads.data(), f.sphere_meta.data(), f.quad_meta.data(), f.materials.data()};
+    size_t off[6], total = 0;
+    for (int i = 0; i < 6; ++i) { off[i] = total; total += align_up(sz[i] ? sz[i] : 16); }
+    if (dc.buf && dc.bytes < total) { cudaFree(dc.buf); dc.buf = nullptr; }
+    if (!dc.buf) { CU(cudaMalloc(&dc.buf, total)); dc.bytes = total; }
+    for (int i = 0; i < 6; ++i) if (sz[i]) CU(cudaMemcpyAsync((char*)dc.buf + off[i], src[i], sz[i], cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    trtk::SceneView& v = dc.view;
+    char* b = (char*)dc.buf;
+    v.nodes = b + off[0]; v.spheres = b + off[1]; v.quads = b + off[2]; v.sphere_meta = b + off[3]; v.quad_meta = b + off[4]; v.materials = b + off[5];
+    v.root = f.root; v.n_nodes = f.n_nodes; v.n_spheres = (uint32_t)f.spheres.size(); v.n_quads = (uint32_t)f.quad_meta.size();
+    v.n_materials = (uint32_t)(f.materials.size() / 2); v.ordered = f.bvh_kind == TRT_BVH_SAH ? 1u : 0u;
+    const float inf = std::numeric_limits<float>::infinity();
+    for (int i = 0; i < 3; ++i) { v.root_min[i] = inf; v.root_max[i] = -inf; }
+    for (const trt::HostPrim& p : s->host.prims)
+        for (int i = 0; i < 3; ++i) { v.root_min[i] = fminf(v.root_min[i], p.bmin[i]); v.root_max[i] = fmaxf(v.root_max[i], p.bmax[i]); }
+    dc.version = s->host.version;
+    return TRT_OK;
+}
+
+// ------------------------------------------------------------------ camera (host only): Camera::new, camera.rs:17-56
+int trt_camera_make(float focus_distance, float defocus_angle, const float position[3], const float look_at[3],
+                    const float up[3], float vertical_fov, uint32_t width, uint32_t height, trt_camera* out) {
+    if (!position || !look_at || !up || !out) return fail(TRT_ERR_INVALID, "trt_camera_make: null argument");
+    if (width == 0 || height == 0) return fail(TRT_ERR_INVALID, "trt_camera_make: empty image");
+    const float rads_per_deg = 3.14159265358979323846f / 180.0f;             // f32::to_radians
+    float viewport_height = 2.0f * focus_distance * std::tan((vertical_fov * rads_per_deg) / 2.0f);
+    float aspect_ratio = (float)width / (float)height;
+    float viewport_width = aspect_ratio * viewport_height;
+    auto norm3 = [](const float v[3], float o[3]) { float l = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); o[0] = v[0] / l; o[1] = v[1] / l; o[2] = v[2] / l; };
+    auto cross3 = [](const float a[3], const float b[3], float o[3]) { o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0]; };
+    float pl[3] = {position[0] - look_at[0], position[1] - look_at[1], position[2] - look_at[2]};
+    float w[3], u[3], v[3], t[3];
+    norm3(pl, w); cross3(up, w, t); norm3(t, u); cross3(w, u, t); norm3(t, v);
+    float defocus_radius = focus_distance * std::tan((defocus_angle * rads_per_deg) / 2.0f);
+    for (int i = 0; i < 3; ++i) {
+        out->position[i] = position[i];
+        out->forward[i] = w[i] * focus_distance;
+        out->horizontal[i] = u[i] * viewport_width;
+        out->vertical[i] = v[i] * viewport_height;
+        out->viewport_upper_left[i] = position[i] - out->horizontal[i] / 2.0f + out->vertical[i] / 2.0f - out->forward[i];
+        out->defocus_disk_u[i] = u[i] * defocus_radius;
+        out->defocus_disk_v[i] = v[i] * defocus_radius;
+    }
+    out->width = width; out->height = height;
+    return TRT_OK;
+}
+
+// ------------------------------------------------------------------ rendering
+static int check_render_args(trt_ctx* c, trt_scene* s, const trt_camera* cam, const trt_params* p, const char* who) {
+    if (!c || !s || !cam || !p) return fail(TRT_ERR_INVALID, std::string(who) + ": null argument");
+    if (!s->host.committed) return fail(TRT_ERR_INVALID, std::string(who) + ": scene not committed (call trt_scene_commit)");
+    if (p->width != cam->width || p->height != cam->height) return fail(TRT_ERR_INVALID, std::string(who) + ": params and camera disagree on the image size");
+    if (p->width == 0 || p->height == 0) return fail(TRT_ERR_INVALID, std::string(who) + ": empty image");
+    if ((uint64_t)p->width * p->height > 0x7FFFFFFFull) return fail(TRT_ERR_INVALID, std::string(who) + ": image too large");
+    if (p->variant != TRT_VARIANT_MEGAKERNEL && p->variant != TRT_VARIANT_WAVEFRONT) return fail(TRT_ERR_INVALID, std::string(who) + ": unknown variant");
+    return TRT_OK;
+}
+
+static int render_into(trt_ctx* c, trt_scene* s, const trt_camera* cam, const trt_params* p, double* d_sum64, trt_stats* stats) {
+    int rc = trt_scene_upload(c, s); if (rc) return rc;
+    const trtk::SceneView& v = s->on_device[c->device].view;
+    if (p->variant == TRT_VARIANT_WAVEFRONT) return fail(TRT_ERR_UNSUPPORTED, "trt_render: wavefront variant not built yet");
+    CU(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long) + 64, c->stream));
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    CU(trtk::launch_render_mega(v, *cam, *p, d_sum64, c->d_counters, c->d_next_item, c->sm_count, c->stream));
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    if (stats) {
+        unsigned long long h[8];
+        CU(cudaMemcpyAsync(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        float ms = 0.f; CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+        stats->rays = h[0]; stats->paths = h[1]; stats->node_visits = h[2]; stats->sphere_tests = h[3]; stats->quad_tests = h[4];
+        stats->device_ms = ms; stats->launches = 1; stats->finalize_ms = 0.f; stats->reserved = 0;
+    }
+    return TRT_OK;
+}
+
+int trt_render_accumulate(trt_ctx* c, trt_scene* s, const trt_camera* cam, const trt_params* p, double* d_sum64, trt_stats* stats) {
+    int rc = check_render_args(c, s, cam, p, "trt_render_accumulate"); if (rc) return rc;
+    if (!d_sum64) return fail(TRT_ERR_INVALID, "trt_render_accumulate: d_sum64 is null");
+    CU(cudaSetDevice(c->device));
+    return render_into(c, s, cam, p, d_sum64, stats);
+}
+
+int trt_finalize(trt_ctx* c, const double* d_sum64, uint32_t width, uint32_t height, uint32_t spp_total, float* d_linear, uint8_t* d_rgb8, trt_stats* stats) {
+    if (!c || !d_sum64) return fail(TRT_ERR_INVALID, "trt_finalize: null argument");
+    if (spp_total == 0) return fail(TRT_ERR_INVALID, "trt_finalize: spp_total is zero");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->ev[2], c->stream));
+    CU(trtk::launch_finalize(d_sum64, (size_t)width * height * 3, spp_total, d_linear, d_rgb8, c->stream));
+    CU(cudaEventRecord(c->ev[3], c->stream));
+    if (stats) {
+        CU(cudaStreamSynchronize(c->stream));
+        float ms = 0.f; CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
+        stats->finalize_ms = ms; stats->launches += 1;
+    }
+    return TRT_OK;
+}
+
+int trt_render(trt_ctx* c, trt_scene* s, const trt_camera* cam, const trt_params* p, float* out_linear, uint8_t* out_rgb8, trt_stats* stats) {
+    int rc = check_render_args(c, s, cam, p, "trt_render"); if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    size_t n = (size_t)p->width * p->height * 3;
+    void *d_sum = nullptr, *d_lin = nullptr, *d_u8 = nullptr;
+    if ((rc = ensure_scratch(c, 0, n * sizeof(double), &d_sum))) return rc;
+    if ((rc = ensure_scratch(c, 1, n * sizeof(float), &d_lin))) return rc;
+    if ((rc = ensure_scratch(c, 2, n, &d_u8))) return rc;
+    CU(cudaMemsetAsync(d_sum, 0, n * sizeof(double), c->stream));
+    trt_stats st; std::memset(&st, 0, sizeof st);
+    if ((rc = render_into(c, s, cam, p, (double*)d_sum, &st))) return rc;
+    uint32_t spp_total = p->spp_total ? p->spp_total : p->spp;
+    if (spp_total == 0) spp_total = 1;
+    if ((rc = trt_finalize(c, (const double*)d_sum, p->width, p->height, spp_total, out_linear ? (float*)d_lin : nullptr, out_rgb8 ? (uint8_t*)d_u8 : nullptr, &st))) return rc;
+    if (out_linear) CU(cudaMemcpyAsync(out_linear, d_lin, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (out_rgb8) CU(cudaMemcpyAsync(out_rgb8, d_u8, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (stats) *stats = st;
+    return TRT_OK;
+}
+
+int trt_render_aov(trt_ctx* c, trt_scene* s, const trt_camera* cam, const trt_params* p, uint32_t* prim_id, float* t, float* radiance, uint32_t* n_rays) {
+    int rc = check_render_args(c, s, cam, p, "trt_render_aov"); if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    if ((rc = trt_scene_upload(c, s))) return rc;
+    const trtk::SceneView& v = s->on_device[c->device].view;
+    size_t n = (size_t)p->width * p->height * p->spp;
+    void *d_prim = nullptr, *d_t = nullptr, *d_rad = nullptr, *d_nr = nullptr;
+    if (prim_id && (rc = ensure_scratch(c, 0, n * 4, &d_prim))) return rc;
+    if (t && (rc = ensure_scratch(c, 1, n * 4, &d_t))) return rc;
+    if (radiance && (rc = ensure_scratch(c, 2, n * 12, &d_rad))) return rc;
+    if (n_rays && (rc = ensure_scratch(c, 3, n * 4, &d_nr))) return rc;
+    CU(trtk::launch_aov(v, *cam, *p, (uint32_t*)d_prim, (float*)d_t, (float*)d_rad, (uint32_t*)d_nr, c->stream));
+    if (prim_id) CU(cudaMemcpyAsync(prim_id, d_prim, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (t) CU(cudaMemcpyAsync(t, d_t, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (radiance) CU(cudaMemcpyAsync(radiance, d_rad, n * 12, cudaMemcpyDeviceToHost, c->stream));
+    if (n_rays) CU(cudaMemcpyAsync(n_rays, d_nr, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TRT_OK;
+}
+
+int trt_sample_batch(trt_ctx* c, trt_scene* s, const trt_sample_point* in, size_t n, const trt_params* p, trt_sampled_color* out) {
+    if (!c || !s || !p || (n && (!in || !out))) return fail(TRT_ERR_INVALID, "trt_sample_batch: null argument");
+    if (!s->host.committed) return fail(TRT_ERR_INVALID, "trt_sample_batch: scene not committed (call trt_scene_commit)");
+    static_assert(sizeof(trt_sample_point) == 32 && sizeof(trt_sampled_color) == 20, "wire structs must match the reference's repr(C) sizes");
+    CU(cudaSetDevice(c->device));
+    int rc; if ((rc = trt_scene_upload(c, s))) return rc;
+    const trtk::SceneView& v = s->on_device[c->device].view;
+    void *d_in = nullptr, *d_out = nullptr;
+    if ((rc = ensure_scratch(c, 0, n * sizeof(trt_sample_point), &d_in))) return rc;
+    if ((rc = ensure_scratch(c, 1, n * sizeof(trt_sampled_color), &d_out))) return rc;
+    if (n) CU(cudaMemcpyAsync(d_in, in, n * sizeof(trt_sample_point), cudaMemcpyHostToDevice, c->stream));
+    CU(trtk::launch_sample_batch(v, *p, (const trt_sample_point_pod*)d_in, n, (trt_sampled_color_pod*)d_out, c->stream));
+    if (n) CU(cudaMemcpyAsync(out, d_out, n * sizeof(trt_sampled_color), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TRT_OK;
+}
+
+int trt_trace_rays(trt_ctx* c, trt_scene* s, size_t n, const float* origins, const float* dirs, float t_min, uint32_t* prim_id, float* t) {
+    if (!c || !s || (n && (!origins || !dirs || !prim_id || !t))) return fail(TRT_ERR_INVALID, "trt_trace_rays: null argument");
+    if (!s->host.committed) return fail(TRT_ERR_INVALID, "trt_trace_rays: scene not committed (call trt_scene_commit)");
+    CU(cudaSetDevice(c->device));
+    int rc; if ((rc = trt_scene_upload(c, s))) return rc;
+    const trtk::SceneView& v = s->on_device[c->device].view;
+    void *d_o = nullptr, *d_d = nullptr, *d_p = nullptr, *d_t = nullptr;
+    if ((rc = ensure_scratch(c, 0, n * 12, &d_o))) return rc;
+    if ((rc = ensure_scratch(c, 1, n * 12, &d_d))) return rc;
+    if ((rc = ensure_scratch(c, 2, n * 4, &d_p))) return rc;
+    if ((rc = ensure_scratch(c, 3, n * 4, &d_t))) return rc;
+    if (n) { CU(cudaMemcpyAsync(d_o, origins, n * 12, cudaMemcpyHostToDevice, c->stream)); CU(cudaMemcpyAsync(d_d, dirs, n * 12, cudaMemcpyHostToDevice, c->stream)); }
+    CU(trtk::launch_trace(v, (const float*)d_o, (const float*)d_d, n, t_min, (uint32_t*)d_p, (float*)d_t, c->stream));
+    if (n) { CU(cudaMemcpyAsync(prim_id, d_p, n * 4, cudaMemcpyDeviceToHost, c->stream)); CU(cudaMemcpyAsync(t, d_t, n * 4, cudaMemcpyDeviceToHost, c->stream)); }
+    CU(cudaStreamSynchronize(c->stream));
+    return TRT_OK;
+}
+
+int trt_debug_math(trt_ctx* c, size_t n, const float* u, float* s, float* co, float* cb) {
+    if (!c || (n && (!u || !s || !co || !cb))) return fail(TRT_ERR_INVALID, "trt_debug_math: null argument");
+    CU(cudaSetDevice(c->device));
+    int rc; void* d[4];
+    for (int i = 0; i < 4; ++i) if ((rc = ensure_scratch(c, i, n * 4, &d[i]))) return rc;
+    if (n) CU(cudaMemcpyAsync(d[0], u, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(trtk::launch_debug_math(n, (const float*)d[0], (float*)d[1], (float*)d[2], (float*)d[3], c->stream));
+    if (n) {
+        CU(cudaMemcpyAsync(s, d[1], n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(co, d[2], n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(cb, d[3], n * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return TRT_OK;
+}
+int trt_debug_philox(trt_ctx* c, size_t n, const uint32_t* ctr, const uint32_t key[2], uint32_t* out) {
+    if (!c || !key || (n && (!ctr || !out))) return fail(TRT_ERR_INVALID, "trt_debug_philox: null argument");
+    CU(cudaSetDevice(c->device));
+    int rc; void *d_c = nullptr, *d_o = nullptr;
+    if ((rc = ensure_scratch(c, 0, n * 16, &d_c))) return rc;
+    if ((rc = ensure_scratch(c, 1, n * 16, &d_o))) return rc;
+    if (n) CU(cudaMemcpyAsync(d_c, ctr, n * 16, cudaMemcpyHostToDevice, c->stream));
+    CU(trtk::launch_debug_philox(n, (const uint32_t*)d_c, key[0], key[1], (uint32_t*)d_o, c->stream));
+    if (n) CU(cudaMemcpyAsync(out, d_o, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TRT_OK;
+}
+
+} // extern "C"

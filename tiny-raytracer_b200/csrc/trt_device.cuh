@@ -1,0 +1,392 @@
+// trt_device.cuh — device-side arithmetic of the path-tracing hot path for sm_100a.
+//
+// Numeric contract: every f32 operation below is a separately rounded IEEE-754 operation in the
+// order the reference performs it (Rust never contracts a*b+c). The translation unit is compiled with
+// -fmad=false -prec-div=true -prec-sqrt=true -ftz=false, so `*`,`+`,`/`,sqrtf are mul.rn/add.rn/div.rn/sqrt.rn.
+// Citations are file:line relative to /root/reference/raytracer/src.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "trt_layout.h"
+
+namespace trtd {
+
+#define TRT_DEV __device__ __forceinline__
+#define TRT_INF __int_as_float(0x7f800000)
+
+struct V3 { float x, y, z; };
+__host__ __device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+TRT_DEV V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }          // math/vec3.rs:70-76
+TRT_DEV V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }          // math/vec3.rs:86-92
+TRT_DEV V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
+TRT_DEV V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }             // math/vec3.rs:102-108
+TRT_DEV V3 operator*(float s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }             // math/vec3.rs:110-116
+TRT_DEV V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }          // math/vec3.rs:126-132
+TRT_DEV V3 operator/(V3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }             // math/vec3.rs:142-148
+TRT_DEV float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }               // math/vec3.rs:49-51
+TRT_DEV V3 cross(V3 a, V3 b) {                                                            // math/vec3.rs:53-59
+    return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+TRT_DEV V3 normalized(V3 a) { return a / sqrtf(dot(a, a)); }                              // math/vec3.rs:45-47
+TRT_DEV bool near_zero(V3 a) { const float e = 1e-7f; return fabsf(a.x) < e && fabsf(a.y) < e && fabsf(a.z) < e; } // math/vec3.rs:32-35
+TRT_DEV V3 reflect(V3 v, V3 n) { return v - (2.0f * dot(v, n)) * n; }                     // math/vec3extend.rs:75-77
+TRT_DEV V3 refract(V3 v, V3 n, float eta) {                                               // math/vec3extend.rs:79-84
+    float c = fminf(-dot(n, v), 1.0f);
+    V3 perp = eta * (v + n * c);
+    V3 par = (-sqrtf(fabsf(1.0f - dot(perp, perp)))) * n;
+    return par + perp;
+}
+TRT_DEV V3 ray_at(V3 o, V3 d, float t) { return o + t * d; }                              // ray.rs:24-26
+
+// ------------------------------------------------------------------ Philox4x32-10, key (seed), counter (pixel, sample, bounce, block)
+struct U4 { uint32_t x, y, z, w; };
+TRT_DEV U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    U4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3; return o;
+}
+// rand 0.8.5 UniformFloat<f32>: 23 mantissa bits -> [0,1)
+TRT_DEV float u01(uint32_t b) { return (float)(b >> 9) * 1.1920928955078125e-07f; }
+TRT_DEV float u11(uint32_t b) { return u01(b) * 2.0f + -1.0f; }   // random_range(-1.0..1.0): f*(hi-lo)+lo
+
+// ------------------------------------------------------------------ deterministic sin/cos(2*pi*u), cbrt
+TRT_DEV void det_sincos2pi(float u, float* s_out, float* c_out) {
+    float q = u * 8.0f;
+    int k = (int)q;
+    float f = q - (float)k;
+    float r = (k & 1) ? (1.0f - f) : f;
+    float x = r * 0.785398163397448309616f;
+    float z = x * x;
+    float sp = -1.9515295891e-4f * z;
+    sp = sp + 8.3321608736e-3f;
+    sp = sp * z;
+    sp = sp - 1.6666654611e-1f;
+    sp = sp * z;
+    sp = sp * x;
+    float s = sp + x;
+    float cp = 2.443315711809948e-5f * z;
+    cp = cp - 1.388731625493765e-3f;
+    cp = cp * z;
+    cp = cp + 4.166664568298827e-2f;
+    cp = cp * z;
+    cp = cp * z;
+    float hz = 0.5f * z;
+    cp = cp - hz;
+    float c = cp + 1.0f;
+    float ss = s, cc = c;
+    if ((k + 1) & 2) { ss = c; cc = s; }
+    if (k >= 4) ss = -ss;
+    if (k >= 2 && k <= 5) cc = -cc;
+    *s_out = ss; *c_out = cc;
+}
+TRT_DEV float det_cbrt(float x) {
+    if (!(x > 0.0f)) return 0.0f;
+    uint32_t b = __float_as_uint(x);
+    b = b / 3u + 709921077u;
+    float y = __uint_as_float(b);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float y2 = y * y;
+        float y3 = y2 * y;
+        float num = y3 - x;
+        float den = 3.0f * y2;
+        y = y - num / den;
+    }
+    return y;
+}
+// math/vec3extend.rs:15-30 with the contract's substitutions (cos(phi) = 1-2u2, sin(phi) = sqrt(1-cos^2))
+TRT_DEV V3 random_in_unit_sphere(float u1, float u2, float u3, bool use_r) {
+    float sin_t, cos_t;
+    det_sincos2pi(u1, &sin_t, &cos_t);
+    float cos_phi = 1.0f - 2.0f * u2;
+    float s2 = 1.0f - cos_phi * cos_phi;
+    float sin_phi = sqrtf(fmaxf(s2, 0.0f));
+    float r = use_r ? det_cbrt(u3) : 1.0f;
+    return mk(r * sin_phi * cos_t, r * sin_phi * sin_t, r * cos_phi);
+}
+
+// ------------------------------------------------------------------ scene access
+struct DevScene {
+    const float4* nodes; const float4* spheres; const float4* quads;
+    const uint4* sphere_meta; const uint4* quad_meta; const float4* materials;
+    uint32_t root, n_nodes, n_spheres, n_quads, n_materials, ordered;
+    float root_min[3], root_max[3];   // the root's own padded box (only consulted when counting events)
+};
+struct DevCamera { V3 position, upper_left, horizontal, vertical, du, dv; uint32_t width, height; };
+struct DevParams {
+    uint32_t width, height, spp, sample_offset, max_bounces;
+    float bg[3]; uint32_t seed_lo, seed_hi; float t_min;
+};
+
+// SMEM = scene staged in shared memory (small scenes): ld.shared.v4; otherwise read-only global path.
+template <bool SMEM> TRT_DEV float4 ld4(const float4* p) {
+    if (SMEM) {
+        float4 v; uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+        return v;
+    } else return __ldg(p);
+}
+template <bool SMEM> TRT_DEV uint4 ld4u(const uint4* p) {
+    if (SMEM) {
+        uint4 v; uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+        return v;
+    } else return __ldg(p);
+}
+
+struct EventCounters { uint32_t node_visits, sphere_tests, quad_tests; };
+
+// ------------------------------------------------------------------ AABB slab test, hittable/aabb.rs:36-61
+// Returns entry (`start`) and exit (`end`) of the range [t_min, +inf) clipped by the three slabs, updated with the
+// reference's exact compare/select sequence (NaN from 0*inf leaves the range untouched; swap only when t1 < t0).
+// The reference's early-outs `end <= start` after each axis are equivalent to one test at the end because start only
+// grows and end only shrinks; the caller combines it with the current closest hit: pass <=> min(hi, end) > start.
+TRT_DEV void slab(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, V3 o, V3 inv, float t_min,
+                  float* start_out, float* end_out) {
+    float start = t_min, end = TRT_INF;
+    {
+        float t0 = (mnx - o.x) * inv.x, t1 = (mxx - o.x) * inv.x;
+        if (t1 < t0) { float tmp = t0; t0 = t1; t1 = tmp; }
+        if (start < t0) start = t0;
+        if (t1 < end) end = t1;
+    }
+    {
+        float t0 = (mny - o.y) * inv.y, t1 = (mxy - o.y) * inv.y;
+        if (t1 < t0) { float tmp = t0; t0 = t1; t1 = tmp; }
+        if (start < t0) start = t0;
+        if (t1 < end) end = t1;
+    }
+    {
+        float t0 = (mnz - o.z) * inv.z, t1 = (mxz - o.z) * inv.z;
+        if (t1 < t0) { float tmp = t0; t0 = t1; t1 = tmp; }
+        if (start < t0) start = t0;
+        if (t1 < end) end = t1;
+    }
+    *start_out = start; *end_out = end;
+}
+
+// ------------------------------------------------------------------ primitives
+// Sphere::hit, hittable/sphere.rs:29-45. Returns t in [t_min, hi) or NaN-free "miss" as false.
+template <bool SMEM> TRT_DEV bool sphere_hit(const DevScene& S, uint32_t idx, V3 o, V3 d, float t_min, float hi, float* t_out) {
+    float4 s = ld4<SMEM>(S.spheres + idx);
+    V3 oc = o - mk(s.x, s.y, s.z);
+    float a = dot(d, d);
+    float half_b = dot(oc, d);
+    float c = dot(oc, oc) - s.w * s.w;
+    float disc = half_b * half_b - a * c;
+    if (disc < 0.0f) return false;
+    float sq = sqrtf(disc);
+    float t = (-half_b - sq) / a;
+    if (!(t_min <= t && t < hi)) {
+        t = (-half_b + sq) / a;
+        if (!(t_min <= t && t < hi)) return false;
+    }
+    *t_out = t; return true;
+}
+// Quad::hit, hittable/quad.rs:33-41
+template <bool SMEM> TRT_DEV bool quad_hit(const DevScene& S, uint32_t idx, V3 o, V3 d, float t_min, float hi, float* t_out) {
+    const float4* q = S.quads + 4 * (size_t)idx;
+    float4 q0 = ld4<SMEM>(q);
+    V3 n = mk(q0.x, q0.y, q0.z);
+    float dir_norm = dot(d, n);
+    float t = (q0.w - dot(o, n)) / dir_norm;
+    if (!(t_min <= t && t < hi)) return false;
+    float4 q1 = ld4<SMEM>(q + 1), q2 = ld4<SMEM>(q + 2), q3 = ld4<SMEM>(q + 3);
+    V3 p = ray_at(o, d, t) - mk(q1.x, q1.y, q1.z);
+    V3 w = mk(q1.w, q2.w, q3.w);
+    float px = dot(cross(p, mk(q3.x, q3.y, q3.z)), w);
+    float py = dot(cross(mk(q2.x, q2.y, q2.z), p), w);
+    if (!(0.0f <= px && px < 1.0f && 0.0f <= py && py < 1.0f)) return false;
+    *t_out = t; return true;
+}
+
+// ------------------------------------------------------------------ closest hit = BVH::hit / Node::hit, hittable/bvh.rs:25-27,88-107
+// ORDERED = false (TRT_BVH_REFERENCE): the tree has the reference's topology and is walked left-first. A deferred right
+//   child is re-checked against the closest hit found in the left subtree when it is popped — exactly the narrowed
+//   range `t_range.start..hit_record.t` of bvh.rs:97 — and a primitive is accepted only for t < closest (half-open
+//   range), so the leftmost leaf wins ties, as in the reference.
+// ORDERED = true (TRT_BVH_SAH): any topology, nearer child first. A subtree is culled only when its entry is beyond
+//   the closest hit; a primitive replaces the closest hit if its t is smaller, or equal with a smaller reference leaf
+//   rank (the reference's tie rule), so the result does not depend on the visiting order.
+struct Hit { float t; uint32_t ref; };
+
+template <bool ORDERED, bool SMEM, bool COUNT>
+TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
+    Hit best; best.t = TRT_INF; best.ref = TRT_REF_INVALID;
+    if (S.root == TRT_REF_INVALID) return best;
+    uint32_t best_rank = 0xFFFFFFFFu;
+    const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);   // aabb.rs:42, identical for every node of this ray
+    uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
+    int sp = 0;
+    uint32_t cur = S.root;
+    if (COUNT) {
+        ec->node_visits += 1;          // the root's own Node::hit call (bvh.rs:25-27); its box test is implied by the
+        float s0, e0;                  // children's tests, so it is only evaluated to keep the event counts faithful
+        slab(S.root_min[0], S.root_min[1], S.root_min[2], S.root_max[0], S.root_max[1], S.root_max[2], o, inv, t_min, &s0, &e0);
+        if (!(e0 > s0)) return best;
+    }
+
+    auto test_leaf = [&](uint32_t ref) {
+        uint32_t idx = ref & TRT_REF_INDEX_MASK;
+        float t; bool h;
+        if (ref & TRT_REF_QUAD) { if (COUNT) ec->quad_tests++; h = quad_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : best.t, &t); }
+        else { if (COUNT) ec->sphere_tests++; h = sphere_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : best.t, &t); }
+        if (!h) return;
+        if (ORDERED) {
+            if (t < best.t) { best.t = t; best.ref = ref; best_rank = 0xFFFFFFFFu; }
+            else if (t == best.t) {
+                if (best_rank == 0xFFFFFFFFu)
+                    best_rank = (best.ref & TRT_REF_QUAD) ? ld4u<SMEM>(S.quad_meta + (best.ref & TRT_REF_INDEX_MASK)).y
+                                                          : ld4u<SMEM>(S.sphere_meta + (best.ref & TRT_REF_INDEX_MASK)).y;
+                uint32_t rk = (ref & TRT_REF_QUAD) ? ld4u<SMEM>(S.quad_meta + idx).y : ld4u<SMEM>(S.sphere_meta + idx).y;
+                if (rk < best_rank) { best.ref = ref; best_rank = rk; }
+            }
+        } else { best.t = t; best.ref = ref; }
+    };
+
+    for (;;) {
+        const float4* np = S.nodes + 4 * (size_t)cur;
+        float4 n0 = ld4<SMEM>(np), n1 = ld4<SMEM>(np + 1), n2 = ld4<SMEM>(np + 2), n3 = ld4<SMEM>(np + 3);
+        uint32_t lref = __float_as_uint(n3.x), rref = __float_as_uint(n3.y);
+        float sl, el, sr, er;
+        slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, &sl, &el);
+        slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, &sr, &er);
+        if (COUNT) ec->node_visits += (rref == TRT_REF_INVALID) ? 0u : 2u;   // left.hit + right.hit of an interior node
+        uint32_t next = TRT_REF_INVALID;
+        if (!ORDERED) {
+            // left now, with the current closest hit as range end
+            if (el > sl && best.t > sl) { if (lref & TRT_REF_LEAF) test_leaf(lref); else next = lref; }
+            if (rref != TRT_REF_INVALID && er > sr) {
+                if (next == TRT_REF_INVALID) {               // left subtree finished: right is entered with the narrowed range
+                    if (best.t > sr) { if (rref & TRT_REF_LEAF) test_leaf(rref); else next = rref; }
+                } else { stack_ref[sp] = rref; stack_t[sp] = sr; ++sp; }
+            }
+        } else {
+            bool pl = el > sl && !(best.t < sl);
+            bool pr = rref != TRT_REF_INVALID && er > sr && !(best.t < sr);
+            // leaves are tested immediately (nearer first), interior children are ordered by entry distance
+            bool l_leaf = (lref & TRT_REF_LEAF) != 0, r_leaf = (rref & TRT_REF_LEAF) != 0;
+            if (pl && pr) {
+                bool left_first = !(sr < sl);
+                uint32_t a = left_first ? lref : rref, b = left_first ? rref : lref;
+                float sb = left_first ? sr : sl;
+                bool a_leaf = left_first ? l_leaf : r_leaf, b_leaf = left_first ? r_leaf : l_leaf;
+                if (a_leaf) test_leaf(a); else next = a;
+                if (b_leaf) { if (!(best.t < sb)) test_leaf(b); }
+                else if (next == TRT_REF_INVALID) { if (!(best.t < sb)) next = b; }
+                else { stack_ref[sp] = b; stack_t[sp] = sb; ++sp; }
+            } else if (pl) { if (l_leaf) test_leaf(lref); else next = lref; }
+            else if (pr) { if (r_leaf) test_leaf(rref); else next = rref; }
+        }
+        while (next == TRT_REF_INVALID && sp > 0) {
+            --sp;
+            uint32_t r = stack_ref[sp]; float s = stack_t[sp];
+            bool pass = ORDERED ? !(best.t < s) : (best.t > s);
+            if (!pass) continue;
+            if (r & TRT_REF_LEAF) test_leaf(r); else next = r;
+        }
+        if (next == TRT_REF_INVALID) break;
+        cur = next;
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------ camera: pointgen.rs:41-43 + camera.rs:58-66 + vec3extend.rs:45-53
+TRT_DEV void primary_ray(const DevCamera& C, const DevParams& P, uint32_t x, uint32_t y, uint32_t pixel, uint32_t sample, V3* o_out, V3* d_out) {
+    U4 r = philox4x32_10(pixel, sample, 0u, 0u, P.seed_lo, P.seed_hi);
+    float u = ((float)x + u01(r.x)) / (float)(C.width - 1);
+    float v = ((float)y + u01(r.y)) / (float)(C.height - 1);
+    float a = u11(r.z), b = u11(r.w);
+    uint32_t block = 1;
+    while (!(a * a + b * b + 0.0f * 0.0f < 1.0f)) {       // squared_length of (a, b, 0)
+        U4 e = philox4x32_10(pixel, sample, 0u, block++, P.seed_lo, P.seed_hi);
+        a = u11(e.x); b = u11(e.y);
+        if (!(a * a + b * b + 0.0f * 0.0f < 1.0f)) { a = u11(e.z); b = u11(e.w); }
+    }
+    V3 origin = C.position + a * C.du + b * C.dv;
+    V3 dir = C.upper_left + (u * C.horizontal) - (v * C.vertical) - origin;
+    *o_out = origin; *d_out = normalized(dir);           // Ray::new normalises, ray.rs:12-14
+}
+
+// ------------------------------------------------------------------ one hit: HitRecord::new (hittable/mod.rs:27-48) + emitted/scatter (material/*.rs)
+// Returns true if the path continues with (o, d) replaced by the scattered ray. `k` is the 1-based hit index (Philox bounce word).
+template <bool SMEM>
+TRT_DEV bool shade(const DevScene& S, const DevParams& P, Hit h, uint32_t pixel, uint32_t sample, uint32_t k,
+                   V3* o, V3* d, V3* atten, V3* color) {
+    uint32_t idx = h.ref & TRT_REF_INDEX_MASK;
+    V3 point = ray_at(*o, *d, h.t);
+    V3 outward; uint32_t mat;
+    if (h.ref & TRT_REF_QUAD) {
+        float4 q0 = ld4<SMEM>(S.quads + 4 * (size_t)idx);
+        outward = mk(q0.x, q0.y, q0.z);                                       // quad.rs:45: the unnormalised n
+        mat = ld4u<SMEM>(S.quad_meta + idx).x;
+    } else {
+        float4 s = ld4<SMEM>(S.spheres + idx);
+        outward = point - mk(s.x, s.y, s.z);                                  // sphere.rs:46-50
+        mat = ld4u<SMEM>(S.sphere_meta + idx).x;
+    }
+    bool front = dot(*d, outward) < 0.0f;
+    V3 nn = normalized(outward);
+    V3 normal = front ? nn : -nn;
+    float4 m0 = ld4<SMEM>(S.materials + 2 * (size_t)mat);
+    uint32_t kind = __float_as_uint(m0.w);
+    V3 rgb = mk(m0.x, m0.y, m0.z);
+    // cpu.rs:49-50: color += cumulated_attenuation * emitted().unwrap_or(0)
+    V3 emission = (kind == TRT_MAT_LIGHT) ? rgb : mk(0.0f, 0.0f, 0.0f);
+    *color = *color + (*atten) * emission;
+    if (kind == TRT_MAT_LIGHT) return false;                                  // light.rs:17-19
+    U4 r = philox4x32_10(pixel, sample, k, 0u, P.seed_lo, P.seed_hi);
+    V3 dir;
+    if (kind == TRT_MAT_LAMBERTIAN) {                                         // lambertian.rs:16-22
+        V3 uv = normalized(random_in_unit_sphere(u01(r.x), u01(r.y), u01(r.z), false));
+        dir = normal + uv;
+        if (near_zero(dir)) dir = normal;
+    } else if (kind == TRT_MAT_METAL) {                                       // metal.rs:18-25
+        float fuzz = ld4<SMEM>(S.materials + 2 * (size_t)mat + 1).x;
+        V3 reflected = reflect(*d, normal);
+        dir = reflected + fuzz * random_in_unit_sphere(u01(r.x), u01(r.y), u01(r.z), true);
+    } else {                                                                  // dielectric.rs:26-46
+        float ior = ld4<SMEM>(S.materials + 2 * (size_t)mat + 1).x;
+        float ri = front ? 1.0f / ior : ior;
+        float c = fminf(-dot(normal, *d), 1.0f);
+        float s = sqrtf(1.0f - c * c);
+        bool total_reflection = ri * s > 1.0f;
+        float sqrt_r0 = (1.0f - ri) / (1.0f + ri);
+        float r0 = sqrt_r0 * sqrt_r0;
+        float m = 1.0f - c;
+        float m2 = m * m;
+        float m5 = (m2 * m2) * m;
+        float reflectance = r0 + (1.0f - r0) * m5;
+        dir = (total_reflection || reflectance > u01(r.x)) ? reflect(*d, normal) : refract(*d, normal, ri);
+    }
+    *atten = (*atten) * rgb;                                                  // cpu.rs:52
+    *o = point; *d = normalized(dir);                                         // Ray::new, ray.rs:12-14
+    return true;
+}
+
+// One whole path: CpuSampler::single_point_sampling, renderer/sampler/cpu.rs:39-65
+template <bool ORDERED, bool SMEM, bool COUNT>
+TRT_DEV V3 trace_path(const DevScene& S, const DevParams& P, V3 o, V3 d, uint32_t pixel, uint32_t sample,
+                      uint32_t* n_rays_out, Hit* first_hit, EventCounters* ec) {
+    V3 color = mk(0.f, 0.f, 0.f), atten = mk(1.f, 1.f, 1.f);
+    uint32_t remain = P.max_bounces, k = 0, rays = 0;
+    while (remain > 0) {
+        Hit h = closest_hit<ORDERED, SMEM, COUNT>(S, o, d, P.t_min, ec);
+        ++rays;
+        if (rays == 1 && first_hit) *first_hit = h;
+        if (h.ref == TRT_REF_INVALID) { color = color + atten * mk(P.bg[0], P.bg[1], P.bg[2]); break; }   // cpu.rs:58-61
+        ++k;
+        if (!shade<SMEM>(S, P, h, pixel, sample, k, &o, &d, &atten, &color)) break;
+        --remain;
+    }
+    if (n_rays_out) *n_rays_out = rays;
+    return color;
+}
+
+} // namespace trtd

@@ -1,0 +1,355 @@
+// trt_kernels.cu — sm_100a kernels of the path-tracing hot path and their launchers.
+//
+//   k_render_mega   persistent-thread megakernel: every lane owns a work item (pixel, sample chunk), runs
+//                   generate -> [closest_hit -> shade]* for one path after another (path regeneration per lane),
+//                   keeps the chunk's f64 sum in registers and adds it to the per-pixel accumulator once.
+//   k_aov           one thread per (pixel, sample): primary-hit AOV (+ optional whole-path radiance / ray count)
+//   k_sample_batch  the reference's Sampler trait on a batch of caller-supplied rays
+//   k_trace         closest hit for arbitrary rays
+//   k_finalize      normalise + gamma 2.2 + 8-bit quantise (imager.rs:35-60, utils/image.rs:92-111)
+//   k_debug_*       device evaluation of the numeric contract for unit parity tests
+#include "trt_device.cuh"
+#include "trt_kernels.h"
+#include <cstdio>
+
+using namespace trtd;
+
+// ------------------------------------------------------------------ shared-memory staging of small scenes
+struct SmemPlan { uint32_t nodes_f4, spheres_f4, quads_f4, smeta_u4, qmeta_u4, mats_f4; };
+
+template <bool SMEM>
+__device__ __forceinline__ DevScene stage_scene(const DevScene& G) {
+    if (!SMEM) return G;
+    extern __shared__ float4 smem_f4[];
+    DevScene S = G;
+    uint32_t off = 0;
+    auto copy = [&](const float4* src, uint32_t n) -> const float4* {
+        float4* dst = smem_f4 + off;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        off += n;
+        return dst;
+    };
+    S.nodes = copy(G.nodes, 4 * G.n_nodes);
+    S.spheres = copy(G.spheres, G.n_spheres);
+    S.quads = copy(G.quads, 4 * G.n_quads);
+    S.sphere_meta = (const uint4*)copy((const float4*)G.sphere_meta, G.n_spheres);
+    S.quad_meta = (const uint4*)copy((const float4*)G.quad_meta, G.n_quads);
+    S.materials = copy(G.materials, 2 * G.n_materials);
+    __syncthreads();
+    return S;
+}
+
+// ------------------------------------------------------------------ megakernel
+struct MegaArgs {
+    DevScene scene; DevCamera cam; DevParams p;
+    double* sum64;                 // [H*W*3]
+    unsigned long long* counters;  // [0] rays [1] paths [2] node_visits [3] sphere_tests [4] quad_tests
+    unsigned int* next_item;       // work counter
+    uint32_t chunk, n_chunks, tiles_x, tiles_y, n_items;
+};
+
+// item -> (pixel, sample range). Items are ordered chunk-major over 8x4 pixel tiles, 32 consecutive items = one tile.
+__device__ __forceinline__ bool decode_item(const MegaArgs& A, uint32_t item, uint32_t* x, uint32_t* y, uint32_t* s0, uint32_t* s1) {
+    uint32_t lane = item & 31u, t = item >> 5;
+    uint32_t n_tiles = A.tiles_x * A.tiles_y;
+    uint32_t chunk = t / n_tiles, tile = t - chunk * n_tiles;
+    uint32_t ty = tile / A.tiles_x, tx = tile - ty * A.tiles_x;
+    *x = tx * 8 + (lane & 7u); *y = ty * 4 + (lane >> 3);
+    *s0 = chunk * A.chunk; uint32_t e = *s0 + A.chunk; *s1 = e < A.p.spp ? e : A.p.spp;
+    return *x < A.p.width && *y < A.p.height;
+}
+
+template <bool ORDERED, bool SMEM, bool COUNT>
+__global__ void __launch_bounds__(256, 2) k_render_mega(const MegaArgs A) {
+    const DevScene S = stage_scene<SMEM>(A.scene);
+    const DevParams& P = A.p;
+    const uint32_t lane = threadIdx.x & 31u;
+    // per-lane path state
+    V3 o = mk(0, 0, 0), d = mk(0, 0, 1), atten = mk(1, 1, 1), color = mk(0, 0, 0);
+    uint32_t pixel = 0, px = 0, py = 0, s_cur = 0, s_end = 0, remain = 0, k = 0;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    bool alive = false, done = false, has_item = false;
+    uint32_t n_rays = 0, n_paths = 0;
+    EventCounters ec; ec.node_visits = ec.sphere_tests = ec.quad_tests = 0;
+
+    for (;;) {
+        // ---- work fetch for lanes whose chunk is finished (warp-aggregated atomic)
+        bool need_item = !alive && !done && s_cur == s_end;
+        unsigned m = __ballot_sync(0xFFFFFFFFu, need_item);
+        if (m) {
+            if (need_item && has_item) {
+                double* dst = A.sum64 + 3 * (size_t)pixel;
+                if (A.n_chunks == 1) { dst[0] += acc0; dst[1] += acc1; dst[2] += acc2; }   // pixel owned by this lane alone
+                else { atomicAdd(dst, acc0); atomicAdd(dst + 1, acc1); atomicAdd(dst + 2, acc2); }
+                has_item = false;
+            }
+            int leader = __ffs(m) - 1;
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(A.next_item, (unsigned)__popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (need_item) {
+                uint32_t item = base + __popc(m & ((1u << lane) - 1u));
+                if (item < A.n_items) {
+                    uint32_t s0, s1;
+                    if (decode_item(A, item, &px, &py, &s0, &s1)) {
+                        pixel = py * P.width + px; s_cur = s0; s_end = s1; has_item = true;
+                        acc0 = acc1 = acc2 = 0.0;
+                    }   // else: padding item outside the image, fetch again next round
+                } else done = true;
+            }
+        }
+        // ---- path regeneration: pointgen.rs:37-52
+        if (!alive && !done && s_cur < s_end) {
+            primary_ray(A.cam, P, px, py, pixel, P.sample_offset + s_cur, &o, &d);
+            atten = mk(1, 1, 1); color = mk(0, 0, 0); remain = P.max_bounces; k = 0;
+            alive = remain > 0;
+            if (!alive) { ++s_cur; ++n_paths; }      // max_bounces == 0: the path contributes nothing
+        }
+        if (__all_sync(0xFFFFFFFFu, done)) break;
+        // ---- one ray segment: cpu.rs:47-62
+        if (alive) {
+            Hit h = closest_hit<ORDERED, SMEM, COUNT>(S, o, d, P.t_min, &ec);
+            ++n_rays;
+            bool cont;
+            if (h.ref == TRT_REF_INVALID) { color = color + atten * mk(P.bg[0], P.bg[1], P.bg[2]); cont = false; }
+            else { ++k; cont = shade<SMEM>(S, P, h, pixel, P.sample_offset + s_cur, k, &o, &d, &atten, &color); if (cont) { --remain; cont = remain > 0; } }
+            if (!cont) {
+                acc0 += (double)color.x; acc1 += (double)color.y; acc2 += (double)color.z;
+                alive = false; ++s_cur; ++n_paths;
+            }
+        }
+    }
+    // ---- statistics: one atomic per warp
+    unsigned long long r = n_rays, pth = n_paths;
+    for (int off = 16; off; off >>= 1) { r += __shfl_xor_sync(0xFFFFFFFFu, r, off); pth += __shfl_xor_sync(0xFFFFFFFFu, pth, off); }
+    if (lane == 0) { atomicAdd(A.counters, r); atomicAdd(A.counters + 1, pth); }
+    if (COUNT) {
+        unsigned long long a = ec.node_visits, b = ec.sphere_tests, c = ec.quad_tests;
+        for (int off = 16; off; off >>= 1) { a += __shfl_xor_sync(0xFFFFFFFFu, a, off); b += __shfl_xor_sync(0xFFFFFFFFu, b, off); c += __shfl_xor_sync(0xFFFFFFFFu, c, off); }
+        if (lane == 0) { atomicAdd(A.counters + 2, a); atomicAdd(A.counters + 3, b); atomicAdd(A.counters + 4, c); }
+    }
+}
+
+// ------------------------------------------------------------------ AOV / sample batch / trace
+struct AovArgs {
+    DevScene scene; DevCamera cam; DevParams p;
+    uint32_t* prim_id; float* t; float* radiance; uint32_t* n_rays;
+    unsigned long long total;   // W*H*spp
+};
+template <bool ORDERED>
+__global__ void __launch_bounds__(128) k_aov(const AovArgs A) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.total) return;
+    const DevScene& S = A.scene; const DevParams& P = A.p;
+    uint32_t pixel = (uint32_t)(i / P.spp), si = (uint32_t)(i - (unsigned long long)pixel * P.spp);
+    uint32_t y = pixel / P.width, x = pixel - y * P.width, sample = P.sample_offset + si;
+    V3 o, d;
+    primary_ray(A.cam, P, x, y, pixel, sample, &o, &d);
+    DevParams Q = P;
+    if (!A.radiance && !A.n_rays) Q.max_bounces = P.max_bounces ? 1u : 0u;
+    Hit first; first.t = TRT_INF; first.ref = TRT_REF_INVALID;
+    uint32_t nr = 0; EventCounters ec;
+    V3 col = trace_path<ORDERED, false, false>(S, Q, o, d, pixel, sample, &nr, &first, &ec);
+    if (A.prim_id) {
+        uint32_t id = 0xFFFFFFFFu;
+        if (first.ref != TRT_REF_INVALID) {
+            uint32_t idx = first.ref & TRT_REF_INDEX_MASK;
+            id = (first.ref & TRT_REF_QUAD) ? S.quad_meta[idx].z : S.sphere_meta[idx].z;
+        }
+        A.prim_id[i] = id;
+    }
+    if (A.t) A.t[i] = first.t;
+    if (A.radiance) { A.radiance[3 * i] = col.x; A.radiance[3 * i + 1] = col.y; A.radiance[3 * i + 2] = col.z; }
+    if (A.n_rays) A.n_rays[i] = nr;
+}
+
+struct BatchArgs { DevScene scene; DevParams p; const trt_sample_point_pod* in; trt_sampled_color_pod* out; unsigned long long n; };
+template <bool ORDERED>
+__global__ void __launch_bounds__(128) k_sample_batch(const BatchArgs A) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    trt_sample_point_pod sp = A.in[i];
+    uint32_t pixel = sp.y * A.p.width + sp.x;
+    EventCounters ec;
+    V3 col = trace_path<ORDERED, false, false>(A.scene, A.p, mk(sp.o[0], sp.o[1], sp.o[2]), mk(sp.d[0], sp.d[1], sp.d[2]), pixel,
+                                               A.p.sample_offset + (uint32_t)i, nullptr, nullptr, &ec);
+    trt_sampled_color_pod c; c.x = sp.x; c.y = sp.y; c.c[0] = col.x; c.c[1] = col.y; c.c[2] = col.z;
+    A.out[i] = c;
+}
+
+struct TraceArgs { DevScene scene; const float* o; const float* d; float t_min; uint32_t* prim_id; float* t; unsigned long long n; };
+template <bool ORDERED>
+__global__ void __launch_bounds__(128) k_trace(const TraceArgs A) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    EventCounters ec;
+    Hit h = closest_hit<ORDERED, false, false>(A.scene, mk(A.o[3 * i], A.o[3 * i + 1], A.o[3 * i + 2]),
+                                               mk(A.d[3 * i], A.d[3 * i + 1], A.d[3 * i + 2]), A.t_min, &ec);
+    uint32_t id = 0xFFFFFFFFu;
+    if (h.ref != TRT_REF_INVALID) {
+        uint32_t idx = h.ref & TRT_REF_INDEX_MASK;
+        id = (h.ref & TRT_REF_QUAD) ? A.scene.quad_meta[idx].z : A.scene.sphere_meta[idx].z;
+    }
+    A.prim_id[i] = id; A.t[i] = h.t;
+}
+
+// ------------------------------------------------------------------ epilogue
+__global__ void __launch_bounds__(256) k_finalize(const double* __restrict__ sum64, size_t n, double inv_spp,
+                                                  float* __restrict__ linear, uint8_t* __restrict__ rgb8) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float lin = (float)(sum64[i] * inv_spp);
+    if (linear) linear[i] = lin;
+    if (rgb8) {
+        float g = powf(lin, 1.0f / 2.2f);                       // Color::gamma_correction, utils/image.rs:92-98
+        float cl = g < 0.0f ? 0.0f : (g > 0.999f ? 0.999f : g);  // clamp(0, 0.999), NaN stays NaN
+        float s = cl * 255.0f;
+        rgb8[i] = (s == s) ? (uint8_t)s : (uint8_t)0;            // `as u8`: truncation, NaN -> 0
+    }
+}
+
+__global__ void k_debug_math(size_t n, const float* u, float* s, float* c, float* cb) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float ss, cc; det_sincos2pi(u[i], &ss, &cc);
+    s[i] = ss; c[i] = cc; cb[i] = det_cbrt(u[i]);
+}
+__global__ void k_debug_philox(size_t n, const uint32_t* ctr, uint32_t k0, uint32_t k1, uint32_t* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    U4 r = philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], k0, k1);
+    out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+}
+
+// ------------------------------------------------------------------ launchers
+namespace trtk {
+
+static DevScene dev_scene(const SceneView& v) {
+    DevScene s;
+    s.nodes = (const float4*)v.nodes; s.spheres = (const float4*)v.spheres; s.quads = (const float4*)v.quads;
+    s.sphere_meta = (const uint4*)v.sphere_meta; s.quad_meta = (const uint4*)v.quad_meta; s.materials = (const float4*)v.materials;
+    s.root = v.root; s.n_nodes = v.n_nodes; s.n_spheres = v.n_spheres; s.n_quads = v.n_quads; s.n_materials = v.n_materials;
+    s.ordered = v.ordered;
+    for (int i = 0; i < 3; ++i) { s.root_min[i] = v.root_min[i]; s.root_max[i] = v.root_max[i]; }
+    return s;
+}
+static DevCamera dev_camera(const trt_camera& c) {
+    DevCamera d;
+    d.position = mk(c.position[0], c.position[1], c.position[2]);
+    d.upper_left = mk(c.viewport_upper_left[0], c.viewport_upper_left[1], c.viewport_upper_left[2]);
+    d.horizontal = mk(c.horizontal[0], c.horizontal[1], c.horizontal[2]);
+    d.vertical = mk(c.vertical[0], c.vertical[1], c.vertical[2]);
+    d.du = mk(c.defocus_disk_u[0], c.defocus_disk_u[1], c.defocus_disk_u[2]);
+    d.dv = mk(c.defocus_disk_v[0], c.defocus_disk_v[1], c.defocus_disk_v[2]);
+    d.width = c.width; d.height = c.height;
+    return d;
+}
+static DevParams dev_params(const trt_params& p) {
+    DevParams d;
+    d.width = p.width; d.height = p.height; d.spp = p.spp; d.sample_offset = p.sample_offset; d.max_bounces = p.max_bounces;
+    d.bg[0] = p.background[0]; d.bg[1] = p.background[1]; d.bg[2] = p.background[2];
+    d.seed_lo = (uint32_t)p.seed; d.seed_hi = (uint32_t)(p.seed >> 32); d.t_min = p.t_min;
+    return d;
+}
+
+size_t scene_smem_bytes(const SceneView& v) {
+    return 16ull * (4ull * v.n_nodes + v.n_spheres + 4ull * v.n_quads + v.n_spheres + v.n_quads + 2ull * v.n_materials);
+}
+
+template <bool ORDERED, bool SMEM, bool COUNT>
+static cudaError_t launch_mega_t(const MegaArgs& A, int grid, size_t smem, cudaStream_t st) {
+    auto kern = k_render_mega<ORDERED, SMEM, COUNT>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<grid, 256, smem, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const trt_params& p, double* d_sum64,
+                               unsigned long long* d_counters, unsigned int* d_next_item, int sm_count, cudaStream_t st) {
+    MegaArgs A;
+    A.scene = dev_scene(v); A.cam = dev_camera(cam); A.p = dev_params(p);
+    A.sum64 = d_sum64; A.counters = d_counters; A.next_item = d_next_item;
+    const int blocks_per_sm = 2, threads = 256;
+    int grid = sm_count * blocks_per_sm;
+    uint64_t resident = (uint64_t)grid * threads;
+    uint64_t pixels = (uint64_t)p.width * p.height;
+    // chunk of samples per work item: whole pixels when there are plenty of them, otherwise split so that the
+    // persistent lanes see >= ~8 items each (tail balance); never below 4 samples per item.
+    uint32_t chunk = p.spp ? p.spp : 1;
+    if (pixels < 8 * resident) {
+        uint64_t want_chunks = (8 * resident + pixels - 1) / (pixels ? pixels : 1);
+        uint64_t c = (p.spp + want_chunks - 1) / want_chunks;
+        if (c < 4) c = 4;
+        if (c < chunk) chunk = (uint32_t)c;
+    }
+    A.chunk = chunk; A.n_chunks = p.spp ? (p.spp + chunk - 1) / chunk : 0;
+    A.tiles_x = (p.width + 7) / 8; A.tiles_y = (p.height + 3) / 4;
+    uint64_t n_items = (uint64_t)A.tiles_x * A.tiles_y * 32ull * A.n_chunks;
+    if (n_items > 0xFFFFFFF0ull - resident) return cudaErrorInvalidValue;
+    A.n_items = (uint32_t)n_items;
+    size_t smem = scene_smem_bytes(v);
+    bool use_smem = smem <= 64 * 1024;
+    bool count = (p.flags & 1u) != 0, ordered = v.ordered != 0;
+#define TRT_DISPATCH(O, S, C) return launch_mega_t<O, S, C>(A, grid, (S) ? smem : 0, st)
+    if (ordered) { if (use_smem) { if (count) TRT_DISPATCH(true, true, true); else TRT_DISPATCH(true, true, false); }
+                   else { if (count) TRT_DISPATCH(true, false, true); else TRT_DISPATCH(true, false, false); } }
+    else { if (use_smem) { if (count) TRT_DISPATCH(false, true, true); else TRT_DISPATCH(false, true, false); }
+           else { if (count) TRT_DISPATCH(false, false, true); else TRT_DISPATCH(false, false, false); } }
+#undef TRT_DISPATCH
+}
+
+cudaError_t launch_aov(const SceneView& v, const trt_camera& cam, const trt_params& p, uint32_t* d_prim, float* d_t,
+                       float* d_rad, uint32_t* d_nrays, cudaStream_t st) {
+    AovArgs A; A.scene = dev_scene(v); A.cam = dev_camera(cam); A.p = dev_params(p);
+    A.prim_id = d_prim; A.t = d_t; A.radiance = d_rad; A.n_rays = d_nrays;
+    A.total = (unsigned long long)p.width * p.height * p.spp;
+    if (A.total == 0) return cudaSuccess;
+    unsigned long long blocks = (A.total + 127) / 128;
+    if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+    if (v.ordered) k_aov<true><<<(unsigned)blocks, 128, 0, st>>>(A); else k_aov<false><<<(unsigned)blocks, 128, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sample_batch(const SceneView& v, const trt_params& p, const trt_sample_point_pod* d_in, size_t n,
+                                trt_sampled_color_pod* d_out, cudaStream_t st) {
+    BatchArgs A; A.scene = dev_scene(v); A.p = dev_params(p); A.in = d_in; A.out = d_out; A.n = n;
+    if (n == 0) return cudaSuccess;
+    unsigned long long blocks = (n + 127) / 128;
+    if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+    if (v.ordered) k_sample_batch<true><<<(unsigned)blocks, 128, 0, st>>>(A); else k_sample_batch<false><<<(unsigned)blocks, 128, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace(const SceneView& v, const float* d_o, const float* d_d, size_t n, float t_min, uint32_t* d_prim,
+                         float* d_t, cudaStream_t st) {
+    TraceArgs A; A.scene = dev_scene(v); A.o = d_o; A.d = d_d; A.t_min = t_min; A.prim_id = d_prim; A.t = d_t; A.n = n;
+    if (n == 0) return cudaSuccess;
+    unsigned long long blocks = (n + 127) / 128;
+    if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+    if (v.ordered) k_trace<true><<<(unsigned)blocks, 128, 0, st>>>(A); else k_trace<false><<<(unsigned)blocks, 128, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(const double* d_sum64, size_t n_values, uint32_t spp_total, float* d_linear, uint8_t* d_rgb8, cudaStream_t st) {
+    if (n_values == 0) return cudaSuccess;
+    double inv = 1.0 / (double)spp_total;
+    size_t blocks = (n_values + 255) / 256;
+    k_finalize<<<(unsigned)blocks, 256, 0, st>>>(d_sum64, n_values, inv, d_linear, d_rgb8);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_debug_math(size_t n, const float* u, float* s, float* c, float* cb, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_debug_math<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, u, s, c, cb);
+    return cudaGetLastError();
+}
+cudaError_t launch_debug_philox(size_t n, const uint32_t* ctr, uint32_t k0, uint32_t k1, uint32_t* out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_debug_philox<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, ctr, k0, k1, out);
+    return cudaGetLastError();
+}
+
+} // namespace trtk

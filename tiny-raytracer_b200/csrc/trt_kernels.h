@@ -1,0 +1,33 @@
+// trt_kernels.h — host-callable launchers of trt_kernels.cu (all pointers are DEVICE pointers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "../../include/trt.h"
+
+struct trt_sample_point_pod { uint32_t x, y; float o[3], d[3]; };   // == trt_sample_point
+struct trt_sampled_color_pod { uint32_t x, y; float c[3]; };        // == trt_sampled_color
+
+namespace trtk {
+
+struct SceneView {   // device copy of trt::FlatScene
+    const void* nodes; const void* spheres; const void* quads; const void* sphere_meta; const void* quad_meta; const void* materials;
+    uint32_t root, n_nodes, n_spheres, n_quads, n_materials, ordered;
+    float root_min[3], root_max[3];
+};
+
+size_t scene_smem_bytes(const SceneView& v);
+
+cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const trt_params& p, double* d_sum64,
+                               unsigned long long* d_counters, unsigned int* d_next_item, int sm_count, cudaStream_t st);
+cudaError_t launch_aov(const SceneView& v, const trt_camera& cam, const trt_params& p, uint32_t* d_prim, float* d_t,
+                       float* d_rad, uint32_t* d_nrays, cudaStream_t st);
+cudaError_t launch_sample_batch(const SceneView& v, const trt_params& p, const trt_sample_point_pod* d_in, size_t n,
+                                trt_sampled_color_pod* d_out, cudaStream_t st);
+cudaError_t launch_trace(const SceneView& v, const float* d_o, const float* d_d, size_t n, float t_min, uint32_t* d_prim,
+                         float* d_t, cudaStream_t st);
+cudaError_t launch_finalize(const double* d_sum64, size_t n_values, uint32_t spp_total, float* d_linear, uint8_t* d_rgb8, cudaStream_t st);
+cudaError_t launch_debug_math(size_t n, const float* u, float* s, float* c, float* cb, cudaStream_t st);
+cudaError_t launch_debug_philox(size_t n, const uint32_t* ctr, uint32_t k0, uint32_t k1, uint32_t* out, cudaStream_t st);
+
+} // namespace trtk

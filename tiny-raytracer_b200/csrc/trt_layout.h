@@ -1,0 +1,38 @@
+// trt_layout.h — HBM data layout shared by the host flattener (trt_scene.cpp) and the kernels (trt_kernels.cu).
+//
+// Everything is 16-byte-vector addressable; a node is one 64-byte record (four float4) so that one visited interior
+// node costs four 128-bit loads from one 64-byte-aligned segment (half a 128-byte line):
+//
+//   node n (float4 nodes[4n .. 4n+3]):
+//     [0] = ( lmin.x, lmin.y, lmin.z, lmax.x )      left child's padded AABB  (hittable/aabb.rs:5-10 is 24 B {min,max})
+//     [1] = ( lmax.y, lmax.z, rmin.x, rmin.y )
+//     [2] = ( rmin.z, rmax.x, rmax.y, rmax.z )      right child's padded AABB
+//     [3] = ( left_ref, right_ref, 0, 0 ) as bits
+//   child ref: bit31 = leaf, bit30 = primitive type (0 sphere, 1 quad), bits0..29 = index into that type's array;
+//              otherwise the index of an interior node; TRT_REF_INVALID = absent child (single-primitive scene).
+//   With one primitive per leaf the child box stored in the parent IS the primitive's own padded box, i.e. the box the
+//   reference tests in the leaf's Node::hit (hittable/bvh.rs:89) — no extra per-primitive box fetch.
+//
+//   sphere i : float4 spheres[i]      = ( center.xyz, radius )                                    16 B (hittable/sphere.rs:8-13)
+//   quad i   : float4 quads[4i..4i+3] = ( n.xyz, d ), ( corner.xyz, w.x ), ( u.xyz, w.y ), ( v.xyz, w.z )   64 B (hittable/quad.rs:8-17)
+//              the plane test needs only the first 16 B; the rest is fetched when t is in range.
+//   meta     : uint4 sphere_meta[i] / quad_meta[i] = ( material_id, reference_leaf_rank, prim_id, 0 ), read for the final hit
+//              (and on exact-t ties in SAH mode).
+//   material m: float4 materials[2m] = ( rgb, kind as bits ), materials[2m+1] = ( fuzz | refraction_index, 0, 0, 0 )   32 B
+#pragma once
+#include <stdint.h>
+
+#define TRT_REF_INVALID 0x7FFFFFFFu
+#define TRT_REF_LEAF 0x80000000u
+#define TRT_REF_QUAD 0x40000000u
+#define TRT_REF_INDEX_MASK 0x3FFFFFFFu
+
+#define TRT_MAT_LAMBERTIAN 0u
+#define TRT_MAT_METAL 1u
+#define TRT_MAT_DIELECTRIC 2u
+#define TRT_MAT_LIGHT 3u
+
+#define TRT_MAX_STACK 64   /* traversal stack entries; trt_scene_commit rejects deeper trees */
+
+struct trt_f4 { float x, y, z, w; };
+struct trt_u4 { uint32_t x, y, z, w; };

@@ -1,0 +1,335 @@
+// trt_scene.cpp — World registry, BVH builders (reference-topology and binned SAH) and the HBM flattener.
+// Host arithmetic that defines geometry (padded boxes, quad n/w/d) follows the reference operation for operation and
+// is compiled without FMA contraction, because the kernels cull with exactly these numbers.
+#include "trt_scene.hpp"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <future>
+#include <limits>
+
+namespace trt {
+
+// ------------------------------------------------------------------ primitives
+static inline void padded_box(const float a[3], const float b[3], float mn[3], float mx[3]) {
+    // AABB::new, hittable/aabb.rs:13-20: PADDING_AMOUNT / 2.0 on each side
+    const float pad = 0.0001f / 2.0f;
+    for (int i = 0; i < 3; ++i) { mn[i] = fminf(a[i], b[i]) - pad; mx[i] = fmaxf(a[i], b[i]) + pad; }
+}
+
+uint32_t HostScene::add_material(uint32_t kind, const float rgb[3], float param) {
+    HostMaterial m; m.kind = kind; m.rgb[0] = rgb[0]; m.rgb[1] = rgb[1]; m.rgb[2] = rgb[2]; m.param = param;
+    if (kind == TRT_MAT_METAL) m.param = param < 0.f ? 0.f : (param > 1.f ? 1.f : param);   // material/metal.rs:13
+    materials.push_back(m); committed = false;
+    return (uint32_t)materials.size() - 1;
+}
+
+bool HostScene::add_sphere(const float c[3], float r, uint32_t mat, uint32_t* id, std::string* err) {
+    if (mat >= materials.size()) { *err = "trt_add_sphere: unknown material id"; return false; }
+    if (prims.size() >= TRT_REF_INDEX_MASK) { *err = "trt_add_sphere: too many primitives"; return false; }
+    HostPrim p; std::memset(&p, 0, sizeof p);
+    p.type = 0; p.mat = mat; p.r = r;
+    float lo[3], hi[3];
+    for (int i = 0; i < 3; ++i) { p.a[i] = c[i]; lo[i] = c[i] - r; hi[i] = c[i] + r; }        // hittable/sphere.rs:17-18
+    padded_box(lo, hi, p.bmin, p.bmax);
+    if (id) *id = (uint32_t)prims.size();
+    prims.push_back(p); committed = false;
+    return true;
+}
+
+bool HostScene::add_quad(const float corner[3], const float u[3], const float v[3], uint32_t mat, uint32_t* id, std::string* err) {
+    if (mat >= materials.size()) { *err = "trt_add_quad: unknown material id"; return false; }
+    if (prims.size() >= TRT_REF_INDEX_MASK) { *err = "trt_add_quad: too many primitives"; return false; }
+    HostPrim p; std::memset(&p, 0, sizeof p);
+    p.type = 1; p.mat = mat;
+    float quv[3], qu[3], qv[3];
+    for (int i = 0; i < 3; ++i) {
+        p.a[i] = corner[i]; p.b[i] = u[i]; p.c[i] = v[i];
+        quv[i] = (corner[i] + u[i]) + v[i]; qu[i] = corner[i] + u[i]; qv[i] = corner[i] + v[i];
+    }
+    // hittable/quad.rs:21-24: merge(new(corner, corner+u+v), new(corner+u, corner+v))
+    float m0[3], x0[3], m1[3], x1[3];
+    padded_box(corner, quv, m0, x0); padded_box(qu, qv, m1, x1);
+    for (int i = 0; i < 3; ++i) { p.bmin[i] = fminf(m0[i], m1[i]); p.bmax[i] = fmaxf(x0[i], x1[i]); }
+    // n = u x v; w = n / (n.n); d = n . corner   (hittable/quad.rs:25-27)
+    p.n[0] = u[1] * v[2] - u[2] * v[1];
+    p.n[1] = u[2] * v[0] - u[0] * v[2];
+    p.n[2] = u[0] * v[1] - u[1] * v[0];
+    float nn = p.n[0] * p.n[0] + p.n[1] * p.n[1] + p.n[2] * p.n[2];
+    for (int i = 0; i < 3; ++i) p.w[i] = p.n[i] / nn;
+    p.d = p.n[0] * corner[0] + p.n[1] * corner[1] + p.n[2] * corner[2];
+    if (id) *id = (uint32_t)prims.size();
+    prims.push_back(p); committed = false;
+    return true;
+}
+
+// ------------------------------------------------------------------ generic binary tree produced by both builders
+struct TNode {
+    uint32_t left, right;    // indices into the TNode array; leaf when prim != ~0u
+    uint32_t prim;
+    float bmin[3], bmax[3];
+};
+static const uint32_t NOPRIM = 0xFFFFFFFFu;
+
+static inline void box_union(TNode& n, const TNode& a, const TNode& b) {
+    for (int i = 0; i < 3; ++i) { n.bmin[i] = fminf(a.bmin[i], b.bmin[i]); n.bmax[i] = fmaxf(a.bmax[i], b.bmax[i]); }
+}
+static inline int32_t total_order_key(float f) {   // f32::total_cmp (hittable/aabb.rs:80-82)
+    int32_t k; std::memcpy(&k, &f, 4);
+    k ^= (int32_t)(((uint32_t)(k >> 31)) >> 1);
+    return k;
+}
+
+// ---- reference topology: Node::new, hittable/bvh.rs:42-84. The subtree over n primitives owns nodes [base, base+2n-1).
+struct RefBuilder {
+    const std::vector<HostPrim>& prims;
+    std::vector<TNode>& nodes;
+    std::vector<uint32_t>& order;   // working permutation, sorted in place slice by slice
+    std::vector<int32_t> key[3];
+
+    uint32_t build(size_t lo, size_t hi, uint32_t base, int par_depth) {
+        size_t n = hi - lo;
+        TNode& node = nodes[base];
+        if (n == 1) {
+            const HostPrim& p = prims[order[lo]];
+            node.left = node.right = NOPRIM; node.prim = order[lo];
+            for (int i = 0; i < 3; ++i) { node.bmin[i] = p.bmin[i]; node.bmax[i] = p.bmax[i]; }
+            return base;
+        }
+        if (n > 2) {
+            // union of the slice's boxes -> longest axis (hittable/aabb.rs:63-78), then stable sort on min[axis]
+            float mn[3], mx[3];
+            for (int i = 0; i < 3; ++i) { mn[i] = prims[order[lo]].bmin[i]; mx[i] = prims[order[lo]].bmax[i]; }
+            for (size_t k = lo + 1; k < hi; ++k)
+                for (int i = 0; i < 3; ++i) { mn[i] = fminf(mn[i], prims[order[k]].bmin[i]); mx[i] = fmaxf(mx[i], prims[order[k]].bmax[i]); }
+            float s0 = mx[0] - mn[0], s1 = mx[1] - mn[1], s2 = mx[2] - mn[2];
+            int axis = (s0 > s1) ? ((s0 > s2) ? 0 : 2) : ((s1 > s2) ? 1 : 2);
+            const std::vector<int32_t>& kk = key[axis];
+            std::stable_sort(order.begin() + lo, order.begin() + hi, [&kk](uint32_t a, uint32_t b) { return kk[a] < kk[b]; });
+        }
+        size_t nl = (n == 2) ? 1 : n / 2;                       // bvh.rs:58-60 (n == 2: unsorted), :75 (mid = len/2)
+        uint32_t lbase = base + 1, rbase = base + (uint32_t)(2 * nl);
+        uint32_t l, r;
+        if (par_depth > 0 && n > 16384) {
+            auto fut = std::async(std::launch::async, [&, lo, nl, lbase, par_depth]() { return build(lo, lo + nl, lbase, par_depth - 1); });
+            r = build(lo + nl, hi, rbase, par_depth - 1);
+            l = fut.get();
+        } else {
+            l = build(lo, lo + nl, lbase, 0);
+            r = build(lo + nl, hi, rbase, 0);
+        }
+        node.left = l; node.right = r; node.prim = NOPRIM;
+        box_union(node, nodes[l], nodes[r]);
+        return base;
+    }
+};
+
+// ---- binned SAH, one primitive per leaf. Same node numbering scheme.
+struct SahBuilder {
+    const std::vector<HostPrim>& prims;
+    std::vector<TNode>& nodes;
+    std::vector<uint32_t>& order;
+    static constexpr int NB = 16;
+
+    static float half_area(const float mn[3], const float mx[3]) {
+        float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+    float centroid(uint32_t p, int ax) const { return 0.5f * (prims[p].bmin[ax] + prims[p].bmax[ax]); }
+
+    uint32_t build(size_t lo, size_t hi, uint32_t base, int depth, int par_depth) {
+        size_t n = hi - lo;
+        TNode& node = nodes[base];
+        if (n == 1) {
+            const HostPrim& p = prims[order[lo]];
+            node.left = node.right = NOPRIM; node.prim = order[lo];
+            for (int i = 0; i < 3; ++i) { node.bmin[i] = p.bmin[i]; node.bmax[i] = p.bmax[i]; }
+            return base;
+        }
+        size_t mid = lo + n / 2;
+        bool split_done = false;
+        if (n > 2 && depth < TRT_MAX_STACK - 16) {
+            float cmn[3], cmx[3];
+            for (int a = 0; a < 3; ++a) { cmn[a] = std::numeric_limits<float>::infinity(); cmx[a] = -cmn[a]; }
+            for (size_t k = lo; k < hi; ++k)
+                for (int a = 0; a < 3; ++a) { float c = centroid(order[k], a); cmn[a] = fminf(cmn[a], c); cmx[a] = fmaxf(cmx[a], c); }
+            float best_cost = std::numeric_limits<float>::infinity(); int best_axis = -1, best_bin = -1;
+            for (int a = 0; a < 3; ++a) {
+                float ext = cmx[a] - cmn[a];
+                if (!(ext > 0.f)) continue;
+                float scale = (float)NB / ext;
+                uint32_t cnt[NB]; float bmn[NB][3], bmx[NB][3];
+                for (int b = 0; b < NB; ++b) { cnt[b] = 0; for (int i = 0; i < 3; ++i) { bmn[b][i] = std::numeric_limits<float>::infinity(); bmx[b][i] = -bmn[b][i]; } }
+                for (size_t k = lo; k < hi; ++k) {
+                    const HostPrim& p = prims[order[k]];
+                    int b = (int)((centroid(order[k], a) - cmn[a]) * scale); if (b >= NB) b = NB - 1; if (b < 0) b = 0;
+                    cnt[b]++;
+                    for (int i = 0; i < 3; ++i) { bmn[b][i] = fminf(bmn[b][i], p.bmin[i]); bmx[b][i] = fmaxf(bmx[b][i], p.bmax[i]); }
+                }
+                float la[NB - 1]; uint32_t lc[NB - 1];
+                float amn[3], amx[3]; uint32_t c = 0;
+                for (int i = 0; i < 3; ++i) { amn[i] = std::numeric_limits<float>::infinity(); amx[i] = -amn[i]; }
+                for (int b = 0; b < NB - 1; ++b) {
+                    c += cnt[b]; for (int i = 0; i < 3; ++i) { amn[i] = fminf(amn[i], bmn[b][i]); amx[i] = fmaxf(amx[i], bmx[b][i]); }
+                    lc[b] = c; la[b] = c ? half_area(amn, amx) : 0.f;
+                }
+                c = 0; for (int i = 0; i < 3; ++i) { amn[i] = std::numeric_limits<float>::infinity(); amx[i] = -amn[i]; }
+                for (int b = NB - 1; b >= 1; --b) {
+                    c += cnt[b]; for (int i = 0; i < 3; ++i) { amn[i] = fminf(amn[i], bmn[b][i]); amx[i] = fmaxf(amx[i], bmx[b][i]); }
+                    if (c == 0 || lc[b - 1] == 0) continue;
+                    float cost = la[b - 1] * (float)lc[b - 1] + half_area(amn, amx) * (float)c;
+                    if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b - 1; }
+                }
+            }
+            if (best_axis >= 0) {
+                float ext = cmx[best_axis] - cmn[best_axis], scale = (float)NB / ext, c0 = cmn[best_axis];
+                int ax = best_axis, bb = best_bin;
+                auto it = std::stable_partition(order.begin() + lo, order.begin() + hi, [&](uint32_t p) {
+                    int b = (int)((centroid(p, ax) - c0) * scale); if (b >= NB) b = NB - 1; if (b < 0) b = 0;
+                    return b <= bb;
+                });
+                size_t m = (size_t)(it - order.begin());
+                if (m > lo && m < hi) { mid = m; split_done = true; }
+            }
+        }
+        if (!split_done && n > 2) {
+            // degenerate centroids or depth cap: median on the widest box axis
+            float mn[3], mx[3];
+            for (int i = 0; i < 3; ++i) { mn[i] = std::numeric_limits<float>::infinity(); mx[i] = -mn[i]; }
+            for (size_t k = lo; k < hi; ++k) for (int i = 0; i < 3; ++i) { mn[i] = fminf(mn[i], prims[order[k]].bmin[i]); mx[i] = fmaxf(mx[i], prims[order[k]].bmax[i]); }
+            int ax = 0; if (mx[1] - mn[1] > mx[ax] - mn[ax]) ax = 1; if (mx[2] - mn[2] > mx[ax] - mn[ax]) ax = 2;
+            std::nth_element(order.begin() + lo, order.begin() + mid, order.begin() + hi, [&](uint32_t a, uint32_t b) { return centroid(a, ax) < centroid(b, ax); });
+        }
+        size_t nl = mid - lo;
+        uint32_t lbase = base + 1, rbase = base + (uint32_t)(2 * nl);
+        uint32_t l, r;
+        if (par_depth > 0 && n > 16384) {
+            auto fut = std::async(std::launch::async, [&, lo, mid, lbase, depth, par_depth]() { return build(lo, mid, lbase, depth + 1, par_depth - 1); });
+            r = build(mid, hi, rbase, depth + 1, par_depth - 1);
+            l = fut.get();
+        } else {
+            l = build(lo, mid, lbase, depth + 1, 0);
+            r = build(mid, hi, rbase, depth + 1, 0);
+        }
+        node.left = l; node.right = r; node.prim = NOPRIM;
+        box_union(node, nodes[l], nodes[r]);
+        return base;
+    }
+};
+
+// ------------------------------------------------------------------ flatten
+static inline float as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+
+static uint32_t leaf_ref(const HostPrim& p) {
+    return TRT_REF_LEAF | (p.type ? TRT_REF_QUAD : 0u) | p.type_index;
+}
+
+static void flatten(const std::vector<TNode>& t, const std::vector<HostPrim>& prims, FlatScene& out) {
+    // interior nodes in DFS preorder (parent, whole left subtree, whole right subtree): a child is near its parent in HBM
+    size_t n_leaves = prims.size();
+    out.nodes.clear();
+    out.root = TRT_REF_INVALID; out.n_nodes = 0; out.max_depth = 0; out.sah_cost = 0.f;
+    if (n_leaves == 0) return;
+    auto put_box = [](trt_f4* rec, const TNode* l, const TNode* r) {
+        const float inf = std::numeric_limits<float>::infinity();
+        float lmn[3] = {inf, inf, inf}, lmx[3] = {-inf, -inf, -inf}, rmn[3] = {inf, inf, inf}, rmx[3] = {-inf, -inf, -inf};
+        if (l) for (int i = 0; i < 3; ++i) { lmn[i] = l->bmin[i]; lmx[i] = l->bmax[i]; }
+        if (r) for (int i = 0; i < 3; ++i) { rmn[i] = r->bmin[i]; rmx[i] = r->bmax[i]; }
+        rec[0] = {lmn[0], lmn[1], lmn[2], lmx[0]};
+        rec[1] = {lmx[1], lmx[2], rmn[0], rmn[1]};
+        rec[2] = {rmn[2], rmx[0], rmx[1], rmx[2]};
+    };
+    if (n_leaves == 1) {   // a lone primitive: pseudo-node whose right child is absent
+        out.nodes.resize(4);
+        put_box(out.nodes.data(), &t[0], nullptr);
+        out.nodes[3] = {as_float(leaf_ref(prims[t[0].prim])), as_float(TRT_REF_INVALID), 0.f, 0.f};
+        out.root = 0; out.n_nodes = 1; out.max_depth = 1;
+        return;
+    }
+    out.nodes.resize(4 * (n_leaves - 1));
+    struct Item { uint32_t tnode, depth; };
+    std::vector<uint32_t> flat_index(t.size(), 0xFFFFFFFFu);
+    // pass 1: assign preorder indices to interior nodes
+    {
+        uint32_t next = 0; std::vector<Item> st; st.push_back({0u, 1u});
+        while (!st.empty()) {
+            Item it = st.back(); st.pop_back();
+            const TNode& n = t[it.tnode];
+            if (n.prim != NOPRIM) { if (it.depth > out.max_depth) out.max_depth = it.depth; continue; }
+            flat_index[it.tnode] = next++;
+            st.push_back({n.right, it.depth + 1}); st.push_back({n.left, it.depth + 1});
+        }
+        out.n_nodes = next;
+    }
+    auto ha = [](const TNode& n) { float dx = n.bmax[0] - n.bmin[0], dy = n.bmax[1] - n.bmin[1], dz = n.bmax[2] - n.bmin[2]; return dx * dy + dy * dz + dz * dx; };
+    double root_area = ha(t[0]) > 0.f ? ha(t[0]) : 1.0, cost = 0.0;
+    for (size_t i = 0; i < t.size(); ++i) {
+        const TNode& n = t[i];
+        cost += (double)ha(n) / root_area;
+        if (n.prim != NOPRIM) continue;
+        const TNode& l = t[n.left]; const TNode& r = t[n.right];
+        trt_f4* rec = &out.nodes[4 * (size_t)flat_index[i]];
+        put_box(rec, &l, &r);
+        uint32_t lr = (l.prim != NOPRIM) ? leaf_ref(prims[l.prim]) : flat_index[n.left];
+        uint32_t rr = (r.prim != NOPRIM) ? leaf_ref(prims[r.prim]) : flat_index[n.right];
+        rec[3] = {as_float(lr), as_float(rr), 0.f, 0.f};
+    }
+    out.root = 0; out.sah_cost = (float)cost;
+}
+
+bool HostScene::commit(int bvh_kind, std::string* err) {
+    if (bvh_kind != 0 && bvh_kind != 1) { *err = "trt_scene_commit: unknown bvh_kind"; return false; }
+    size_t n = prims.size();
+    // per-type arrays in insertion order (what World::get_geometries::<T>() returns, hittable/world.rs:47-55)
+    uint32_t ns = 0, nq = 0;
+    for (auto& p : prims) p.type_index = p.type ? nq++ : ns++;
+    leaf_rank.assign(n, 0);
+    flat = FlatScene(); flat.bvh_kind = bvh_kind;
+
+    std::vector<TNode> ref_tree(n ? 2 * n - 1 : 0), sah_tree;
+    std::vector<uint32_t> order(n);
+    for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
+    if (n) {
+        RefBuilder rb{prims, ref_tree, order, {}};
+        for (int a = 0; a < 3; ++a) { rb.key[a].resize(n); for (size_t i = 0; i < n; ++i) rb.key[a][i] = total_order_key(prims[i].bmin[a]); }
+        rb.build(0, n, 0, 3);
+        // the in-place sorts leave `order` in left-to-right leaf order
+        for (size_t i = 0; i < n; ++i) leaf_rank[order[i]] = (uint32_t)i;
+    }
+    const std::vector<TNode>* tree = &ref_tree;
+    if (bvh_kind == 1 && n) {
+        sah_tree.resize(2 * n - 1);
+        for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
+        SahBuilder sb{prims, sah_tree, order};
+        sb.build(0, n, 0, 1, 3);
+        tree = &sah_tree;
+    }
+    flatten(*tree, prims, flat);
+    if (flat.max_depth > TRT_MAX_STACK) { *err = "trt_scene_commit: tree deeper than the traversal stack"; return false; }
+
+    flat.spheres.resize(ns); flat.sphere_meta.resize(ns); flat.quads.resize(4 * (size_t)nq); flat.quad_meta.resize(nq);
+    for (size_t i = 0; i < n; ++i) {
+        const HostPrim& p = prims[i];
+        trt_u4 meta = {p.mat, leaf_rank[i], (uint32_t)i, 0u};
+        if (p.type == 0) {
+            flat.spheres[p.type_index] = {p.a[0], p.a[1], p.a[2], p.r};
+            flat.sphere_meta[p.type_index] = meta;
+        } else {
+            trt_f4* q = &flat.quads[4 * (size_t)p.type_index];
+            q[0] = {p.n[0], p.n[1], p.n[2], p.d};
+            q[1] = {p.a[0], p.a[1], p.a[2], p.w[0]};
+            q[2] = {p.b[0], p.b[1], p.b[2], p.w[1]};
+            q[3] = {p.c[0], p.c[1], p.c[2], p.w[2]};
+            flat.quad_meta[p.type_index] = meta;
+        }
+    }
+    flat.materials.resize(2 * materials.size());
+    for (size_t m = 0; m < materials.size(); ++m) {
+        flat.materials[2 * m] = {materials[m].rgb[0], materials[m].rgb[1], materials[m].rgb[2], as_float(materials[m].kind)};
+        flat.materials[2 * m + 1] = {materials[m].param, 0.f, 0.f, 0.f};
+    }
+    committed = true; version++;
+    return true;
+}
+
+} // namespace trt

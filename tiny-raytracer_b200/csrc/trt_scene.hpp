@@ -1,0 +1,53 @@
+// trt_scene.hpp — host side of the scene: the World registry (hittable/world.rs), the two BVH builders and the
+// flattener that produces the HBM layout of trt_layout.h. Plain C++17, no CUDA.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "trt_layout.h"
+
+namespace trt {
+
+struct HostMaterial { uint32_t kind; float rgb[3]; float param; };
+
+struct HostPrim {
+    uint32_t type;        // 0 sphere, 1 quad
+    uint32_t mat;
+    float a[3], b[3], c[3]; float r;   // sphere: a = center, r = radius; quad: a = corner, b = u, c = v
+    float n[3], w[3], d;               // quad derived (hittable/quad.rs:25-27)
+    float bmin[3], bmax[3];            // padded AABB (hittable/aabb.rs:13-20)
+    uint32_t type_index;               // index inside its type's array
+};
+
+struct FlatScene {
+    std::vector<trt_f4> nodes;         // 4 per interior node
+    std::vector<trt_f4> spheres;
+    std::vector<trt_f4> quads;         // 4 per quad
+    std::vector<trt_u4> sphere_meta, quad_meta;
+    std::vector<trt_f4> materials;     // 2 per material
+    uint32_t root = TRT_REF_INVALID;   // interior node 0, or INVALID for an empty scene
+    uint32_t n_nodes = 0, max_depth = 0;
+    float sah_cost = 0.f;
+    int bvh_kind = 0;
+    size_t bytes() const {
+        return (nodes.size() + spheres.size() + quads.size() + materials.size()) * sizeof(trt_f4) +
+               (sphere_meta.size() + quad_meta.size()) * sizeof(trt_u4);
+    }
+};
+
+struct HostScene {
+    std::vector<HostMaterial> materials;
+    std::vector<HostPrim> prims;        // insertion order == prim_id
+    std::vector<uint32_t> leaf_rank;    // reference-topology leaf order per prim_id (after commit)
+    FlatScene flat;
+    bool committed = false;
+    uint64_t version = 0;               // bumped by every commit; the device copy remembers which one it holds
+
+    uint32_t add_material(uint32_t kind, const float rgb[3], float param);
+    // returns false + message on bad input
+    bool add_sphere(const float c[3], float r, uint32_t mat, uint32_t* id, std::string* err);
+    bool add_quad(const float corner[3], const float u[3], const float v[3], uint32_t mat, uint32_t* id, std::string* err);
+    bool commit(int bvh_kind, std::string* err);
+};
+
+} // namespace trt
