@@ -86,6 +86,9 @@ int trt_ctx_destroy(trt_ctx* ctx);
 int trt_ctx_device_name(trt_ctx* ctx, char* buf, size_t buf_len);
 int trt_ctx_sm_count(trt_ctx* ctx, int* out);
 int trt_ctx_synchronize(trt_ctx* ctx);
+/* Run all later work of this ctx on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL = the legacy default
+ * stream), e.g. the framework stream that also carries the NCCL reduce, so that ordering and CUDA-event timing line up. */
+int trt_ctx_set_stream(trt_ctx* ctx, void* cuda_stream);
 
 /* ---- scene building: World::new / add_material / add_geometry (hittable/world.rs:16-31). Host only, no GPU needed. */
 int trt_scene_create(trt_scene** out);

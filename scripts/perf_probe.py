@@ -1,0 +1,45 @@
+"""Quick device-timed probe of the render kernels on the BASELINE workloads at reduced spp (development aid)."""
+import argparse
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import tiny_raytracer_b200 as trt
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workloads", default="c3,c2,c4,c5")
+ap.add_argument("--spp", type=int, default=32)
+ap.add_argument("--kinds", default="0,1")
+ap.add_argument("--variant", type=int, default=0)
+ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--c4n", type=int, default=1_000_000)
+a = ap.parse_args()
+
+ctx = trt.Context(0)
+print(ctx.name, ctx.sm_count, flush=True)
+for wl in a.workloads.split(","):
+    desc = trt.scenes.WORKLOADS[wl]() if wl != "c4" else trt.scenes.random_spheres(a.c4n)
+    if wl == "c5":
+        desc = desc.with_image(1920, 1080)
+    w, h = desc.camera["width"], desc.camera["height"]
+    cam = trt.make_camera(**desc.camera)
+    for kind in [int(k) for k in a.kinds.split(",")]:
+        t0 = time.time()
+        sc = trt.Scene.from_desc(desc, kind)
+        t_build = time.time() - t0
+        sc.upload(ctx)
+        acc = torch.zeros(h * w * 3, dtype=torch.float64, device="cuda:0")
+        torch.cuda.synchronize()
+        p = trt.make_params(w, h, a.spp, desc.max_bounces, desc.background, desc.seed, spp_total=a.spp, variant=a.variant)
+        best = None
+        for r in range(a.reps):
+            acc.zero_(); torch.cuda.synchronize()
+            st = sc.render_accumulate(ctx, cam, p, acc.data_ptr())
+            if best is None or st.device_ms < best.device_ms:
+                best = st
+        print("%-3s kind=%d variant=%d spp=%d  build %.2fs  %s  %.2f ms  %.1f Mpaths/s  %.1f Mrays/s  rays/path %.2f" % (
+            wl, kind, a.variant, a.spp, t_build, sc.bvh_info(), best.device_ms, best.paths / best.device_ms / 1e3,
+            best.rays / best.device_ms / 1e3, best.rays / max(best.paths, 1)), flush=True)
+        sc.close()

@@ -1,0 +1,113 @@
+"""CPU tests of the C-ABI library and the host-side mirror: the .so loads and exports every symbol include/trt.h
+declares; host-only entry points (scene building, BVH build, camera) work without a GPU and agree with the oracle;
+compute entry points fail loudly without a device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(trt):
+    hdr = open(os.path.join(ROOT, "include", "trt.h")).read()
+    declared = set(re.findall(r"\b(trt_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(trt._lib.SYMBOLS), declared ^ set(trt._lib.SYMBOLS)
+    lib = C.CDLL(trt.LIB_PATH)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    nm = subprocess.run(["nm", "-D", "--defined-only", trt.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (trt_[a-z0-9_]+)", nm))
+    assert declared <= exported
+    assert trt._lib.load().trt_abi_version() == 1
+
+
+def test_wire_struct_sizes(trt):
+    # #[repr(C)] SamplePoint 32 B (pointgen.rs:7-13) and SampledColor 20 B (imager.rs:9-15)
+    assert C.sizeof(trt._lib.SamplePoint) == 32 and C.sizeof(trt._lib.SampledColor) == 20
+    assert trt.SAMPLE_POINT_DTYPE.itemsize == 32 and trt.SAMPLED_COLOR_DTYPE.itemsize == 20
+
+
+def test_camera_pod_equals_oracle_bitwise(trt, orc):
+    for args in ((140.0, 0.6, (50, 50, -140), (50, 50, 0), (0, 1, 0), 40.0, 1920, 1080),
+                 (10.0, 0.6, (13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 1200, 675),
+                 (3.4, 10.0, (-2, 2, 1), (0, 0, -1), (0, 1, 0), 20.0, 400, 300)):
+        a, b = trt.make_camera(*args), orc.make_camera(*args)
+        assert bytes(a) == bytes(b)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_host_bvh_build_and_ranks(trt, orc, kind):
+    for desc in (trt.scenes.cornell(), trt.scenes.final_scene(), trt.scenes.random_mixed(500, 2), trt.scenes.random_spheres(30000, 64, 64)):
+        sc = trt.Scene.from_desc(desc, kind)
+        info = sc.bvh_info()
+        assert info["nodes"] == desc.n_prims - 1 and 0 < info["max_depth"] <= 64
+        assert np.array_equal(sc.leaf_ranks(), orc.Scene.from_desc(desc).leaf_ranks())   # reference-topology leaf order
+        if kind == 0:
+            assert info["max_depth"] == orc.Scene.from_desc(desc).tree_stats()["max_depth"]
+    sah = trt.Scene.from_desc(trt.scenes.final_scene(), 1).bvh_info()["sah_cost"]
+    med = trt.Scene.from_desc(trt.scenes.final_scene(), 0).bvh_info()["sah_cost"]
+    assert sah < med
+
+
+def test_errors_are_values_not_crashes(trt):
+    lib = trt._lib.load()
+    sc = trt.Scene()
+    with pytest.raises(trt.TrtError) as e:
+        sc.add_sphere((0, 0, 0), 1.0, 7)                      # unknown material
+    assert e.value.code == -1 and "material" in str(e.value)
+    with pytest.raises(trt.TrtError):
+        sc.bvh_info()                                          # not committed
+    with pytest.raises(trt.TrtError):
+        sc.commit(5)
+    m = sc.add_material(1, (1, 1, 1), 9.0)                     # metal fuzz clamps silently like Metal::new
+    sc.add_sphere((0, 0, 0), 1.0, m); sc.commit(1)
+    assert sc.bvh_info()["nodes"] == 1 and sc.num_prims == 1
+    assert lib.trt_scene_destroy(None) == 0 and lib.trt_ctx_destroy(None) == 0
+    assert lib.trt_scene_commit(None, 0) == -1
+
+
+def test_no_cpu_fallback(trt):
+    """Without a usable GPU every compute entry point must fail loudly (skipped where a GPU exists)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(trt.TrtError) as e:
+        trt.Context(0)
+    assert e.value.code == -2 and "no CPU path" in str(e.value)
+
+
+def test_product_does_not_reference_the_oracle():
+    """The product path must never route through oracle/ (only tests, smoke() and bench.py's CPU legs may)."""
+    pkg = os.path.join(ROOT, "tiny-raytracer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h", ".hpp", ".sh")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle/" not in src.replace("oracle/pyoracle.py", "").replace("`oracle/", "") or f == "scenes.py", f
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+    ldd = subprocess.run(["ldd", os.path.join(pkg, "libtrt_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd
+
+
+def test_reference_api_mirror(trt, tmp_path):
+    w = trt.World.new()
+    w.add_material("white", trt.Lambertian(trt.Vec3.new(0.73, 0.73, 0.73)))
+    with pytest.raises(KeyError):
+        w.add_material("white", trt.Light(trt.Vec3.new_diagonal(1.0)))      # world.rs:29-31 panics on a duplicate name
+    assert w.get_material("nope") is None
+    w.add_geometry(trt.Sphere(trt.Vec3.new(0, 0, 0), 1.0, w.get_material("white")))
+    w.add_geometry(trt.new_box(trt.Vec3.new(25, 0, 50), trt.Vec3.new(55, 60, 80), w.get_material("white")))
+    assert len(w.get_geometries(trt.Quad)) == 6 and len(w.get_geometries(trt.Sphere)) == 1
+    d = w.to_desc()
+    ref = trt.scenes.cornell()
+    assert np.array_equal(d.prim_data[1:7], ref.prim_data[6:12])               # new_box order == main.rs:99-122
+    cam = trt.Camera.new(1.0, 10.0, trt.Vec3.zero(), trt.Vec3.new(0, 0, 1), trt.Vec3.new(0, 1, 0), 90.0, 16, 9)
+    assert cam.get_image_size() == (16, 9)
+    img = trt.Image(np.zeros((4, 5, 3), np.float32), (np.arange(60).reshape(4, 5, 3) * 4).astype(np.uint8))
+    p = tmp_path / "x.png"; img.save(str(p))
+    raw = p.read_bytes()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n" and img.size() == (5, 4)

@@ -57,6 +57,7 @@ SYMBOLS = {
     "trt_ctx_device_name": (C.c_int, [_P, C.c_char_p, C.c_size_t]),
     "trt_ctx_sm_count": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "trt_ctx_synchronize": (C.c_int, [_P]),
+    "trt_ctx_set_stream": (C.c_int, [_P, _P]),
     "trt_scene_create": (C.c_int, [C.POINTER(_P)]),
     "trt_scene_destroy": (C.c_int, [_P]),
     "trt_add_lambertian": (C.c_int, [_P, _F3, _U32P]),

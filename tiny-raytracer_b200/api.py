@@ -65,6 +65,10 @@ class Context:
     def synchronize(self):
         L.check(self._lib.trt_ctx_synchronize(self._h))
 
+    def set_stream(self, cuda_stream: int):
+        """Run on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = legacy default stream."""
+        L.check(self._lib.trt_ctx_set_stream(self._h, C.c_void_p(int(cuda_stream)) if cuda_stream else None))
+
 
 def make_camera(focus_distance, defocus_angle, position, look_at, up, vertical_fov, width, height) -> L.Camera:
     """Camera::new (camera.rs:17-56) -> plain-data camera."""

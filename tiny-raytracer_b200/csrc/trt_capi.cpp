@@ -28,7 +28,7 @@ struct trt_scene {
     std::map<int, DeviceCopy> on_device;   // device ordinal -> copy
 };
 struct trt_ctx {
-    int device = 0; int sm_count = 0; cudaStream_t stream = nullptr; cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int device = 0; int sm_count = 0; cudaStream_t stream = nullptr; cudaStream_t own_stream = nullptr; cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long* d_counters = nullptr;   // 8 x u64 (5 used) followed by the u32 work counter
     unsigned int* d_next_item = nullptr;
     // scratch reused across calls (grown on demand)
@@ -68,7 +68,8 @@ int trt_ctx_create(int device_ordinal, trt_ctx** out) {
     if (!c) return fail(TRT_ERR_OOM, "trt_ctx_create: host allocation failed");
     c->device = device_ordinal; c->sm_count = prop.multiProcessorCount;
     std::snprintf(c->name, sizeof c->name, "%s", prop.name);
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&c->ev[i]));
     CU(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long) + 64));
     c->d_next_item = (unsigned int*)(c->d_counters + 8);
@@ -82,7 +83,7 @@ int trt_ctx_destroy(trt_ctx* c) {
     for (int i = 0; i < 4; ++i) if (c->scratch[i]) cudaFree(c->scratch[i]);
     if (c->d_counters) cudaFree(c->d_counters);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return TRT_OK;
 }
@@ -92,6 +93,14 @@ int trt_ctx_device_name(trt_ctx* c, char* buf, size_t n) {
 }
 int trt_ctx_sm_count(trt_ctx* c, int* out) { if (!c || !out) return fail(TRT_ERR_INVALID, "trt_ctx_sm_count: bad argument"); *out = c->sm_count; return TRT_OK; }
 int trt_ctx_synchronize(trt_ctx* c) { if (!c) return fail(TRT_ERR_INVALID, "trt_ctx_synchronize: null ctx"); CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->stream)); return TRT_OK; }
+
+int trt_ctx_set_stream(trt_ctx* c, void* cuda_stream) {
+    if (!c) return fail(TRT_ERR_INVALID, "trt_ctx_set_stream: null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = (cudaStream_t)cuda_stream;
+    return TRT_OK;
+}
 
 // ------------------------------------------------------------------ scene (host only)
 int trt_scene_create(trt_scene** out) {
