@@ -214,92 +214,85 @@ template <bool SMEM> TRT_DEV bool quad_hit(const DevScene& S, uint32_t idx, V3 o
 // ORDERED = true (TRT_BVH_SAH): any topology, nearer child first. A subtree is culled only when its entry is beyond
 //   the closest hit; a primitive replaces the closest hit if its t is smaller, or equal with a smaller reference leaf
 //   rank (the reference's tie rule), so the result does not depend on the visiting order.
+//
+// SIMT shape: one loop whose body has exactly one interior-node region (A) and one primitive region (B). A lane is in
+// A when its current ref is an interior node and in B when it is a leaf (possibly the leaf A just selected), so each
+// region's code is issued once per iteration for all lanes that need it instead of once per call site.
 struct Hit { float t; uint32_t ref; };
 
 template <bool ORDERED, bool SMEM, bool COUNT>
 TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
     Hit best; best.t = TRT_INF; best.ref = TRT_REF_INVALID;
-    if (S.root == TRT_REF_INVALID) return best;
+    uint32_t cur = S.root;
+    if (cur == TRT_REF_INVALID) return best;
     uint32_t best_rank = 0xFFFFFFFFu;
     const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);   // aabb.rs:42, identical for every node of this ray
     uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
     int sp = 0;
-    uint32_t cur = S.root;
     if (COUNT) {
         ec->node_visits += 1;          // the root's own Node::hit call (bvh.rs:25-27); its box test is implied by the
         float s0, e0;                  // children's tests, so it is only evaluated to keep the event counts faithful
         slab(S.root_min[0], S.root_min[1], S.root_min[2], S.root_max[0], S.root_max[1], S.root_max[2], o, inv, t_min, &s0, &e0);
         if (!(e0 > s0)) return best;
     }
-
-    auto test_leaf = [&](uint32_t ref) {
-        uint32_t idx = ref & TRT_REF_INDEX_MASK;
-        float t; bool h;
-        if (ref & TRT_REF_QUAD) { if (COUNT) ec->quad_tests++; h = quad_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : best.t, &t); }
-        else { if (COUNT) ec->sphere_tests++; h = sphere_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : best.t, &t); }
-        if (!h) return;
-        if (ORDERED) {
-            if (t < best.t) { best.t = t; best.ref = ref; best_rank = 0xFFFFFFFFu; }
-            else if (t == best.t) {
-                if (best_rank == 0xFFFFFFFFu)
-                    best_rank = (best.ref & TRT_REF_QUAD) ? ld4u<SMEM>(S.quad_meta + (best.ref & TRT_REF_INDEX_MASK)).y
-                                                          : ld4u<SMEM>(S.sphere_meta + (best.ref & TRT_REF_INDEX_MASK)).y;
-                uint32_t rk = (ref & TRT_REF_QUAD) ? ld4u<SMEM>(S.quad_meta + idx).y : ld4u<SMEM>(S.sphere_meta + idx).y;
-                if (rk < best_rank) { best.ref = ref; best_rank = rk; }
-            }
-        } else { best.t = t; best.ref = ref; }
-    };
-
-    for (;;) {
-        const float4* np = S.nodes + 4 * (size_t)cur;
-        float4 n0 = ld4<SMEM>(np), n1 = ld4<SMEM>(np + 1), n2 = ld4<SMEM>(np + 2), n3 = ld4<SMEM>(np + 3);
-        uint32_t lref = __float_as_uint(n3.x), rref = __float_as_uint(n3.y);
-        float sl, el, sr, er;
-        slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, &sl, &el);
-        slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, &sr, &er);
-        if (COUNT) ec->node_visits += (rref == TRT_REF_INVALID) ? 0u : 2u;   // left.hit + right.hit of an interior node
-        uint32_t next = TRT_REF_INVALID;
-        if (!ORDERED) {
-            // left now, with the current closest hit as range end
-            if (el > sl && best.t > sl) { if (lref & TRT_REF_LEAF) test_leaf(lref); else next = lref; }
-            if (rref != TRT_REF_INVALID && er > sr) {
-                if (next == TRT_REF_INVALID) {               // left subtree finished: right is entered with the narrowed range
-                    if (best.t > sr) { if (rref & TRT_REF_LEAF) test_leaf(rref); else next = rref; }
-                } else { stack_ref[sp] = rref; stack_t[sp] = sr; ++sp; }
-            }
-        } else {
-            bool pl = el > sl && !(best.t < sl);
-            bool pr = rref != TRT_REF_INVALID && er > sr && !(best.t < sr);
-            // leaves are tested immediately (nearer first), interior children are ordered by entry distance
-            bool l_leaf = (lref & TRT_REF_LEAF) != 0, r_leaf = (rref & TRT_REF_LEAF) != 0;
-            if (pl && pr) {
-                bool left_first = !(sr < sl);
-                uint32_t a = left_first ? lref : rref, b = left_first ? rref : lref;
-                float sb = left_first ? sr : sl;
-                bool a_leaf = left_first ? l_leaf : r_leaf, b_leaf = left_first ? r_leaf : l_leaf;
-                if (a_leaf) test_leaf(a); else next = a;
-                if (b_leaf) { if (!(best.t < sb)) test_leaf(b); }
-                else if (next == TRT_REF_INVALID) { if (!(best.t < sb)) next = b; }
-                else { stack_ref[sp] = b; stack_t[sp] = sb; ++sp; }
-            } else if (pl) { if (l_leaf) test_leaf(lref); else next = lref; }
-            else if (pr) { if (r_leaf) test_leaf(rref); else next = rref; }
+    do {
+        if (!(cur & TRT_REF_LEAF)) {
+            // ---- region A: one interior node = two child boxes (aabb.rs:36-61 twice)
+            const float4* np = S.nodes + 4 * (size_t)cur;
+            float4 n0 = ld4<SMEM>(np), n1 = ld4<SMEM>(np + 1), n2 = ld4<SMEM>(np + 2), n3 = ld4<SMEM>(np + 3);
+            uint32_t lref = __float_as_uint(n3.x), rref = __float_as_uint(n3.y);
+            float sl, el, sr, er;
+            slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, &sl, &el);
+            slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, &sr, &er);
+            if (COUNT) ec->node_visits += (rref == TRT_REF_INVALID) ? 0u : 2u;   // left.hit + right.hit
+            bool pl, pr;
+            if (ORDERED) { pl = el > sl && !(best.t < sl); pr = er > sr && !(best.t < sr); }
+            else { pl = el > sl && best.t > sl; pr = er > sr; }                  // right: range end re-checked when it is entered
+            pr = pr && rref != TRT_REF_INVALID;
+            bool right_first = ORDERED && pl && pr && sr < sl;
+            uint32_t c0 = right_first ? rref : lref, c1 = right_first ? lref : rref;
+            float s1 = right_first ? sl : sr;
+            bool p0 = right_first ? pr : pl, p1 = right_first ? pl : pr;
+            if (p0) {
+                cur = c0;
+                if (p1) { stack_ref[sp] = c1; stack_t[sp] = s1; ++sp; }
+            } else if (p1 && (ORDERED || best.t > s1)) cur = c1;
+            else cur = TRT_REF_INVALID;
         }
-        while (next == TRT_REF_INVALID && sp > 0) {
+        if (cur != TRT_REF_INVALID && (cur & TRT_REF_LEAF)) {
+            // ---- region B: one primitive (sphere.rs:29-45 / quad.rs:33-41)
+            uint32_t idx = cur & TRT_REF_INDEX_MASK;
+            float t; bool h;
+            if (cur & TRT_REF_QUAD) { if (COUNT) ec->quad_tests++; h = quad_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : best.t, &t); }
+            else { if (COUNT) ec->sphere_tests++; h = sphere_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : best.t, &t); }
+            if (h) {
+                if (!ORDERED) { best.t = t; best.ref = cur; }
+                else if (t < best.t) { best.t = t; best.ref = cur; best_rank = 0xFFFFFFFFu; }
+                else if (t == best.t) {
+                    if (best_rank == 0xFFFFFFFFu)
+                        best_rank = (best.ref & TRT_REF_QUAD) ? ld4u<SMEM>(S.quad_meta + (best.ref & TRT_REF_INDEX_MASK)).y
+                                                              : ld4u<SMEM>(S.sphere_meta + (best.ref & TRT_REF_INDEX_MASK)).y;
+                    uint32_t rk = (cur & TRT_REF_QUAD) ? ld4u<SMEM>(S.quad_meta + idx).y : ld4u<SMEM>(S.sphere_meta + idx).y;
+                    if (rk < best_rank) { best.ref = cur; best_rank = rk; }
+                }
+            }
+            cur = TRT_REF_INVALID;
+        }
+        // ---- pop: skip entries that the closest hit found meanwhile has cut off
+        while (cur == TRT_REF_INVALID && sp > 0) {
             --sp;
-            uint32_t r = stack_ref[sp]; float s = stack_t[sp];
-            bool pass = ORDERED ? !(best.t < s) : (best.t > s);
-            if (!pass) continue;
-            if (r & TRT_REF_LEAF) test_leaf(r); else next = r;
+            float s = stack_t[sp];
+            if (ORDERED ? !(best.t < s) : (best.t > s)) cur = stack_ref[sp];
         }
-        if (next == TRT_REF_INVALID) break;
-        cur = next;
-    }
+    } while (cur != TRT_REF_INVALID);
     return best;
 }
 
 // ------------------------------------------------------------------ camera: pointgen.rs:41-43 + camera.rs:58-66 + vec3extend.rs:45-53
-TRT_DEV void primary_ray(const DevCamera& C, const DevParams& P, uint32_t x, uint32_t y, uint32_t pixel, uint32_t sample, V3* o_out, V3* d_out) {
-    U4 r = philox4x32_10(pixel, sample, 0u, 0u, P.seed_lo, P.seed_hi);
+// `r` is Philox block 0 of the stream (pixel, sample, bounce 0): (xi1, xi2, a, b); further blocks feed the lens rejection loop.
+// Returns the UN-normalised direction; Ray::new's normalisation (ray.rs:12-14) is applied by the caller.
+TRT_DEV void camera_ray(const DevCamera& C, const DevParams& P, uint32_t x, uint32_t y, uint32_t pixel, uint32_t sample, U4 r,
+                        V3* o_out, V3* dir_out) {
     float u = ((float)x + u01(r.x)) / (float)(C.width - 1);
     float v = ((float)y + u01(r.y)) / (float)(C.height - 1);
     float a = u11(r.z), b = u11(r.w);
@@ -310,17 +303,24 @@ TRT_DEV void primary_ray(const DevCamera& C, const DevParams& P, uint32_t x, uin
         if (!(a * a + b * b + 0.0f * 0.0f < 1.0f)) { a = u11(e.z); b = u11(e.w); }
     }
     V3 origin = C.position + a * C.du + b * C.dv;
-    V3 dir = C.upper_left + (u * C.horizontal) - (v * C.vertical) - origin;
-    *o_out = origin; *d_out = normalized(dir);           // Ray::new normalises, ray.rs:12-14
+    *o_out = origin;
+    *dir_out = C.upper_left + (u * C.horizontal) - (v * C.vertical) - origin;
+}
+TRT_DEV void primary_ray(const DevCamera& C, const DevParams& P, uint32_t x, uint32_t y, uint32_t pixel, uint32_t sample, V3* o_out, V3* d_out) {
+    U4 r = philox4x32_10(pixel, sample, 0u, 0u, P.seed_lo, P.seed_hi);
+    V3 dir;
+    camera_ray(C, P, x, y, pixel, sample, r, o_out, &dir);
+    *d_out = normalized(dir);
 }
 
 // ------------------------------------------------------------------ one hit: HitRecord::new (hittable/mod.rs:27-48) + emitted/scatter (material/*.rs)
-// Returns true if the path continues with (o, d) replaced by the scattered ray. `k` is the 1-based hit index (Philox bounce word).
+struct Surface { V3 point, normal; bool front; uint32_t kind; V3 rgb; float param; };
+
 template <bool SMEM>
-TRT_DEV bool shade(const DevScene& S, const DevParams& P, Hit h, uint32_t pixel, uint32_t sample, uint32_t k,
-                   V3* o, V3* d, V3* atten, V3* color) {
+TRT_DEV Surface hit_record(const DevScene& S, Hit h, V3 o, V3 d) {
+    Surface sf;
     uint32_t idx = h.ref & TRT_REF_INDEX_MASK;
-    V3 point = ray_at(*o, *d, h.t);
+    sf.point = ray_at(o, d, h.t);
     V3 outward; uint32_t mat;
     if (h.ref & TRT_REF_QUAD) {
         float4 q0 = ld4<SMEM>(S.quads + 4 * (size_t)idx);
@@ -328,33 +328,31 @@ TRT_DEV bool shade(const DevScene& S, const DevParams& P, Hit h, uint32_t pixel,
         mat = ld4u<SMEM>(S.quad_meta + idx).x;
     } else {
         float4 s = ld4<SMEM>(S.spheres + idx);
-        outward = point - mk(s.x, s.y, s.z);                                  // sphere.rs:46-50
+        outward = sf.point - mk(s.x, s.y, s.z);                               // sphere.rs:46-50
         mat = ld4u<SMEM>(S.sphere_meta + idx).x;
     }
-    bool front = dot(*d, outward) < 0.0f;
+    sf.front = dot(d, outward) < 0.0f;
     V3 nn = normalized(outward);
-    V3 normal = front ? nn : -nn;
+    sf.normal = sf.front ? nn : -nn;
     float4 m0 = ld4<SMEM>(S.materials + 2 * (size_t)mat);
-    uint32_t kind = __float_as_uint(m0.w);
-    V3 rgb = mk(m0.x, m0.y, m0.z);
-    // cpu.rs:49-50: color += cumulated_attenuation * emitted().unwrap_or(0)
-    V3 emission = (kind == TRT_MAT_LIGHT) ? rgb : mk(0.0f, 0.0f, 0.0f);
-    *color = *color + (*atten) * emission;
-    if (kind == TRT_MAT_LIGHT) return false;                                  // light.rs:17-19
-    U4 r = philox4x32_10(pixel, sample, k, 0u, P.seed_lo, P.seed_hi);
-    V3 dir;
-    if (kind == TRT_MAT_LAMBERTIAN) {                                         // lambertian.rs:16-22
+    sf.kind = __float_as_uint(m0.w);
+    sf.rgb = mk(m0.x, m0.y, m0.z);
+    sf.param = (sf.kind == TRT_MAT_METAL || sf.kind == TRT_MAT_DIELECTRIC) ? ld4<SMEM>(S.materials + 2 * (size_t)mat + 1).x : 0.0f;
+    return sf;
+}
+// Un-normalised scattered direction for the three scattering materials; `r` is Philox block 0 of (pixel, sample, k).
+TRT_DEV V3 scatter_direction(const Surface& sf, V3 d, U4 r) {
+    if (sf.kind == TRT_MAT_LAMBERTIAN) {                                      // lambertian.rs:16-22
         V3 uv = normalized(random_in_unit_sphere(u01(r.x), u01(r.y), u01(r.z), false));
-        dir = normal + uv;
-        if (near_zero(dir)) dir = normal;
-    } else if (kind == TRT_MAT_METAL) {                                       // metal.rs:18-25
-        float fuzz = ld4<SMEM>(S.materials + 2 * (size_t)mat + 1).x;
-        V3 reflected = reflect(*d, normal);
-        dir = reflected + fuzz * random_in_unit_sphere(u01(r.x), u01(r.y), u01(r.z), true);
+        V3 dir = sf.normal + uv;
+        if (near_zero(dir)) dir = sf.normal;
+        return dir;
+    } else if (sf.kind == TRT_MAT_METAL) {                                    // metal.rs:18-25
+        V3 reflected = reflect(d, sf.normal);
+        return reflected + sf.param * random_in_unit_sphere(u01(r.x), u01(r.y), u01(r.z), true);
     } else {                                                                  // dielectric.rs:26-46
-        float ior = ld4<SMEM>(S.materials + 2 * (size_t)mat + 1).x;
-        float ri = front ? 1.0f / ior : ior;
-        float c = fminf(-dot(normal, *d), 1.0f);
+        float ri = sf.front ? 1.0f / sf.param : sf.param;
+        float c = fminf(-dot(sf.normal, d), 1.0f);
         float s = sqrtf(1.0f - c * c);
         bool total_reflection = ri * s > 1.0f;
         float sqrt_r0 = (1.0f - ri) / (1.0f + ri);
@@ -363,10 +361,22 @@ TRT_DEV bool shade(const DevScene& S, const DevParams& P, Hit h, uint32_t pixel,
         float m2 = m * m;
         float m5 = (m2 * m2) * m;
         float reflectance = r0 + (1.0f - r0) * m5;
-        dir = (total_reflection || reflectance > u01(r.x)) ? reflect(*d, normal) : refract(*d, normal, ri);
+        return (total_reflection || reflectance > u01(r.x)) ? reflect(d, sf.normal) : refract(d, sf.normal, ri);
     }
-    *atten = (*atten) * rgb;                                                  // cpu.rs:52
-    *o = point; *d = normalized(dir);                                         // Ray::new, ray.rs:12-14
+}
+// Returns true if the path continues with (o, d) replaced by the scattered ray. `k` is the 1-based hit index (Philox bounce word).
+template <bool SMEM>
+TRT_DEV bool shade(const DevScene& S, const DevParams& P, Hit h, uint32_t pixel, uint32_t sample, uint32_t k,
+                   V3* o, V3* d, V3* atten, V3* color) {
+    Surface sf = hit_record<SMEM>(S, h, *o, *d);
+    // cpu.rs:49-50: color += cumulated_attenuation * emitted().unwrap_or(0)
+    V3 emission = (sf.kind == TRT_MAT_LIGHT) ? sf.rgb : mk(0.0f, 0.0f, 0.0f);
+    *color = *color + (*atten) * emission;
+    if (sf.kind == TRT_MAT_LIGHT) return false;                               // light.rs:17-19
+    U4 r = philox4x32_10(pixel, sample, k, 0u, P.seed_lo, P.seed_hi);
+    V3 dir = scatter_direction(sf, *d, r);
+    *atten = (*atten) * sf.rgb;                                               // cpu.rs:52
+    *o = sf.point; *d = normalized(dir);                                      // Ray::new, ray.rs:12-14
     return true;
 }
 

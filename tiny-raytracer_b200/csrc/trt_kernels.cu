@@ -59,12 +59,14 @@ __device__ __forceinline__ bool decode_item(const MegaArgs& A, uint32_t item, ui
     return *x < A.p.width && *y < A.p.height;
 }
 
+// Loop body = T (one ray segment for every live lane) then S (shade-or-regenerate, fused so that the scattering lanes
+// and the lanes starting a new path share ONE Philox call, ONE normalisation and the work-fetch point; every lane that
+// still has work leaves S with a live ray, so T always runs with full lanes until the work counter runs dry).
 template <bool ORDERED, bool SMEM, bool COUNT>
-__global__ void __launch_bounds__(256, 2) k_render_mega(const MegaArgs A) {
+__global__ void __launch_bounds__(256, 3) k_render_mega(const MegaArgs A) {
     const DevScene S = stage_scene<SMEM>(A.scene);
     const DevParams& P = A.p;
     const uint32_t lane = threadIdx.x & 31u;
-    // per-lane path state
     V3 o = mk(0, 0, 0), d = mk(0, 0, 1), atten = mk(1, 1, 1), color = mk(0, 0, 0);
     uint32_t pixel = 0, px = 0, py = 0, s_cur = 0, s_end = 0, remain = 0, k = 0;
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
@@ -73,7 +75,28 @@ __global__ void __launch_bounds__(256, 2) k_render_mega(const MegaArgs A) {
     EventCounters ec; ec.node_visits = ec.sphere_tests = ec.quad_tests = 0;
 
     for (;;) {
-        // ---- work fetch for lanes whose chunk is finished (warp-aggregated atomic)
+        // ---- T: cpu.rs:48
+        Hit h; h.t = TRT_INF; h.ref = TRT_REF_INVALID;
+        if (alive) { h = closest_hit<ORDERED, SMEM, COUNT>(S, o, d, P.t_min, &ec); ++n_rays; }
+        // ---- S1: cpu.rs:49-61 up to the scatter decision
+        Surface sf; sf.kind = TRT_MAT_LIGHT; sf.front = false; sf.param = 0.f;
+        sf.point = sf.normal = sf.rgb = mk(0, 0, 0);
+        bool scatter = false;
+        if (alive) {
+            if (h.ref == TRT_REF_INVALID) color = color + atten * mk(P.bg[0], P.bg[1], P.bg[2]);
+            else {
+                sf = hit_record<SMEM>(S, h, o, d);
+                V3 emission = (sf.kind == TRT_MAT_LIGHT) ? sf.rgb : mk(0.0f, 0.0f, 0.0f);
+                color = color + atten * emission;
+                // a scattered ray is only traced while bounces remain (cpu.rs:47,54): the last scatter is never used
+                scatter = sf.kind != TRT_MAT_LIGHT && remain > 1;
+            }
+            if (!scatter) {       // imager.rs:50 (f64 here)
+                acc0 += (double)color.x; acc1 += (double)color.y; acc2 += (double)color.z;
+                alive = false; ++s_cur; ++n_paths;
+            }
+        }
+        // ---- S2: work fetch for lanes whose chunk is finished (warp-aggregated atomic)
         bool need_item = !alive && !done && s_cur == s_end;
         unsigned m = __ballot_sync(0xFFFFFFFFu, need_item);
         if (m) {
@@ -94,30 +117,28 @@ __global__ void __launch_bounds__(256, 2) k_render_mega(const MegaArgs A) {
                     if (decode_item(A, item, &px, &py, &s0, &s1)) {
                         pixel = py * P.width + px; s_cur = s0; s_end = s1; has_item = true;
                         acc0 = acc1 = acc2 = 0.0;
+                        if (P.max_bounces == 0) { n_paths += s1 - s0; s_cur = s1; }      // no ray is ever cast (cpu.rs:47)
                     }   // else: padding item outside the image, fetch again next round
                 } else done = true;
             }
         }
-        // ---- path regeneration: pointgen.rs:37-52
-        if (!alive && !done && s_cur < s_end) {
-            primary_ray(A.cam, P, px, py, pixel, P.sample_offset + s_cur, &o, &d);
-            atten = mk(1, 1, 1); color = mk(0, 0, 0); remain = P.max_bounces; k = 0;
-            alive = remain > 0;
-            if (!alive) { ++s_cur; ++n_paths; }      // max_bounces == 0: the path contributes nothing
+        // ---- S3: the next ray of every lane that scatters (material/*.rs) or starts a new path (pointgen.rs:37-52)
+        bool regen = !alive && !done && s_cur < s_end;
+        if (scatter || regen) {
+            uint32_t sample = P.sample_offset + s_cur;
+            if (scatter) ++k; else k = 0;
+            U4 r = philox4x32_10(pixel, sample, k, 0u, P.seed_lo, P.seed_hi);
+            V3 dir;
+            if (scatter) {
+                dir = scatter_direction(sf, d, r);
+                atten = atten * sf.rgb; o = sf.point; --remain;                           // cpu.rs:52-54
+            } else {
+                camera_ray(A.cam, P, px, py, pixel, sample, r, &o, &dir);
+                atten = mk(1, 1, 1); color = mk(0, 0, 0); remain = P.max_bounces; alive = true;
+            }
+            d = normalized(dir);                                                         // Ray::new, ray.rs:12-14
         }
         if (__all_sync(0xFFFFFFFFu, done)) break;
-        // ---- one ray segment: cpu.rs:47-62
-        if (alive) {
-            Hit h = closest_hit<ORDERED, SMEM, COUNT>(S, o, d, P.t_min, &ec);
-            ++n_rays;
-            bool cont;
-            if (h.ref == TRT_REF_INVALID) { color = color + atten * mk(P.bg[0], P.bg[1], P.bg[2]); cont = false; }
-            else { ++k; cont = shade<SMEM>(S, P, h, pixel, P.sample_offset + s_cur, k, &o, &d, &atten, &color); if (cont) { --remain; cont = remain > 0; } }
-            if (!cont) {
-                acc0 += (double)color.x; acc1 += (double)color.y; acc2 += (double)color.z;
-                alive = false; ++s_cur; ++n_paths;
-            }
-        }
     }
     // ---- statistics: one atomic per warp
     unsigned long long r = n_rays, pth = n_paths;
@@ -257,14 +278,14 @@ size_t scene_smem_bytes(const SceneView& v) {
 }
 
 template <bool ORDERED, bool SMEM, bool COUNT>
-static cudaError_t launch_mega_t(const MegaArgs& A, int grid, size_t smem, cudaStream_t st) {
+static cudaError_t mega_fn(const void** fn, int* blocks_per_sm, size_t smem) {
     auto kern = k_render_mega<ORDERED, SMEM, COUNT>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<grid, 256, smem, st>>>(A);
-    return cudaGetLastError();
+    *fn = (const void*)kern;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, 256, smem);
 }
 
 cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const trt_params& p, double* d_sum64,
@@ -272,7 +293,19 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     MegaArgs A;
     A.scene = dev_scene(v); A.cam = dev_camera(cam); A.p = dev_params(p);
     A.sum64 = d_sum64; A.counters = d_counters; A.next_item = d_next_item;
-    const int blocks_per_sm = 2, threads = 256;
+    size_t smem = scene_smem_bytes(v);
+    bool use_smem = smem <= 64 * 1024;
+    if (!use_smem) smem = 0;
+    bool count = (p.flags & 1u) != 0, ordered = v.ordered != 0;
+    const void* fn = nullptr; int blocks_per_sm = 0; cudaError_t e;
+    if (ordered) { if (use_smem) e = count ? mega_fn<true, true, true>(&fn, &blocks_per_sm, smem) : mega_fn<true, true, false>(&fn, &blocks_per_sm, smem);
+                   else e = count ? mega_fn<true, false, true>(&fn, &blocks_per_sm, smem) : mega_fn<true, false, false>(&fn, &blocks_per_sm, smem); }
+    else { if (use_smem) e = count ? mega_fn<false, true, true>(&fn, &blocks_per_sm, smem) : mega_fn<false, true, false>(&fn, &blocks_per_sm, smem);
+           else e = count ? mega_fn<false, false, true>(&fn, &blocks_per_sm, smem) : mega_fn<false, false, false>(&fn, &blocks_per_sm, smem); }
+    if (e != cudaSuccess) return e;
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    // persistent grid: every SM filled to the kernel's occupancy limit, one wave
+    const int threads = 256;
     int grid = sm_count * blocks_per_sm;
     uint64_t resident = (uint64_t)grid * threads;
     uint64_t pixels = (uint64_t)p.width * p.height;
@@ -290,15 +323,8 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     uint64_t n_items = (uint64_t)A.tiles_x * A.tiles_y * 32ull * A.n_chunks;
     if (n_items > 0xFFFFFFF0ull - resident) return cudaErrorInvalidValue;
     A.n_items = (uint32_t)n_items;
-    size_t smem = scene_smem_bytes(v);
-    bool use_smem = smem <= 64 * 1024;
-    bool count = (p.flags & 1u) != 0, ordered = v.ordered != 0;
-#define TRT_DISPATCH(O, S, C) return launch_mega_t<O, S, C>(A, grid, (S) ? smem : 0, st)
-    if (ordered) { if (use_smem) { if (count) TRT_DISPATCH(true, true, true); else TRT_DISPATCH(true, true, false); }
-                   else { if (count) TRT_DISPATCH(true, false, true); else TRT_DISPATCH(true, false, false); } }
-    else { if (use_smem) { if (count) TRT_DISPATCH(false, true, true); else TRT_DISPATCH(false, true, false); }
-           else { if (count) TRT_DISPATCH(false, false, true); else TRT_DISPATCH(false, false, false); } }
-#undef TRT_DISPATCH
+    void* args[] = {(void*)&A};
+    return cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, st);
 }
 
 cudaError_t launch_aov(const SceneView& v, const trt_camera& cam, const trt_params& p, uint32_t* d_prim, float* d_t,
