@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtrt_b200.so")
 
 TRT_OK = 0
-BVH_REFERENCE, BVH_SAH = 0, 1
+BVH_REFERENCE, BVH_SAH, BVH_FLAT, BVH_AUTO = 0, 1, 2, 3
 VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT = 0, 1
 FLAG_COUNT_EVENTS = 1
 

@@ -20,7 +20,7 @@ import numpy as np
 from . import _lib as L
 from .scenes import SceneDesc, LAMBERTIAN, METAL, DIELECTRIC, LIGHT, SPHERE, QUAD
 
-BVH_REFERENCE, BVH_SAH = L.BVH_REFERENCE, L.BVH_SAH
+BVH_REFERENCE, BVH_SAH, BVH_FLAT, BVH_AUTO = L.BVH_REFERENCE, L.BVH_SAH, L.BVH_FLAT, L.BVH_AUTO
 VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT = L.VARIANT_MEGAKERNEL, L.VARIANT_WAVEFRONT
 
 

@@ -152,7 +152,7 @@ int trt_scene_num_prims(trt_scene* s, uint32_t* out) { if (!s || !out) return fa
 int trt_scene_commit(trt_scene* s, int bvh_kind) {
     if (!s) return fail(TRT_ERR_INVALID, "trt_scene_commit: null scene");
     std::string err;
-    if (!s->host.commit(bvh_kind, &err)) return fail(bvh_kind == 0 || bvh_kind == 1 ? TRT_ERR_UNSUPPORTED : TRT_ERR_INVALID, err);
+    if (!s->host.commit(bvh_kind, &err)) return fail(bvh_kind >= 0 && bvh_kind <= 3 ? TRT_ERR_UNSUPPORTED : TRT_ERR_INVALID, err);
     return TRT_OK;
 }
 int trt_scene_leaf_ranks(trt_scene* s, uint32_t* rank) {
@@ -179,19 +179,20 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
     DeviceCopy& dc = s->on_device[c->device];
     if (dc.buf && dc.version == s->host.version) return TRT_OK;
     const trt::FlatScene& f = s->host.flat;
-    size_t sz[6] = {f.nodes.size() * 16, f.spheres.size() * 16, f.quads.size() * 16, f.sphere_meta.size() * 16, f.quad_meta.size() * 16, f.materials.size() * 16};
-    const void* src[6] = {f.nodes.data(), f.spheres.data(), f.quads.data(), f.sphere_meta.data(), f.quad_meta.data(), f.materials.data()};
-    size_t off[6], total = 0;
-    for (int i = 0; i < 6; ++i) { off[i] = total; total += align_up(sz[i] ? sz[i] : 16); }
+    size_t sz[7] = {f.nodes.size() * 16, f.spheres.size() * 16, f.quads.size() * 16, f.sphere_meta.size() * 16, f.quad_meta.size() * 16, f.materials.size() * 16, f.flat.size() * 16};
+    const void* src[7] = {f.nodes.data(), f.spheres.data(), f.quads.data(), f.sphere_meta.data(), f.quad_meta.data(), f.materials.data(), f.flat.data()};
+    size_t off[7], total = 0;
+    for (int i = 0; i < 7; ++i) { off[i] = total; total += align_up(sz[i] ? sz[i] : 16); }
     if (dc.buf && dc.bytes < total) { cudaFree(dc.buf); dc.buf = nullptr; }
     if (!dc.buf) { CU(cudaMalloc(&dc.buf, total)); dc.bytes = total; }
-    for (int i = 0; i < 6; ++i) if (sz[i]) CU(cudaMemcpyAsync((char*)dc.buf + off[i], src[i], sz[i], cudaMemcpyHostToDevice, c->stream));
+    for (int i = 0; i < 7; ++i) if (sz[i]) CU(cudaMemcpyAsync((char*)dc.buf + off[i], src[i], sz[i], cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     trtk::SceneView& v = dc.view;
     char* b = (char*)dc.buf;
     v.nodes = b + off[0]; v.spheres = b + off[1]; v.quads = b + off[2]; v.sphere_meta = b + off[3]; v.quad_meta = b + off[4]; v.materials = b + off[5];
     v.root = f.root; v.n_nodes = f.n_nodes; v.n_spheres = (uint32_t)f.spheres.size(); v.n_quads = (uint32_t)f.quad_meta.size();
-    v.n_materials = (uint32_t)(f.materials.size() / 2); v.ordered = f.bvh_kind == TRT_BVH_SAH ? 1u : 0u;
+    v.n_materials = (uint32_t)(f.materials.size() / 2); v.kind = (uint32_t)f.bvh_kind;
+    v.flat = f.flat.empty() ? nullptr : b + off[6]; v.flat_host = f.flat.empty() ? nullptr : f.flat.data(); v.n_flat = (uint32_t)(f.flat.size() / 6);
     const float inf = std::numeric_limits<float>::infinity();
     for (int i = 0; i < 3; ++i) { v.root_min[i] = inf; v.root_max[i] = -inf; }
     for (const trt::HostPrim& p : s->host.prims)

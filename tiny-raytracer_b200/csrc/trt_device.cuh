@@ -112,9 +112,11 @@ TRT_DEV V3 random_in_unit_sphere(float u1, float u2, float u3, bool use_r) {
 }
 
 // ------------------------------------------------------------------ scene access
+struct FlatPrim;
 struct DevScene {
     const float4* nodes; const float4* spheres; const float4* quads;
     const uint4* sphere_meta; const uint4* quad_meta; const float4* materials;
+    const FlatPrim* flat; uint32_t n_flat;      // TRT_BVH_FLAT: primitives in reference leaf order (else null / 0)
     uint32_t root, n_nodes, n_spheres, n_quads, n_materials, ordered;
     float root_min[3], root_max[3];   // the root's own padded box (only consulted when counting events)
 };
@@ -170,6 +172,24 @@ TRT_DEV void slab(float mnx, float mny, float mnz, float mxx, float mxy, float m
     }
     *start_out = start; *end_out = end;
 }
+// The same function for rays that cannot produce a NaN in (plane - o) * inv — finite origin, finite non-zero 1/d on all
+// three axes (`ray_is_tame`): then t0, t1 are ordered numbers, the conditional swap is min/max and the conditional
+// updates are max/min, so FMNMX gives bit-identical start/end with a third of the instructions. Every other ray
+// (a zero or denormal direction component, NaN/inf anywhere) takes slab() above.
+TRT_DEV void slab_tame(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, V3 o, V3 inv, float t_min,
+                       float* start_out, float* end_out) {
+    float ax = (mnx - o.x) * inv.x, bx = (mxx - o.x) * inv.x;
+    float ay = (mny - o.y) * inv.y, by = (mxy - o.y) * inv.y;
+    float az = (mnz - o.z) * inv.z, bz = (mxz - o.z) * inv.z;
+    *start_out = fmaxf(fmaxf(t_min, fminf(ax, bx)), fmaxf(fminf(ay, by), fminf(az, bz)));
+    *end_out = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+}
+TRT_DEV bool finite_nonzero(float x) { float a = fabsf(x); return a > 0.0f && a < TRT_INF; }
+TRT_DEV bool ray_is_tame(V3 o, V3 inv) {
+    return finite_nonzero(inv.x) && finite_nonzero(inv.y) && finite_nonzero(inv.z) &&
+           fabsf(o.x) < TRT_INF && fabsf(o.y) < TRT_INF && fabsf(o.z) < TRT_INF;
+}
+TRT_DEV float rcp_approx(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // ------------------------------------------------------------------ primitives
 // Sphere::hit, hittable/sphere.rs:29-45. Returns t in [t_min, hi) or NaN-free "miss" as false.
@@ -190,12 +210,19 @@ template <bool SMEM> TRT_DEV bool sphere_hit(const DevScene& S, uint32_t idx, V3
     *t_out = t; return true;
 }
 // Quad::hit, hittable/quad.rs:33-41
-template <bool SMEM> TRT_DEV bool quad_hit(const DevScene& S, uint32_t idx, V3 o, V3 d, float t_min, float hi, float* t_out) {
+// `hi` is the range end of the reference's `contains`; `hi_cut` (>= any t the caller could still accept) only feeds the pre-reject.
+template <bool SMEM> TRT_DEV bool quad_hit(const DevScene& S, uint32_t idx, V3 o, V3 d, float t_min, float hi, float hi_cut, float* t_out) {
     const float4* q = S.quads + 4 * (size_t)idx;
     float4 q0 = ld4<SMEM>(q);
     V3 n = mk(q0.x, q0.y, q0.z);
     float dir_norm = dot(d, n);
-    float t = (q0.w - dot(o, n)) / dir_norm;
+    float num = q0.w - dot(o, n);
+    // Cheap conservative reject before the IEEE division: num * rcp.approx(dn) is within 2^-22 relative of the exact
+    // quotient, so a value clearly outside [t_min, hi) means the exact t is outside too. This removes the division
+    // (and its slow path for num == 0) for the common case of a ray leaving the very quad it starts on.
+    float ta = num * rcp_approx(dir_norm);
+    if (ta < t_min - fabsf(t_min) * 1e-6f || ta > hi_cut + fabsf(hi_cut) * 1e-6f) return false;
+    float t = num / dir_norm;
     if (!(t_min <= t && t < hi)) return false;
     float4 q1 = ld4<SMEM>(q + 1), q2 = ld4<SMEM>(q + 2), q3 = ld4<SMEM>(q + 3);
     V3 p = ray_at(o, d, t) - mk(q1.x, q1.y, q1.z);
@@ -227,6 +254,7 @@ TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounter
     if (cur == TRT_REF_INVALID) return best;
     uint32_t best_rank = 0xFFFFFFFFu;
     const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);   // aabb.rs:42, identical for every node of this ray
+    const bool tame = ray_is_tame(o, inv);
     uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
     int sp = 0;
     if (COUNT) {
@@ -242,8 +270,13 @@ TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounter
             float4 n0 = ld4<SMEM>(np), n1 = ld4<SMEM>(np + 1), n2 = ld4<SMEM>(np + 2), n3 = ld4<SMEM>(np + 3);
             uint32_t lref = __float_as_uint(n3.x), rref = __float_as_uint(n3.y);
             float sl, el, sr, er;
-            slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, &sl, &el);
-            slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, &sr, &er);
+            if (tame) {
+                slab_tame(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, &sl, &el);
+                slab_tame(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, &sr, &er);
+            } else {
+                slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, &sl, &el);
+                slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, &sr, &er);
+            }
             if (COUNT) ec->node_visits += (rref == TRT_REF_INVALID) ? 0u : 2u;   // left.hit + right.hit
             bool pl, pr;
             if (ORDERED) { pl = el > sl && !(best.t < sl); pr = er > sr && !(best.t < sr); }
@@ -263,7 +296,7 @@ TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounter
             // ---- region B: one primitive (sphere.rs:29-45 / quad.rs:33-41)
             uint32_t idx = cur & TRT_REF_INDEX_MASK;
             float t; bool h;
-            if (cur & TRT_REF_QUAD) { if (COUNT) ec->quad_tests++; h = quad_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : best.t, &t); }
+            if (cur & TRT_REF_QUAD) { if (COUNT) ec->quad_tests++; h = quad_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : best.t, best.t, &t); }
             else { if (COUNT) ec->sphere_tests++; h = sphere_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : best.t, &t); }
             if (h) {
                 if (!ORDERED) { best.t = t; best.ref = cur; }
@@ -380,14 +413,139 @@ TRT_DEV bool shade(const DevScene& S, const DevParams& P, Hit h, uint32_t pixel,
     return true;
 }
 
+// ------------------------------------------------------------------ flat list (TRT_BVH_FLAT): closest hit without a tree
+// For scenes of at most TRT_FLAT_MAX primitives the tree is replaced by the list of primitives in the reference tree's
+// left-to-right leaf order. The reference's Node::hit is then exactly a scan of that list with the running closest hit
+// as range end (every ancestor box contains the leaf box, so only the leaf's own box test can cull).
+// A SIMT machine runs that scan with zero control divergence, because every lane tests primitive i in iteration i:
+//   phase A  (uniform loop, data from the kernel-parameter bank): the ray parameter t_i of every primitive — plane t of a
+//            quad, near/far root of a sphere — or +inf when out of [t_min, inf); kept in a per-thread shared-memory column.
+//   phase B  (per lane): take candidates in increasing (t, rank) order; the first one that also passes the inside test
+//            (quad.rs:39-41) and its own padded-box test (bvh.rs:89) is the (t, rank)-smallest valid primitive W.
+//            If W's box entry does not exceed its t — always, except for fp-cancellation on grazing hits — the
+//            reference's scan returns W whatever it visited before (nothing valid is closer; a tie is lower-ranked);
+//            otherwise the lane replays the reference's scan literally (flat_scan_reference).
+struct FlatPrim { float4 g0, g1, g2, g3, b0, b1; };   // geometry as in trt_layout.h; b0 = (bmin, ref bits), b1 = (bmax, 0)
+
+template <bool DSMEM> TRT_DEV float4 ldf(const float4* p) { return ld4<DSMEM>(p); }
+
+// the reference's scan, literally: used only when the closest valid primitive is culled-or-not depending on the range end
+template <bool DSMEM>
+TRT_DEV Hit flat_scan_reference(const FlatPrim* Dv, uint32_t n, V3 o, V3 d, V3 inv, float t_min) {
+    Hit best; best.t = TRT_INF; best.ref = TRT_REF_INVALID;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float4* p = (const float4*)(Dv + i);
+        float4 b0 = ldf<DSMEM>(p + 4), b1 = ldf<DSMEM>(p + 5);
+        float s, e;
+        slab(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, o, inv, t_min, &s, &e);
+        if (!(e > s && best.t > s)) continue;
+        uint32_t ref = __float_as_uint(b0.w);
+        float4 g0 = ldf<DSMEM>(p);
+        float t;
+        if (ref & TRT_REF_QUAD) {
+            V3 nrm = mk(g0.x, g0.y, g0.z);
+            t = (g0.w - dot(o, nrm)) / dot(d, nrm);
+            if (!(t_min <= t && t < best.t)) continue;
+            float4 g1 = ldf<DSMEM>(p + 1), g2 = ldf<DSMEM>(p + 2), g3 = ldf<DSMEM>(p + 3);
+            V3 pp = ray_at(o, d, t) - mk(g1.x, g1.y, g1.z);
+            V3 w = mk(g1.w, g2.w, g3.w);
+            float px = dot(cross(pp, mk(g3.x, g3.y, g3.z)), w), py = dot(cross(mk(g2.x, g2.y, g2.z), pp), w);
+            if (!(0.0f <= px && px < 1.0f && 0.0f <= py && py < 1.0f)) continue;
+        } else {
+            V3 oc = o - mk(g0.x, g0.y, g0.z);
+            float a = dot(d, d), half_b = dot(oc, d), c = dot(oc, oc) - g0.w * g0.w;
+            float disc = half_b * half_b - a * c;
+            if (disc < 0.0f) continue;
+            float sq = sqrtf(disc);
+            t = (-half_b - sq) / a;
+            if (!(t_min <= t && t < best.t)) { t = (-half_b + sq) / a; if (!(t_min <= t && t < best.t)) continue; }
+        }
+        best.t = t; best.ref = ref;
+    }
+    return best;
+}
+
+// U: the list as seen by uniform (same-address) loads; Dv: the same list for per-lane indexed loads; tt: this thread's
+// scratch column, element i at tt[i * tt_stride].
+template <bool DSMEM>
+TRT_DEV Hit closest_hit_flat(const FlatPrim* __restrict__ U, const FlatPrim* Dv, uint32_t n, float* tt, uint32_t tt_stride,
+                             V3 o, V3 d, float t_min) {
+    Hit best; best.t = TRT_INF; best.ref = TRT_REF_INVALID;
+    const float a = dot(d, d);                       // sphere.rs:31, the same for every sphere
+    float m = TRT_INF; uint32_t mi = 0;
+    // ---- phase A
+    for (uint32_t i = 0; i < n; ++i) {
+        const float4 g0 = U[i].g0;
+        const uint32_t ref = __float_as_uint(U[i].b0.w);
+        float t;
+        if (ref & TRT_REF_QUAD) {                    // quad.rs:34-36
+            V3 nrm = mk(g0.x, g0.y, g0.z);
+            t = (g0.w - dot(o, nrm)) / dot(d, nrm);
+            if (!(t_min <= t && t < TRT_INF)) t = TRT_INF;
+        } else {                                     // sphere.rs:30-45 with an open range end
+            V3 oc = o - mk(g0.x, g0.y, g0.z);
+            float half_b = dot(oc, d), c = dot(oc, oc) - g0.w * g0.w;
+            float disc = half_b * half_b - a * c;
+            t = TRT_INF;
+            if (!(disc < 0.0f)) {
+                float sq = sqrtf(disc);
+                float t0 = (-half_b - sq) / a;
+                if (t_min <= t0 && t0 < TRT_INF) t = t0;
+                else { float t1 = (-half_b + sq) / a; if (t_min <= t1 && t1 < TRT_INF) t = t1; }
+            }
+        }
+        tt[i * tt_stride] = t;
+        if (t < m) { m = t; mi = i; }                // ties keep the lower rank
+    }
+    if (!(m < TRT_INF)) return best;
+    // ---- phase B
+    const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    for (;;) {
+        const float4* p = (const float4*)(Dv + mi);
+        float4 b0 = ldf<DSMEM>(p + 4), b1 = ldf<DSMEM>(p + 5);
+        uint32_t ref = __float_as_uint(b0.w);
+        bool valid = true;
+        if (ref & TRT_REF_QUAD) {                    // quad.rs:38-41
+            float4 g1 = ldf<DSMEM>(p + 1), g2 = ldf<DSMEM>(p + 2), g3 = ldf<DSMEM>(p + 3);
+            V3 pp = ray_at(o, d, m) - mk(g1.x, g1.y, g1.z);
+            V3 w = mk(g1.w, g2.w, g3.w);
+            float px = dot(cross(pp, mk(g3.x, g3.y, g3.z)), w), py = dot(cross(mk(g2.x, g2.y, g2.z), pp), w);
+            valid = 0.0f <= px && px < 1.0f && 0.0f <= py && py < 1.0f;
+        }
+        if (valid) {
+            float s, e;
+            slab(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, o, inv, t_min, &s, &e);   // the leaf's own box (bvh.rs:89)
+            if (e > s) {
+                if (s > m) return flat_scan_reference<DSMEM>(Dv, n, o, d, inv, t_min);
+                best.t = m; best.ref = ref;
+                return best;
+            }
+        }
+        tt[mi * tt_stride] = TRT_INF;                // not a hit: next candidate in (t, rank) order
+        m = TRT_INF;
+        for (uint32_t i = 0; i < n; ++i) { float t = tt[i * tt_stride]; if (t < m) { m = t; mi = i; } }
+        if (!(m < TRT_INF)) return best;
+    }
+}
+
 // One whole path: CpuSampler::single_point_sampling, renderer/sampler/cpu.rs:39-65
-template <bool ORDERED, bool SMEM, bool COUNT>
+// KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH, 2 = TRT_BVH_FLAT
+template <int KIND, bool SMEM, bool COUNT>
+TRT_DEV Hit closest_hit_any(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
+    if (KIND == 2) {
+        float tt[TRT_FLAT_MAX];
+        return closest_hit_flat<false>(S.flat, S.flat, S.n_flat, tt, 1u, o, d, t_min);
+    }
+    return closest_hit<KIND == 1, SMEM, COUNT>(S, o, d, t_min, ec);
+}
+
+template <int KIND, bool SMEM, bool COUNT>
 TRT_DEV V3 trace_path(const DevScene& S, const DevParams& P, V3 o, V3 d, uint32_t pixel, uint32_t sample,
                       uint32_t* n_rays_out, Hit* first_hit, EventCounters* ec) {
     V3 color = mk(0.f, 0.f, 0.f), atten = mk(1.f, 1.f, 1.f);
     uint32_t remain = P.max_bounces, k = 0, rays = 0;
     while (remain > 0) {
-        Hit h = closest_hit<ORDERED, SMEM, COUNT>(S, o, d, P.t_min, ec);
+        Hit h = closest_hit_any<KIND, SMEM, COUNT>(S, o, d, P.t_min, ec);
         ++rays;
         if (rays == 1 && first_hit) *first_hit = h;
         if (h.ref == TRT_REF_INVALID) { color = color + atten * mk(P.bg[0], P.bg[1], P.bg[2]); break; }   // cpu.rs:58-61

@@ -1,8 +1,10 @@
 // trt_kernels.cu — sm_100a kernels of the path-tracing hot path and their launchers.
 //
-//   k_render_mega   persistent-thread megakernel: every lane owns a work item (pixel, sample chunk), runs
-//                   generate -> [closest_hit -> shade]* for one path after another (path regeneration per lane),
-//                   keeps the chunk's f64 sum in registers and adds it to the per-pixel accumulator once.
+//   k_render_mega / k_render_mega_flat
+//                   persistent-thread megakernel: every lane owns a work item (pixel, sample chunk) and alternates
+//                   T (one closest-hit query) and S (shade-or-regenerate); the chunk's f64 sum stays in registers and
+//                   is added to the per-pixel accumulator once. The _flat entry carries the primitive list of a
+//                   TRT_BVH_FLAT scene in its kernel parameters (constant bank) for the uniform phase-A loop.
 //   k_aov           one thread per (pixel, sample): primary-hit AOV (+ optional whole-path radiance / ray count)
 //   k_sample_batch  the reference's Sampler trait on a batch of caller-supplied rays
 //   k_trace         closest hit for arbitrary rays
@@ -14,11 +16,13 @@
 
 using namespace trtd;
 
-// ------------------------------------------------------------------ shared-memory staging of small scenes
-struct SmemPlan { uint32_t nodes_f4, spheres_f4, quads_f4, smeta_u4, qmeta_u4, mats_f4; };
+#define MEGA_THREADS 256
 
+// ------------------------------------------------------------------ shared-memory staging of small scenes
+// layout: [nodes | spheres | quads | sphere_meta | quad_meta | materials | flat list | per-thread phase-A columns]
 template <bool SMEM>
-__device__ __forceinline__ DevScene stage_scene(const DevScene& G) {
+__device__ __forceinline__ DevScene stage_scene(const DevScene& G, float** tt_out) {
+    *tt_out = nullptr;
     if (!SMEM) return G;
     extern __shared__ float4 smem_f4[];
     DevScene S = G;
@@ -35,6 +39,8 @@ __device__ __forceinline__ DevScene stage_scene(const DevScene& G) {
     S.sphere_meta = (const uint4*)copy((const float4*)G.sphere_meta, G.n_spheres);
     S.quad_meta = (const uint4*)copy((const float4*)G.quad_meta, G.n_quads);
     S.materials = copy(G.materials, 2 * G.n_materials);
+    S.flat = (const FlatPrim*)copy((const float4*)G.flat, 6 * G.n_flat);
+    *tt_out = (float*)(smem_f4 + off) + threadIdx.x;     // column of this thread, stride blockDim.x
     __syncthreads();
     return S;
 }
@@ -47,6 +53,7 @@ struct MegaArgs {
     unsigned int* next_item;       // work counter
     uint32_t chunk, n_chunks, tiles_x, tiles_y, n_items;
 };
+struct FlatList { FlatPrim prim[TRT_FLAT_MAX]; };
 
 // item -> (pixel, sample range). Items are ordered chunk-major over 8x4 pixel tiles, 32 consecutive items = one tile.
 __device__ __forceinline__ bool decode_item(const MegaArgs& A, uint32_t item, uint32_t* x, uint32_t* y, uint32_t* s0, uint32_t* s1) {
@@ -62,9 +69,11 @@ __device__ __forceinline__ bool decode_item(const MegaArgs& A, uint32_t item, ui
 // Loop body = T (one ray segment for every live lane) then S (shade-or-regenerate, fused so that the scattering lanes
 // and the lanes starting a new path share ONE Philox call, ONE normalisation and the work-fetch point; every lane that
 // still has work leaves S with a live ray, so T always runs with full lanes until the work counter runs dry).
-template <bool ORDERED, bool SMEM, bool COUNT>
-__global__ void __launch_bounds__(256, 3) k_render_mega(const MegaArgs A) {
-    const DevScene S = stage_scene<SMEM>(A.scene);
+// KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH, 2 = TRT_BVH_FLAT (U = the list in the constant bank).
+template <int KIND, bool SMEM, bool COUNT>
+__device__ __forceinline__ void mega_body(const MegaArgs& A, const FlatPrim* U) {
+    float* tt;
+    const DevScene S = stage_scene<SMEM>(A.scene, &tt);
     const DevParams& P = A.p;
     const uint32_t lane = threadIdx.x & 31u;
     V3 o = mk(0, 0, 0), d = mk(0, 0, 1), atten = mk(1, 1, 1), color = mk(0, 0, 0);
@@ -77,7 +86,11 @@ __global__ void __launch_bounds__(256, 3) k_render_mega(const MegaArgs A) {
     for (;;) {
         // ---- T: cpu.rs:48
         Hit h; h.t = TRT_INF; h.ref = TRT_REF_INVALID;
-        if (alive) { h = closest_hit<ORDERED, SMEM, COUNT>(S, o, d, P.t_min, &ec); ++n_rays; }
+        if (alive) {
+            if (KIND == 2) h = closest_hit_flat<true>(U, S.flat, S.n_flat, tt, MEGA_THREADS, o, d, P.t_min);
+            else h = closest_hit<KIND == 1, SMEM, COUNT>(S, o, d, P.t_min, &ec);
+            ++n_rays;
+        }
         // ---- S1: cpu.rs:49-61 up to the scatter decision
         Surface sf; sf.kind = TRT_MAT_LIGHT; sf.front = false; sf.param = 0.f;
         sf.point = sf.normal = sf.rgb = mk(0, 0, 0);
@@ -151,13 +164,26 @@ __global__ void __launch_bounds__(256, 3) k_render_mega(const MegaArgs A) {
     }
 }
 
+template <int KIND, bool SMEM, bool COUNT>
+__global__ void __launch_bounds__(MEGA_THREADS, 3) k_render_mega(const __grid_constant__ MegaArgs A) {
+    mega_body<KIND, SMEM, COUNT>(A, nullptr);
+}
+__global__ void __launch_bounds__(MEGA_THREADS, 3) k_render_mega_flat(const __grid_constant__ MegaArgs A, const __grid_constant__ FlatList L) {
+    mega_body<2, true, false>(A, L.prim);
+}
+
 // ------------------------------------------------------------------ AOV / sample batch / trace
 struct AovArgs {
     DevScene scene; DevCamera cam; DevParams p;
     uint32_t* prim_id; float* t; float* radiance; uint32_t* n_rays;
     unsigned long long total;   // W*H*spp
 };
-template <bool ORDERED>
+__device__ __forceinline__ uint32_t prim_id_of(const DevScene& S, uint32_t ref) {
+    if (ref == TRT_REF_INVALID) return 0xFFFFFFFFu;
+    uint32_t idx = ref & TRT_REF_INDEX_MASK;
+    return (ref & TRT_REF_QUAD) ? S.quad_meta[idx].z : S.sphere_meta[idx].z;
+}
+template <int KIND>
 __global__ void __launch_bounds__(128) k_aov(const AovArgs A) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.total) return;
@@ -170,48 +196,36 @@ __global__ void __launch_bounds__(128) k_aov(const AovArgs A) {
     if (!A.radiance && !A.n_rays) Q.max_bounces = P.max_bounces ? 1u : 0u;
     Hit first; first.t = TRT_INF; first.ref = TRT_REF_INVALID;
     uint32_t nr = 0; EventCounters ec;
-    V3 col = trace_path<ORDERED, false, false>(S, Q, o, d, pixel, sample, &nr, &first, &ec);
-    if (A.prim_id) {
-        uint32_t id = 0xFFFFFFFFu;
-        if (first.ref != TRT_REF_INVALID) {
-            uint32_t idx = first.ref & TRT_REF_INDEX_MASK;
-            id = (first.ref & TRT_REF_QUAD) ? S.quad_meta[idx].z : S.sphere_meta[idx].z;
-        }
-        A.prim_id[i] = id;
-    }
+    V3 col = trace_path<KIND, false, false>(S, Q, o, d, pixel, sample, &nr, &first, &ec);
+    if (A.prim_id) A.prim_id[i] = prim_id_of(S, first.ref);
     if (A.t) A.t[i] = first.t;
     if (A.radiance) { A.radiance[3 * i] = col.x; A.radiance[3 * i + 1] = col.y; A.radiance[3 * i + 2] = col.z; }
     if (A.n_rays) A.n_rays[i] = nr;
 }
 
 struct BatchArgs { DevScene scene; DevParams p; const trt_sample_point_pod* in; trt_sampled_color_pod* out; unsigned long long n; };
-template <bool ORDERED>
+template <int KIND>
 __global__ void __launch_bounds__(128) k_sample_batch(const BatchArgs A) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n) return;
     trt_sample_point_pod sp = A.in[i];
     uint32_t pixel = sp.y * A.p.width + sp.x;
     EventCounters ec;
-    V3 col = trace_path<ORDERED, false, false>(A.scene, A.p, mk(sp.o[0], sp.o[1], sp.o[2]), mk(sp.d[0], sp.d[1], sp.d[2]), pixel,
-                                               A.p.sample_offset + (uint32_t)i, nullptr, nullptr, &ec);
+    V3 col = trace_path<KIND, false, false>(A.scene, A.p, mk(sp.o[0], sp.o[1], sp.o[2]), mk(sp.d[0], sp.d[1], sp.d[2]), pixel,
+                                            A.p.sample_offset + (uint32_t)i, nullptr, nullptr, &ec);
     trt_sampled_color_pod c; c.x = sp.x; c.y = sp.y; c.c[0] = col.x; c.c[1] = col.y; c.c[2] = col.z;
     A.out[i] = c;
 }
 
 struct TraceArgs { DevScene scene; const float* o; const float* d; float t_min; uint32_t* prim_id; float* t; unsigned long long n; };
-template <bool ORDERED>
+template <int KIND>
 __global__ void __launch_bounds__(128) k_trace(const TraceArgs A) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n) return;
     EventCounters ec;
-    Hit h = closest_hit<ORDERED, false, false>(A.scene, mk(A.o[3 * i], A.o[3 * i + 1], A.o[3 * i + 2]),
-                                               mk(A.d[3 * i], A.d[3 * i + 1], A.d[3 * i + 2]), A.t_min, &ec);
-    uint32_t id = 0xFFFFFFFFu;
-    if (h.ref != TRT_REF_INVALID) {
-        uint32_t idx = h.ref & TRT_REF_INDEX_MASK;
-        id = (h.ref & TRT_REF_QUAD) ? A.scene.quad_meta[idx].z : A.scene.sphere_meta[idx].z;
-    }
-    A.prim_id[i] = id; A.t[i] = h.t;
+    Hit h = closest_hit_any<KIND, false, false>(A.scene, mk(A.o[3 * i], A.o[3 * i + 1], A.o[3 * i + 2]),
+                                                mk(A.d[3 * i], A.d[3 * i + 1], A.d[3 * i + 2]), A.t_min, &ec);
+    A.prim_id[i] = prim_id_of(A.scene, h.ref); A.t[i] = h.t;
 }
 
 // ------------------------------------------------------------------ epilogue
@@ -249,8 +263,9 @@ static DevScene dev_scene(const SceneView& v) {
     DevScene s;
     s.nodes = (const float4*)v.nodes; s.spheres = (const float4*)v.spheres; s.quads = (const float4*)v.quads;
     s.sphere_meta = (const uint4*)v.sphere_meta; s.quad_meta = (const uint4*)v.quad_meta; s.materials = (const float4*)v.materials;
+    s.flat = (const FlatPrim*)v.flat; s.n_flat = v.n_flat;
     s.root = v.root; s.n_nodes = v.n_nodes; s.n_spheres = v.n_spheres; s.n_quads = v.n_quads; s.n_materials = v.n_materials;
-    s.ordered = v.ordered;
+    s.ordered = v.kind == 1 ? 1u : 0u;
     for (int i = 0; i < 3; ++i) { s.root_min[i] = v.root_min[i]; s.root_max[i] = v.root_max[i]; }
     return s;
 }
@@ -274,18 +289,20 @@ static DevParams dev_params(const trt_params& p) {
 }
 
 size_t scene_smem_bytes(const SceneView& v) {
-    return 16ull * (4ull * v.n_nodes + v.n_spheres + 4ull * v.n_quads + v.n_spheres + v.n_quads + 2ull * v.n_materials);
+    size_t b = 16ull * (4ull * v.n_nodes + v.n_spheres + 4ull * v.n_quads + v.n_spheres + v.n_quads + 2ull * v.n_materials + 6ull * v.n_flat);
+    if (v.kind == 2) b += 4ull * MEGA_THREADS * v.n_flat;     // phase-A columns
+    return b;
 }
 
-template <bool ORDERED, bool SMEM, bool COUNT>
+template <int KIND, bool SMEM, bool COUNT>
 static cudaError_t mega_fn(const void** fn, int* blocks_per_sm, size_t smem) {
-    auto kern = k_render_mega<ORDERED, SMEM, COUNT>;
+    auto kern = k_render_mega<KIND, SMEM, COUNT>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     *fn = (const void*)kern;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, 256, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, MEGA_THREADS, smem);
 }
 
 cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const trt_params& p, double* d_sum64,
@@ -295,19 +312,26 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     A.sum64 = d_sum64; A.counters = d_counters; A.next_item = d_next_item;
     size_t smem = scene_smem_bytes(v);
     bool use_smem = smem <= 64 * 1024;
+    if (v.kind == 2 && (!use_smem || v.n_flat > TRT_FLAT_MAX || !v.flat_host)) return cudaErrorInvalidValue;
     if (!use_smem) smem = 0;
-    bool count = (p.flags & 1u) != 0, ordered = v.ordered != 0;
+    bool count = (p.flags & 1u) != 0;
     const void* fn = nullptr; int blocks_per_sm = 0; cudaError_t e;
-    if (ordered) { if (use_smem) e = count ? mega_fn<true, true, true>(&fn, &blocks_per_sm, smem) : mega_fn<true, true, false>(&fn, &blocks_per_sm, smem);
-                   else e = count ? mega_fn<true, false, true>(&fn, &blocks_per_sm, smem) : mega_fn<true, false, false>(&fn, &blocks_per_sm, smem); }
-    else { if (use_smem) e = count ? mega_fn<false, true, true>(&fn, &blocks_per_sm, smem) : mega_fn<false, true, false>(&fn, &blocks_per_sm, smem);
-           else e = count ? mega_fn<false, false, true>(&fn, &blocks_per_sm, smem) : mega_fn<false, false, false>(&fn, &blocks_per_sm, smem); }
+    if (v.kind == 2) {
+        if (smem > 48 * 1024) { e = cudaFuncSetAttribute(k_render_mega_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+        fn = (const void*)k_render_mega_flat;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_render_mega_flat, MEGA_THREADS, smem);
+    } else if (v.kind == 1) {
+        if (use_smem) e = count ? mega_fn<1, true, true>(&fn, &blocks_per_sm, smem) : mega_fn<1, true, false>(&fn, &blocks_per_sm, smem);
+        else e = count ? mega_fn<1, false, true>(&fn, &blocks_per_sm, smem) : mega_fn<1, false, false>(&fn, &blocks_per_sm, smem);
+    } else {
+        if (use_smem) e = count ? mega_fn<0, true, true>(&fn, &blocks_per_sm, smem) : mega_fn<0, true, false>(&fn, &blocks_per_sm, smem);
+        else e = count ? mega_fn<0, false, true>(&fn, &blocks_per_sm, smem) : mega_fn<0, false, false>(&fn, &blocks_per_sm, smem);
+    }
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     // persistent grid: every SM filled to the kernel's occupancy limit, one wave
-    const int threads = 256;
     int grid = sm_count * blocks_per_sm;
-    uint64_t resident = (uint64_t)grid * threads;
+    uint64_t resident = (uint64_t)grid * MEGA_THREADS;
     uint64_t pixels = (uint64_t)p.width * p.height;
     // chunk of samples per work item: whole pixels when there are plenty of them, otherwise split so that the
     // persistent lanes see >= ~8 items each (tail balance); never below 4 samples per item.
@@ -323,9 +347,21 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     uint64_t n_items = (uint64_t)A.tiles_x * A.tiles_y * 32ull * A.n_chunks;
     if (n_items > 0xFFFFFFF0ull - resident) return cudaErrorInvalidValue;
     A.n_items = (uint32_t)n_items;
+    if (v.kind == 2) {
+        static_assert(sizeof(FlatList) == 96 * TRT_FLAT_MAX, "FlatPrim must be 6 float4");
+        FlatList L;
+        memset(&L, 0, sizeof L);
+        memcpy(&L, v.flat_host, 96ull * v.n_flat);
+        void* args[] = {(void*)&A, (void*)&L};
+        return cudaLaunchKernel(fn, dim3(grid), dim3(MEGA_THREADS), args, smem, st);
+    }
     void* args[] = {(void*)&A};
-    return cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, st);
+    return cudaLaunchKernel(fn, dim3(grid), dim3(MEGA_THREADS), args, smem, st);
 }
+
+#define TRT_KIND_LAUNCH(kern, kind, blocks, threads, st, A) \
+    do { if ((kind) == 2) kern<2><<<(blocks), (threads), 0, (st)>>>(A); else if ((kind) == 1) kern<1><<<(blocks), (threads), 0, (st)>>>(A); \
+         else kern<0><<<(blocks), (threads), 0, (st)>>>(A); } while (0)
 
 cudaError_t launch_aov(const SceneView& v, const trt_camera& cam, const trt_params& p, uint32_t* d_prim, float* d_t,
                        float* d_rad, uint32_t* d_nrays, cudaStream_t st) {
@@ -335,7 +371,7 @@ cudaError_t launch_aov(const SceneView& v, const trt_camera& cam, const trt_para
     if (A.total == 0) return cudaSuccess;
     unsigned long long blocks = (A.total + 127) / 128;
     if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-    if (v.ordered) k_aov<true><<<(unsigned)blocks, 128, 0, st>>>(A); else k_aov<false><<<(unsigned)blocks, 128, 0, st>>>(A);
+    TRT_KIND_LAUNCH(k_aov, v.kind, (unsigned)blocks, 128, st, A);
     return cudaGetLastError();
 }
 
@@ -345,7 +381,7 @@ cudaError_t launch_sample_batch(const SceneView& v, const trt_params& p, const t
     if (n == 0) return cudaSuccess;
     unsigned long long blocks = (n + 127) / 128;
     if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-    if (v.ordered) k_sample_batch<true><<<(unsigned)blocks, 128, 0, st>>>(A); else k_sample_batch<false><<<(unsigned)blocks, 128, 0, st>>>(A);
+    TRT_KIND_LAUNCH(k_sample_batch, v.kind, (unsigned)blocks, 128, st, A);
     return cudaGetLastError();
 }
 
@@ -355,7 +391,7 @@ cudaError_t launch_trace(const SceneView& v, const float* d_o, const float* d_d,
     if (n == 0) return cudaSuccess;
     unsigned long long blocks = (n + 127) / 128;
     if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-    if (v.ordered) k_trace<true><<<(unsigned)blocks, 128, 0, st>>>(A); else k_trace<false><<<(unsigned)blocks, 128, 0, st>>>(A);
+    TRT_KIND_LAUNCH(k_trace, v.kind, (unsigned)blocks, 128, st, A);
     return cudaGetLastError();
 }
 

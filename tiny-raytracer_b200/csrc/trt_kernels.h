@@ -12,7 +12,11 @@ namespace trtk {
 
 struct SceneView {   // device copy of trt::FlatScene
     const void* nodes; const void* spheres; const void* quads; const void* sphere_meta; const void* quad_meta; const void* materials;
-    uint32_t root, n_nodes, n_spheres, n_quads, n_materials, ordered;
+    const void* flat;          // device copy of the flat list (6 float4 per primitive, reference leaf order) or null
+    const void* flat_host;     // the same list on the host: copied into the kernel parameters of k_render_mega_flat
+    uint32_t n_flat;
+    uint32_t root, n_nodes, n_spheres, n_quads, n_materials;
+    uint32_t kind;             // trt_bvh_kind after AUTO resolution: 0 reference, 1 SAH, 2 flat
     float root_min[3], root_max[3];
 };
 

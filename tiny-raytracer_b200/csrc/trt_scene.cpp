@@ -278,8 +278,10 @@ static void flatten(const std::vector<TNode>& t, const std::vector<HostPrim>& pr
 }
 
 bool HostScene::commit(int bvh_kind, std::string* err) {
-    if (bvh_kind != 0 && bvh_kind != 1) { *err = "trt_scene_commit: unknown bvh_kind"; return false; }
+    if (bvh_kind < 0 || bvh_kind > 3) { *err = "trt_scene_commit: unknown bvh_kind"; return false; }
     size_t n = prims.size();
+    if (bvh_kind == 3) bvh_kind = (n >= 1 && n <= TRT_FLAT_MAX) ? 2 : 1;            // TRT_BVH_AUTO
+    if (bvh_kind == 2 && (n < 1 || n > TRT_FLAT_MAX)) { *err = "trt_scene_commit: TRT_BVH_FLAT takes 1..48 primitives"; return false; }
     // per-type arrays in insertion order (what World::get_geometries::<T>() returns, hittable/world.rs:47-55)
     uint32_t ns = 0, nq = 0;
     for (auto& p : prims) p.type_index = p.type ? nq++ : ns++;
@@ -321,6 +323,18 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
             q[2] = {p.b[0], p.b[1], p.b[2], p.w[1]};
             q[3] = {p.c[0], p.c[1], p.c[2], p.w[2]};
             flat.quad_meta[p.type_index] = meta;
+        }
+    }
+    if (bvh_kind == 2) {
+        // the list, in reference leaf order: geometry, then the primitive's own padded box and its child-ref bits
+        flat.flat.resize(6 * n);
+        for (size_t i = 0; i < n; ++i) {
+            const HostPrim& p = prims[i];
+            trt_f4* f = &flat.flat[6 * (size_t)leaf_rank[i]];
+            if (p.type == 0) { f[0] = {p.a[0], p.a[1], p.a[2], p.r}; f[1] = f[2] = f[3] = {0.f, 0.f, 0.f, 0.f}; }
+            else { for (int k = 0; k < 4; ++k) f[k] = flat.quads[4 * (size_t)p.type_index + k]; }
+            f[4] = {p.bmin[0], p.bmin[1], p.bmin[2], as_float(leaf_ref(p))};
+            f[5] = {p.bmax[0], p.bmax[1], p.bmax[2], 0.f};
         }
     }
     flat.materials.resize(2 * materials.size());

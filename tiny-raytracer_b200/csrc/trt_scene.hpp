@@ -25,6 +25,7 @@ struct FlatScene {
     std::vector<trt_f4> quads;         // 4 per quad
     std::vector<trt_u4> sphere_meta, quad_meta;
     std::vector<trt_f4> materials;     // 2 per material
+    std::vector<trt_f4> flat;          // TRT_BVH_FLAT: 6 per primitive, reference leaf order (trt_layout.h)
     uint32_t root = TRT_REF_INVALID;   // interior node 0, or INVALID for an empty scene
     uint32_t n_nodes = 0, max_depth = 0;
     float sah_cost = 0.f;
