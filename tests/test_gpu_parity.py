@@ -207,6 +207,27 @@ def test_render_matches_oracle(trt, orc, ctx, kind, case):
     assert psnr8(u8, ou8) >= PSNR_MIN_DB
 
 
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("case", ["c1", "c1s", "final_small", "glass_small", "ragged", "tiny"])
+def test_wavefront_render_matches_oracle(trt, orc, ctx, kind, case):
+    """TRT_VARIANT_WAVEFRONT traces the same paths (same Philox keys) through queues in HBM; only the order of the f64
+    accumulation differs, so the image must agree with the oracle to <= 1 ulp and ray / path counts exactly."""
+    desc = RENDER_CASES[case](trt.scenes)
+    osc, ocam, cam = both(trt, orc, desc)
+    sc = trt.Scene.from_desc(desc, kind)
+    w, h = desc.camera["width"], desc.camera["height"]
+    p = trt.make_params(w, h, desc.spp, desc.max_bounces, desc.background, desc.seed, variant=trt.VARIANT_WAVEFRONT)
+    _, op = params(trt, orc, desc)
+    lin, u8, st = sc.render(ctx, cam, p)
+    olin, ou8, ost, _ = osc.render(ocam, op)
+    assert (st.paths, st.rays) == (ost.paths, ost.rays)
+    d = ulp_diff(lin, olin)
+    assert d.max() <= 1, "linear image: max %d ulp, %d values differ" % (int(d.max()), int((d > 0).sum()))
+    assert np.abs(u8.astype(np.int32) - ou8.astype(np.int32)).max() <= 1 and psnr8(u8, ou8) >= PSNR_MIN_DB
+    mega, _, _ = sc.render(ctx, cam, params(trt, orc, desc)[0])
+    assert ulp_diff(lin, mega).max() <= 1
+
+
 @pytest.mark.parametrize("kind", KINDS)
 def test_event_counters_match_oracle(trt, orc, ctx, kind):
     """Node visits and primitive tests are topology-dependent: with TRT_BVH_REFERENCE they must equal the oracle's

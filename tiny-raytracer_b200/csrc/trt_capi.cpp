@@ -5,6 +5,7 @@
 #include "trt_scene.hpp"
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -243,7 +244,25 @@ static int check_render_args(trt_ctx* c, trt_scene* s, const trt_camera* cam, co
 static int render_into(trt_ctx* c, trt_scene* s, const trt_camera* cam, const trt_params* p, double* d_sum64, trt_stats* stats) {
     int rc = trt_scene_upload(c, s); if (rc) return rc;
     const trtk::SceneView& v = s->on_device[c->device].view;
-    if (p->variant == TRT_VARIANT_WAVEFRONT) return fail(TRT_ERR_UNSUPPORTED, "trt_render: wavefront variant not built yet");
+    if (p->variant == TRT_VARIANT_WAVEFRONT) {
+        if (v.kind == TRT_BVH_FLAT) return fail(TRT_ERR_UNSUPPORTED, "wavefront variant needs a tree: commit with TRT_BVH_REFERENCE or TRT_BVH_SAH");
+        if (p->max_bounces > 0xFFFFu) return fail(TRT_ERR_UNSUPPORTED, "wavefront variant: max_bounces above 65535");
+        uint32_t n_slots = 1u << 20;                       // 68 B per slot: 68 MB of path state, L2-resident on B200
+        if (const char* e = std::getenv("TRT_WF_SLOTS")) { long x = std::atol(e); if (x >= 1024 && x <= (1l << 26)) n_slots = (uint32_t)x & ~31u; }
+        void* d_state = nullptr; int rc2;
+        if ((rc2 = ensure_scratch(c, 3, trtk::wavefront_scratch_bytes(n_slots), &d_state))) return rc2;
+        unsigned long long rp[2] = {0, 0}; uint32_t launches = 0;
+        CU(cudaEventRecord(c->ev[0], c->stream));
+        CU(trtk::launch_render_wavefront(v, *cam, *p, d_sum64, d_state, n_slots, c->d_counters, c->sm_count, c->stream, rp, &launches));
+        CU(cudaEventRecord(c->ev[1], c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (stats) {
+            float ms = 0.f; CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+            stats->rays = rp[0]; stats->paths = rp[1]; stats->node_visits = stats->sphere_tests = stats->quad_tests = 0;
+            stats->device_ms = ms; stats->launches = launches; stats->finalize_ms = 0.f; stats->reserved = 0;
+        }
+        return TRT_OK;
+    }
     CU(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long) + 64, c->stream));
     CU(cudaEventRecord(c->ev[0], c->stream));
     CU(trtk::launch_render_mega(v, *cam, *p, d_sum64, c->d_counters, c->d_next_item, c->sm_count, c->stream));

@@ -247,78 +247,95 @@ template <bool SMEM> TRT_DEV bool quad_hit(const DevScene& S, uint32_t idx, V3 o
 // region's code is issued once per iteration for all lanes that need it instead of once per call site.
 struct Hit { float t; uint32_t ref; };
 
-template <bool ORDERED, bool SMEM, bool COUNT>
-TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
-    Hit best; best.t = TRT_INF; best.ref = TRT_REF_INVALID;
-    uint32_t cur = S.root;
-    if (cur == TRT_REF_INVALID) return best;
-    uint32_t best_rank = 0xFFFFFFFFu;
-    const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);   // aabb.rs:42, identical for every node of this ray
-    const bool tame = ray_is_tame(o, inv);
-    uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
-    int sp = 0;
-    if (COUNT) {
+// Resumable form: trav_begin() sets the state up, every trav_step() runs one iteration of the loop (region A, region B,
+// pop). closest_hit() is begin + step until done; the wavefront extend kernel interleaves steps of different rays.
+struct Trav {
+    V3 o, d, inv; float t_min; bool tame;
+    uint32_t cur; int sp; Hit best; uint32_t best_rank;
+};
+
+template <bool COUNT>
+TRT_DEV void trav_begin(Trav& T, const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
+    T.o = o; T.d = d; T.t_min = t_min;
+    T.best.t = TRT_INF; T.best.ref = TRT_REF_INVALID; T.best_rank = 0xFFFFFFFFu; T.sp = 0;
+    T.cur = S.root;
+    T.inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);           // aabb.rs:42, identical for every node of this ray
+    T.tame = ray_is_tame(o, T.inv);
+    if (COUNT && T.cur != TRT_REF_INVALID) {
         ec->node_visits += 1;          // the root's own Node::hit call (bvh.rs:25-27); its box test is implied by the
         float s0, e0;                  // children's tests, so it is only evaluated to keep the event counts faithful
-        slab(S.root_min[0], S.root_min[1], S.root_min[2], S.root_max[0], S.root_max[1], S.root_max[2], o, inv, t_min, &s0, &e0);
-        if (!(e0 > s0)) return best;
+        slab(S.root_min[0], S.root_min[1], S.root_min[2], S.root_max[0], S.root_max[1], S.root_max[2], o, T.inv, t_min, &s0, &e0);
+        if (!(e0 > s0)) T.cur = TRT_REF_INVALID;
     }
-    do {
-        if (!(cur & TRT_REF_LEAF)) {
-            // ---- region A: one interior node = two child boxes (aabb.rs:36-61 twice)
-            const float4* np = S.nodes + 4 * (size_t)cur;
-            float4 n0 = ld4<SMEM>(np), n1 = ld4<SMEM>(np + 1), n2 = ld4<SMEM>(np + 2), n3 = ld4<SMEM>(np + 3);
-            uint32_t lref = __float_as_uint(n3.x), rref = __float_as_uint(n3.y);
-            float sl, el, sr, er;
-            if (tame) {
-                slab_tame(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, &sl, &el);
-                slab_tame(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, &sr, &er);
-            } else {
-                slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, &sl, &el);
-                slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, &sr, &er);
+}
+
+template <bool ORDERED, bool SMEM, bool COUNT>
+TRT_DEV void trav_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* stack_t, EventCounters* ec) {
+    uint32_t cur = T.cur;
+    const V3 o = T.o, d = T.d, inv = T.inv; const float t_min = T.t_min;
+    if (!(cur & TRT_REF_LEAF)) {
+        // ---- region A: one interior node = two child boxes (aabb.rs:36-61 twice)
+        const float4* np = S.nodes + 4 * (size_t)cur;
+        float4 n0 = ld4<SMEM>(np), n1 = ld4<SMEM>(np + 1), n2 = ld4<SMEM>(np + 2), n3 = ld4<SMEM>(np + 3);
+        uint32_t lref = __float_as_uint(n3.x), rref = __float_as_uint(n3.y);
+        float sl, el, sr, er;
+        if (T.tame) {
+            slab_tame(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, &sl, &el);
+            slab_tame(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, &sr, &er);
+        } else {
+            slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, &sl, &el);
+            slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, &sr, &er);
+        }
+        if (COUNT) ec->node_visits += (rref == TRT_REF_INVALID) ? 0u : 2u;   // left.hit + right.hit
+        bool pl, pr;
+        if (ORDERED) { pl = el > sl && !(T.best.t < sl); pr = er > sr && !(T.best.t < sr); }
+        else { pl = el > sl && T.best.t > sl; pr = er > sr; }                // right: range end re-checked when it is entered
+        pr = pr && rref != TRT_REF_INVALID;
+        bool right_first = ORDERED && pl && pr && sr < sl;
+        uint32_t c0 = right_first ? rref : lref, c1 = right_first ? lref : rref;
+        float s1 = right_first ? sl : sr;
+        bool p0 = right_first ? pr : pl, p1 = right_first ? pl : pr;
+        if (p0) {
+            cur = c0;
+            if (p1) { stack_ref[T.sp] = c1; stack_t[T.sp] = s1; ++T.sp; }
+        } else if (p1 && (ORDERED || T.best.t > s1)) cur = c1;
+        else cur = TRT_REF_INVALID;
+    }
+    if (cur != TRT_REF_INVALID && (cur & TRT_REF_LEAF)) {
+        // ---- region B: one primitive (sphere.rs:29-45 / quad.rs:33-41)
+        uint32_t idx = cur & TRT_REF_INDEX_MASK;
+        float t; bool h;
+        if (cur & TRT_REF_QUAD) { if (COUNT) ec->quad_tests++; h = quad_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : T.best.t, T.best.t, &t); }
+        else { if (COUNT) ec->sphere_tests++; h = sphere_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : T.best.t, &t); }
+        if (h) {
+            if (!ORDERED) { T.best.t = t; T.best.ref = cur; }
+            else if (t < T.best.t) { T.best.t = t; T.best.ref = cur; T.best_rank = 0xFFFFFFFFu; }
+            else if (t == T.best.t) {
+                if (T.best_rank == 0xFFFFFFFFu)
+                    T.best_rank = (T.best.ref & TRT_REF_QUAD) ? ld4u<SMEM>(S.quad_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y
+                                                              : ld4u<SMEM>(S.sphere_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y;
+                uint32_t rk = (cur & TRT_REF_QUAD) ? ld4u<SMEM>(S.quad_meta + idx).y : ld4u<SMEM>(S.sphere_meta + idx).y;
+                if (rk < T.best_rank) { T.best.ref = cur; T.best_rank = rk; }
             }
-            if (COUNT) ec->node_visits += (rref == TRT_REF_INVALID) ? 0u : 2u;   // left.hit + right.hit
-            bool pl, pr;
-            if (ORDERED) { pl = el > sl && !(best.t < sl); pr = er > sr && !(best.t < sr); }
-            else { pl = el > sl && best.t > sl; pr = er > sr; }                  // right: range end re-checked when it is entered
-            pr = pr && rref != TRT_REF_INVALID;
-            bool right_first = ORDERED && pl && pr && sr < sl;
-            uint32_t c0 = right_first ? rref : lref, c1 = right_first ? lref : rref;
-            float s1 = right_first ? sl : sr;
-            bool p0 = right_first ? pr : pl, p1 = right_first ? pl : pr;
-            if (p0) {
-                cur = c0;
-                if (p1) { stack_ref[sp] = c1; stack_t[sp] = s1; ++sp; }
-            } else if (p1 && (ORDERED || best.t > s1)) cur = c1;
-            else cur = TRT_REF_INVALID;
         }
-        if (cur != TRT_REF_INVALID && (cur & TRT_REF_LEAF)) {
-            // ---- region B: one primitive (sphere.rs:29-45 / quad.rs:33-41)
-            uint32_t idx = cur & TRT_REF_INDEX_MASK;
-            float t; bool h;
-            if (cur & TRT_REF_QUAD) { if (COUNT) ec->quad_tests++; h = quad_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : best.t, best.t, &t); }
-            else { if (COUNT) ec->sphere_tests++; h = sphere_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : best.t, &t); }
-            if (h) {
-                if (!ORDERED) { best.t = t; best.ref = cur; }
-                else if (t < best.t) { best.t = t; best.ref = cur; best_rank = 0xFFFFFFFFu; }
-                else if (t == best.t) {
-                    if (best_rank == 0xFFFFFFFFu)
-                        best_rank = (best.ref & TRT_REF_QUAD) ? ld4u<SMEM>(S.quad_meta + (best.ref & TRT_REF_INDEX_MASK)).y
-                                                              : ld4u<SMEM>(S.sphere_meta + (best.ref & TRT_REF_INDEX_MASK)).y;
-                    uint32_t rk = (cur & TRT_REF_QUAD) ? ld4u<SMEM>(S.quad_meta + idx).y : ld4u<SMEM>(S.sphere_meta + idx).y;
-                    if (rk < best_rank) { best.ref = cur; best_rank = rk; }
-                }
-            }
-            cur = TRT_REF_INVALID;
-        }
-        // ---- pop: skip entries that the closest hit found meanwhile has cut off
-        while (cur == TRT_REF_INVALID && sp > 0) {
-            --sp;
-            float s = stack_t[sp];
-            if (ORDERED ? !(best.t < s) : (best.t > s)) cur = stack_ref[sp];
-        }
-    } while (cur != TRT_REF_INVALID);
-    return best;
+        cur = TRT_REF_INVALID;
+    }
+    // ---- pop: skip entries that the closest hit found meanwhile has cut off
+    while (cur == TRT_REF_INVALID && T.sp > 0) {
+        --T.sp;
+        float s = stack_t[T.sp];
+        if (ORDERED ? !(T.best.t < s) : (T.best.t > s)) cur = stack_ref[T.sp];
+    }
+    T.cur = cur;
+}
+
+template <bool ORDERED, bool SMEM, bool COUNT>
+TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
+    Trav T;
+    trav_begin<COUNT>(T, S, o, d, t_min, ec);
+    uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
+    while (T.cur != TRT_REF_INVALID) trav_step<ORDERED, SMEM, COUNT>(T, S, stack_ref, stack_t, ec);
+    return T.best;
 }
 
 // ------------------------------------------------------------------ camera: pointgen.rs:41-43 + camera.rs:58-66 + vec3extend.rs:45-53

@@ -12,6 +12,7 @@
 //   k_debug_*       device evaluation of the numeric contract for unit parity tests
 #include "trt_device.cuh"
 #include "trt_kernels.h"
+#include "trt_host_glue.cuh"
 #include <cstdio>
 
 using namespace trtd;
@@ -258,35 +259,6 @@ __global__ void k_debug_philox(size_t n, const uint32_t* ctr, uint32_t k0, uint3
 
 // ------------------------------------------------------------------ launchers
 namespace trtk {
-
-static DevScene dev_scene(const SceneView& v) {
-    DevScene s;
-    s.nodes = (const float4*)v.nodes; s.spheres = (const float4*)v.spheres; s.quads = (const float4*)v.quads;
-    s.sphere_meta = (const uint4*)v.sphere_meta; s.quad_meta = (const uint4*)v.quad_meta; s.materials = (const float4*)v.materials;
-    s.flat = (const FlatPrim*)v.flat; s.n_flat = v.n_flat;
-    s.root = v.root; s.n_nodes = v.n_nodes; s.n_spheres = v.n_spheres; s.n_quads = v.n_quads; s.n_materials = v.n_materials;
-    s.ordered = v.kind == 1 ? 1u : 0u;
-    for (int i = 0; i < 3; ++i) { s.root_min[i] = v.root_min[i]; s.root_max[i] = v.root_max[i]; }
-    return s;
-}
-static DevCamera dev_camera(const trt_camera& c) {
-    DevCamera d;
-    d.position = mk(c.position[0], c.position[1], c.position[2]);
-    d.upper_left = mk(c.viewport_upper_left[0], c.viewport_upper_left[1], c.viewport_upper_left[2]);
-    d.horizontal = mk(c.horizontal[0], c.horizontal[1], c.horizontal[2]);
-    d.vertical = mk(c.vertical[0], c.vertical[1], c.vertical[2]);
-    d.du = mk(c.defocus_disk_u[0], c.defocus_disk_u[1], c.defocus_disk_u[2]);
-    d.dv = mk(c.defocus_disk_v[0], c.defocus_disk_v[1], c.defocus_disk_v[2]);
-    d.width = c.width; d.height = c.height;
-    return d;
-}
-static DevParams dev_params(const trt_params& p) {
-    DevParams d;
-    d.width = p.width; d.height = p.height; d.spp = p.spp; d.sample_offset = p.sample_offset; d.max_bounces = p.max_bounces;
-    d.bg[0] = p.background[0]; d.bg[1] = p.background[1]; d.bg[2] = p.background[2];
-    d.seed_lo = (uint32_t)p.seed; d.seed_hi = (uint32_t)(p.seed >> 32); d.t_min = p.t_min;
-    return d;
-}
 
 size_t scene_smem_bytes(const SceneView& v) {
     size_t b = 16ull * (4ull * v.n_nodes + v.n_spheres + 4ull * v.n_quads + v.n_spheres + v.n_quads + 2ull * v.n_materials + 6ull * v.n_flat);

@@ -24,6 +24,11 @@ size_t scene_smem_bytes(const SceneView& v);
 
 cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const trt_params& p, double* d_sum64,
                                unsigned long long* d_counters, unsigned int* d_next_item, int sm_count, cudaStream_t st);
+size_t wavefront_scratch_bytes(uint32_t n_slots);
+// Runs the whole wavefront render (host loop inside; synchronises the stream). h_rays_paths[0] = rays, [1] = paths.
+cudaError_t launch_render_wavefront(const SceneView& v, const trt_camera& cam, const trt_params& p, double* d_sum64,
+                                    void* d_scratch, uint32_t n_slots, void* d_ctl, int sm_count, cudaStream_t st,
+                                    unsigned long long* h_rays_paths, uint32_t* launches_out);
 cudaError_t launch_aov(const SceneView& v, const trt_camera& cam, const trt_params& p, uint32_t* d_prim, float* d_t,
                        float* d_rad, uint32_t* d_nrays, cudaStream_t st);
 cudaError_t launch_sample_batch(const SceneView& v, const trt_params& p, const trt_sample_point_pod* d_in, size_t n,
