@@ -35,7 +35,7 @@ typedef enum trt_bvh_kind {
     TRT_BVH_REFERENCE = 0,   /* the reference's median-split topology, traversed left-first: reference results by construction */
     TRT_BVH_SAH = 1,         /* binned-SAH topology, near-child-first traversal, ties broken by reference leaf order */
     TRT_BVH_FLAT = 2,        /* no tree: <= 48 primitives as a list in reference leaf order; reference results by construction */
-    TRT_BVH_AUTO = 3         /* FLAT when the scene has <= 48 primitives, else SAH */
+    TRT_BVH_AUTO = 3         /* REFERENCE when the scene has <= 64 primitives (as fast there, exact by construction), else SAH */
 } trt_bvh_kind;
 
 /* Which kernel family renders. */

@@ -1,0 +1,157 @@
+// include/trt.hpp — header-only C++17 mirror of tiny-raytracer's public Rust API over the C ABI of trt.h.
+//
+// The reference is compiled Rust and this image has no Rust toolchain, so the host side above the C ABI is written
+// here in C++ with the reference's names, argument meanings and error behaviour (the Rust crate a maintainer would
+// add is kept as source under rust/). A reference scene script such as /root/reference/src/main.rs
+// translates line by line:
+//
+//     trt::World world;                                                       // World::new()            hittable/world.rs:16-21
+//     world.add_material("white", trt::Lambertian({0.73f, 0.73f, 0.73f}));    // add_material            hittable/world.rs:27-33
+//     world.add_geometry(trt::Quad({0,0,0}, {100,0,0}, {0,0,100}, world.get_material("white")));   // hittable/world.rs:23-25
+//     trt::Camera camera(140.f, 0.6f, {50,50,-140}, {50,50,0}, {0,1,0}, 40.f, 300, 300);            // camera.rs:17-26
+//     trt::Renderer renderer(300, 8, 20, true, trt::Vec3::new_diagonal(0.001f));                    // renderer/renderer.rs:21-35
+//     trt::Image image = renderer.render(camera, world);                                            // renderer/renderer.rs:37
+//     image.save_ppm("output.ppm");
+//
+// Errors: the reference panics (`.expect`, world.rs:29-31); this mirror throws trt::Error carrying the C ABI's status and
+// message, so nothing unwinds across the C boundary.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "trt.h"
+
+namespace trt {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int rc) { if (rc != TRT_OK) throw Error(rc, trt_last_error()); }
+
+struct Vec3 {                                                   // math/vec3.rs:9-30
+    float x, y, z;
+    Vec3() : x(0), y(0), z(0) {}
+    Vec3(float x_, float y_, float z_) : x(x_), y(y_), z(z_) {}
+    static Vec3 new_diagonal(float v) { return Vec3(v, v, v); }
+    static Vec3 zero() { return Vec3(); }
+    const float* data() const { return &x; }
+};
+
+struct Material {                                               // material/mod.rs:5-11
+    enum Kind { LAMBERTIAN = 0, METAL = 1, DIELECTRIC = 2, LIGHT = 3 } kind;
+    Vec3 rgb; float param;
+};
+inline std::shared_ptr<Material> Lambertian(Vec3 albedo) { return std::make_shared<Material>(Material{Material::LAMBERTIAN, albedo, 0.f}); }
+inline std::shared_ptr<Material> Metal(Vec3 albedo, float fuzz) { return std::make_shared<Material>(Material{Material::METAL, albedo, fuzz}); }
+inline std::shared_ptr<Material> Dielectric(Vec3 albedo, float refraction_index) { return std::make_shared<Material>(Material{Material::DIELECTRIC, albedo, refraction_index}); }
+inline std::shared_ptr<Material> Light(Vec3 color) { return std::make_shared<Material>(Material{Material::LIGHT, color, 0.f}); }
+
+struct Geometry {                                               // hittable/{sphere,quad}.rs
+    bool is_quad; Vec3 a, u, v; float radius; std::shared_ptr<Material> material;
+};
+inline Geometry Sphere(Vec3 center, float radius, std::shared_ptr<Material> m) { return Geometry{false, center, Vec3(), Vec3(), radius, std::move(m)}; }
+inline Geometry Quad(Vec3 corner, Vec3 u, Vec3 v, std::shared_ptr<Material> m) { return Geometry{true, corner, u, v, 0.f, std::move(m)}; }
+
+// new_box of /root/reference/src/main.rs:89-125 (front, right, back, left, top, bottom), flattened to six quads
+inline std::vector<Geometry> new_box(Vec3 a, Vec3 b, std::shared_ptr<Material> m) {
+    auto mn = [](float p, float q) { return p < q ? p : q; };
+    auto mx = [](float p, float q) { return p > q ? p : q; };
+    Vec3 lo(mn(a.x, b.x), mn(a.y, b.y), mn(a.z, b.z)), hi(mx(a.x, b.x), mx(a.y, b.y), mx(a.z, b.z));
+    Vec3 dx(hi.x - lo.x, 0, 0), dy(0, hi.y - lo.y, 0), dz(0, 0, hi.z - lo.z), ndx(-dx.x, 0, 0), ndz(0, 0, -dz.z);
+    return {Quad({lo.x, lo.y, hi.z}, dx, dy, m), Quad({hi.x, lo.y, hi.z}, ndz, dy, m), Quad({hi.x, lo.y, lo.z}, ndx, dy, m),
+            Quad({lo.x, lo.y, lo.z}, dz, dy, m), Quad({lo.x, hi.y, hi.z}, dx, ndz, m), Quad({lo.x, lo.y, lo.z}, dx, dz, m)};
+}
+
+class World {                                                   // hittable/world.rs:10-55
+public:
+    void add_geometry(Geometry g) { geometries_.push_back(std::move(g)); }
+    void add_geometry(const std::vector<Geometry>& list) { for (auto& g : list) geometries_.push_back(g); }
+    void add_material(const std::string& name, std::shared_ptr<Material> m) {
+        if (materials_.count(name)) throw Error(TRT_ERR_INVALID, name + " key is already in the material table");   // world.rs:29-31
+        materials_[name] = std::move(m);
+    }
+    std::shared_ptr<Material> get_material(const std::string& name) const {
+        auto it = materials_.find(name); return it == materials_.end() ? nullptr : it->second;
+    }
+    const std::vector<Geometry>& geometries() const { return geometries_; }
+private:
+    std::vector<Geometry> geometries_;
+    std::map<std::string, std::shared_ptr<Material>> materials_;
+};
+
+class Camera {                                                  // camera.rs:17-56
+public:
+    Camera(float focus_distance, float defocus_angle, Vec3 position, Vec3 look_at, Vec3 up, float vertical_fov, uint32_t width, uint32_t height) {
+        check(trt_camera_make(focus_distance, defocus_angle, position.data(), look_at.data(), up.data(), vertical_fov, width, height, &pod));
+    }
+    std::pair<uint32_t, uint32_t> get_image_size() const { return {pod.width, pod.height}; }
+    trt_camera pod;
+};
+
+struct Image {                                                  // utils/image.rs
+    uint32_t width = 0, height = 0;
+    std::vector<float> linear;        // H*W*3, sum / spp
+    std::vector<uint8_t> rgb8;        // gamma 2.2, clamp, * 255
+    void save_ppm(const std::string& filename) const {
+        FILE* f = std::fopen(filename.c_str(), "wb");
+        if (!f) throw Error(TRT_ERR_INVALID, "cannot open " + filename);
+        std::fprintf(f, "P6\n%u %u\n255\n", width, height);
+        std::fwrite(rgb8.data(), 1, rgb8.size(), f); std::fclose(f);
+    }
+};
+
+class Renderer {                                                // renderer/renderer.rs:13-79
+public:
+    Renderer(uint32_t samples_per_pixel, uint32_t /*num_sampler_threads*/, uint32_t max_bounces, bool /*progressbar*/,
+             std::optional<Vec3> background_color = std::nullopt, uint64_t seed = 1, int device = 0,
+             int bvh_kind = TRT_BVH_AUTO, uint32_t variant = TRT_VARIANT_MEGAKERNEL)
+        : spp_(samples_per_pixel), max_bounces_(max_bounces), bg_(background_color.value_or(Vec3::zero())), seed_(seed),
+          device_(device), bvh_kind_(bvh_kind), variant_(variant) {}
+
+    Image render(const Camera& camera, const World& world) {
+        trt_ctx* ctx = nullptr; trt_scene* scene = nullptr;
+        check(trt_ctx_create(device_, &ctx));
+        try {
+            check(trt_scene_create(&scene));
+            std::map<const Material*, uint32_t> ids;
+            auto mat_id = [&](const std::shared_ptr<Material>& m) {
+                auto it = ids.find(m.get()); if (it != ids.end()) return it->second;
+                uint32_t id = 0;
+                switch (m->kind) {
+                    case Material::LAMBERTIAN: check(trt_add_lambertian(scene, m->rgb.data(), &id)); break;
+                    case Material::METAL: check(trt_add_metal(scene, m->rgb.data(), m->param, &id)); break;
+                    case Material::DIELECTRIC: check(trt_add_dielectric(scene, m->rgb.data(), m->param, &id)); break;
+                    default: check(trt_add_light(scene, m->rgb.data(), &id));
+                }
+                return ids[m.get()] = id;
+            };
+            for (const Geometry& g : world.geometries()) {
+                if (!g.material) throw Error(TRT_ERR_INVALID, "geometry without material");
+                uint32_t m = mat_id(g.material);
+                if (g.is_quad) check(trt_add_quad(scene, g.a.data(), g.u.data(), g.v.data(), m, nullptr));
+                else check(trt_add_sphere(scene, g.a.data(), g.radius, m, nullptr));
+            }
+            check(trt_scene_commit(scene, bvh_kind_));
+            trt_params p{};
+            p.width = camera.pod.width; p.height = camera.pod.height; p.spp = spp_; p.sample_offset = 0; p.max_bounces = max_bounces_;
+            p.background[0] = bg_.x; p.background[1] = bg_.y; p.background[2] = bg_.z;
+            p.seed = seed_; p.t_min = 0.001f; p.spp_total = spp_; p.variant = variant_; p.flags = 0;
+            Image img; img.width = p.width; img.height = p.height;
+            img.linear.resize((size_t)p.width * p.height * 3); img.rgb8.resize(img.linear.size());
+            check(trt_render(ctx, scene, &camera.pod, &p, img.linear.data(), img.rgb8.data(), &last_stats));
+            trt_scene_destroy(scene); trt_ctx_destroy(ctx);
+            return img;
+        } catch (...) { trt_scene_destroy(scene); trt_ctx_destroy(ctx); throw; }
+    }
+    trt_stats last_stats{};
+private:
+    uint32_t spp_, max_bounces_; Vec3 bg_; uint64_t seed_; int device_; int bvh_kind_; uint32_t variant_;
+};
+
+} // namespace trt

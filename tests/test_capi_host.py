@@ -111,3 +111,24 @@ def test_reference_api_mirror(trt, tmp_path):
     p = tmp_path / "x.png"; img.save(str(p))
     raw = p.read_bytes()
     assert raw[:8] == b"\x89PNG\r\n\x1a\n" and img.size() == (5, 4)
+
+
+def test_rust_bindings_name_every_symbol():
+    """rust/trt-sys/src/lib.rs is source only (no Rust toolchain here); keep it in lock-step with include/trt.h."""
+    hdr = open(os.path.join(ROOT, "include", "trt.h")).read()
+    declared = set(re.findall(r"\b(trt_[a-z0-9_]+)\s*\(", hdr))
+    rs = open(os.path.join(ROOT, "rust", "trt-sys", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (trt_[a-z0-9_]+)\s*\(", rs))
+    assert declared == bound, declared ^ bound
+
+
+def test_cpp_mirror_compiles_and_fails_loudly_without_gpu(trt, tmp_path):
+    """include/trt.hpp + examples/cornell.cpp (main.rs translated) compile and link against the C ABI."""
+    exe = str(tmp_path / "cornell")
+    pkg = os.path.join(ROOT, "tiny-raytracer_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "cornell.cpp"), "-o", exe, "-L" + pkg, "-ltrt_b200", "-Wl,-rpath," + pkg])
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, str(tmp_path / "o.ppm")], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU path" in r.stderr
