@@ -65,6 +65,10 @@ typedef struct trt_params {
     uint32_t flags;              /* TRT_FLAG_* */
 } trt_params;
 #define TRT_FLAG_COUNT_EVENTS 1u   /* also count node visits / primitive tests (slower; for roofline accounting) */
+/* bits 8..15 of flags: megakernel tuning override, the number of lanes of a warp (1..32) that must have finished their ray
+ * before the shade/regenerate block runs; 0 = chosen from the tree size (32 for tiny trees, 8 for big ones). Results do not
+ * depend on it. */
+#define TRT_FLAG_REGEN_MIN(n) (((uint32_t)(n) & 0xFFu) << 8)
 
 typedef struct trt_stats {
     uint64_t paths, rays;                          /* pixel-samples; ray segments = iterations of sampler/cpu.rs:47 */

@@ -15,6 +15,7 @@ ap.add_argument("--kinds", default="0,1")
 ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--c4n", type=int, default=1_000_000)
+ap.add_argument("--regen", default="0", help="comma list of regen_min overrides (0 = auto)")
 a = ap.parse_args()
 
 ctx = trt.Context(0)
@@ -32,14 +33,15 @@ for wl in a.workloads.split(","):
         sc.upload(ctx)
         acc = torch.zeros(h * w * 3, dtype=torch.float64, device="cuda:0")
         torch.cuda.synchronize()
-        p = trt.make_params(w, h, a.spp, desc.max_bounces, desc.background, desc.seed, spp_total=a.spp, variant=a.variant)
-        best = None
-        for r in range(a.reps):
-            acc.zero_(); torch.cuda.synchronize()
-            st = sc.render_accumulate(ctx, cam, p, acc.data_ptr())
-            if best is None or st.device_ms < best.device_ms:
-                best = st
-        print("%-3s kind=%d variant=%d spp=%d  build %.2fs  %s  %.2f ms  %.1f Mpaths/s  %.1f Mrays/s  rays/path %.2f" % (
-            wl, kind, a.variant, a.spp, t_build, sc.bvh_info(), best.device_ms, best.paths / best.device_ms / 1e3,
-            best.rays / best.device_ms / 1e3, best.rays / max(best.paths, 1)), flush=True)
+        for regen in [int(x) for x in a.regen.split(",")]:
+            p = trt.make_params(w, h, a.spp, desc.max_bounces, desc.background, desc.seed, spp_total=a.spp, variant=a.variant, flags=(regen & 255) << 8)
+            best = None
+            for r in range(a.reps):
+                acc.zero_(); torch.cuda.synchronize()
+                st = sc.render_accumulate(ctx, cam, p, acc.data_ptr())
+                if best is None or st.device_ms < best.device_ms:
+                    best = st
+            print("%-3s kind=%d variant=%d spp=%d regen=%d  build %.2fs  nodes %d  %.2f ms  %.1f Mpaths/s  %.1f Mrays/s  rays/path %.2f" % (
+                wl, kind, a.variant, a.spp, regen, t_build, sc.bvh_info()["nodes"], best.device_ms, best.paths / best.device_ms / 1e3,
+                best.rays / best.device_ms / 1e3, best.rays / max(best.paths, 1)), flush=True)
         sc.close()

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtrt_b200.so")
+LIB_PATH = os.environ.get("TRT_B200_LIB") or os.path.join(_HERE, "libtrt_b200.so")   # override: A/B builds of the same ABI
 
 TRT_OK = 0
 BVH_REFERENCE, BVH_SAH, BVH_FLAT, BVH_AUTO = 0, 1, 2, 3

@@ -6,8 +6,8 @@ cd "$(dirname "$0")"
 CUDA=${CUDA_HOME:-/usr/local/cuda}
 NVCC=${NVCC:-$CUDA/bin/nvcc}
 CXX=${CXX:-g++}
-OUT=../libtrt_b200.so
-DEVFLAGS="-std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -fmad=false -prec-div=true -prec-sqrt=true -ftz=false"
+OUT=${TRT_OUT:-../libtrt_b200.so}
+DEVFLAGS="${TRT_EXTRA_DEVFLAGS:-} -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -fmad=false -prec-div=true -prec-sqrt=true -ftz=false"
 HOSTFLAGS="-std=c++17 -O2 -fPIC -ffp-contract=off -fno-fast-math -Wall -pthread"
 $NVCC $DEVFLAGS -Xcompiler -fPIC,-ffp-contract=off ${TRT_PTXAS_V:+-Xptxas -v} -c trt_kernels.cu -o trt_kernels.o
 $NVCC $DEVFLAGS -Xcompiler -fPIC,-ffp-contract=off ${TRT_PTXAS_V:+-Xptxas -v} -c trt_wavefront.cu -o trt_wavefront.o

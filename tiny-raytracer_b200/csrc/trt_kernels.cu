@@ -17,7 +17,13 @@
 
 using namespace trtd;
 
-#define MEGA_THREADS 256
+#ifndef TRT_MEGA_THREADS
+#define TRT_MEGA_THREADS 256
+#endif
+#ifndef TRT_MEGA_MIN_BLOCKS
+#define TRT_MEGA_MIN_BLOCKS 4      // 64 registers, ~120 B of spills that stay in L1: measured +6 % (Cornell) and +14 % (1 M spheres) over 3 blocks at 80 registers
+#endif
+#define MEGA_THREADS TRT_MEGA_THREADS
 
 // ------------------------------------------------------------------ shared-memory staging of small scenes
 // layout: [nodes | spheres | quads | sphere_meta | quad_meta | materials | flat list | per-thread phase-A columns]
@@ -53,6 +59,7 @@ struct MegaArgs {
     unsigned long long* counters;  // [0] rays [1] paths [2] node_visits [3] sphere_tests [4] quad_tests
     unsigned int* next_item;       // work counter
     uint32_t chunk, n_chunks, tiles_x, tiles_y, n_items;
+    uint32_t regen_min;            // lanes that must be waiting before the shade/regenerate block runs (32 = T-then-S)
 };
 struct FlatList { FlatPrim prim[TRT_FLAT_MAX]; };
 
@@ -165,11 +172,118 @@ __device__ __forceinline__ void mega_body(const MegaArgs& A, const FlatPrim* U) 
     }
 }
 
+// The tree kinds use this form of the same loop: the traversal is advanced ONE step (trav_step) per iteration, and the
+// S block runs as soon as `A.regen_min` lanes have finished their ray (or nobody is traversing any more). With
+// regen_min = 32 this is the T-then-S schedule above; smaller values stop a warp from idling behind its slowest ray,
+// which pays when a ray costs many steps (1 M spheres: ~50 node steps per ray and 7.7 of 32 lanes active under the
+// T-then-S schedule, profiles/r1g) and costs when S (≈ 800 instructions) would run for a handful of lanes on a
+// 7-step Cornell ray. The launcher picks regen_min from the tree size; trt_params.flags bits 8..15 override it.
 template <int KIND, bool SMEM, bool COUNT>
-__global__ void __launch_bounds__(MEGA_THREADS, 3) k_render_mega(const __grid_constant__ MegaArgs A) {
-    mega_body<KIND, SMEM, COUNT>(A, nullptr);
+__device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
+    float* tt;
+    const DevScene S = stage_scene<SMEM>(A.scene, &tt);
+    const DevParams& P = A.p;
+    const uint32_t lane = threadIdx.x & 31u;
+    Trav T; T.cur = TRT_REF_INVALID; T.sp = 0; T.best.t = TRT_INF; T.best.ref = TRT_REF_INVALID;
+    T.o = mk(0, 0, 0); T.d = mk(0, 0, 1); T.inv = mk(0, 0, 1); T.t_min = P.t_min; T.tame = false; T.best_rank = 0xFFFFFFFFu;
+    uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
+    V3 atten = mk(1, 1, 1), color = mk(0, 0, 0);
+    uint32_t pixel = 0, px = 0, py = 0, s_cur = 0, s_end = 0, remain = 0, k = 0;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    bool alive = false, done = false, has_item = false;     // alive: the lane carries a path; T.cur != INVALID: its ray is still being traced
+    uint32_t n_rays = 0, n_paths = 0;
+    EventCounters ec; ec.node_visits = ec.sphere_tests = ec.quad_tests = 0;
+    const int regen_min = (int)A.regen_min;
+
+    for (;;) {
+        // ---- T: one step of cpu.rs:48 for every lane whose ray is in flight
+        if (T.cur != TRT_REF_INVALID) trav_step<KIND == 1, SMEM, COUNT>(T, S, stack_ref, stack_t, &ec);
+        const bool tracing = T.cur != TRT_REF_INVALID;
+        const unsigned tm = __ballot_sync(0xFFFFFFFFu, tracing);
+        const unsigned wm = __ballot_sync(0xFFFFFFFFu, !tracing && !done);
+        if (tm != 0u && __popc(wm) < regen_min) continue;
+        // ---- S1: cpu.rs:49-61 up to the scatter decision, for the lanes whose ray just finished
+        const bool in_s = !tracing && !done;
+        Surface sf; sf.kind = TRT_MAT_LIGHT; sf.front = false; sf.param = 0.f;
+        sf.point = sf.normal = sf.rgb = mk(0, 0, 0);
+        bool scatter = false;
+        if (in_s && alive) {
+            const Hit h = T.best;
+            if (h.ref == TRT_REF_INVALID) color = color + atten * mk(P.bg[0], P.bg[1], P.bg[2]);
+            else {
+                sf = hit_record<SMEM>(S, h, T.o, T.d);
+                V3 emission = (sf.kind == TRT_MAT_LIGHT) ? sf.rgb : mk(0.0f, 0.0f, 0.0f);
+                color = color + atten * emission;
+                scatter = sf.kind != TRT_MAT_LIGHT && remain > 1;
+            }
+            if (!scatter) {       // imager.rs:50 (f64 here)
+                acc0 += (double)color.x; acc1 += (double)color.y; acc2 += (double)color.z;
+                alive = false; ++s_cur; ++n_paths;
+            }
+        }
+        // ---- S2: work fetch for lanes whose chunk is finished (warp-aggregated atomic)
+        bool need_item = in_s && !alive && s_cur == s_end;
+        unsigned m = __ballot_sync(0xFFFFFFFFu, need_item);
+        if (m) {
+            if (need_item && has_item) {
+                double* dst = A.sum64 + 3 * (size_t)pixel;
+                if (A.n_chunks == 1) { dst[0] += acc0; dst[1] += acc1; dst[2] += acc2; }
+                else { atomicAdd(dst, acc0); atomicAdd(dst + 1, acc1); atomicAdd(dst + 2, acc2); }
+                has_item = false;
+            }
+            int leader = __ffs(m) - 1;
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(A.next_item, (unsigned)__popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (need_item) {
+                uint32_t item = base + __popc(m & ((1u << lane) - 1u));
+                if (item < A.n_items) {
+                    uint32_t s0, s1;
+                    if (decode_item(A, item, &px, &py, &s0, &s1)) {
+                        pixel = py * P.width + px; s_cur = s0; s_end = s1; has_item = true;
+                        acc0 = acc1 = acc2 = 0.0;
+                        if (P.max_bounces == 0) { n_paths += s1 - s0; s_cur = s1; }
+                    }
+                } else done = true;
+            }
+        }
+        // ---- S3: next ray of the lanes that scatter or start a new path; its traversal state is set up here
+        bool regen = in_s && !alive && !done && s_cur < s_end;
+        if (scatter || regen) {
+            uint32_t sample = P.sample_offset + s_cur;
+            if (scatter) ++k; else k = 0;
+            U4 r = philox4x32_10(pixel, sample, k, 0u, P.seed_lo, P.seed_hi);
+            V3 o, dir;
+            if (scatter) {
+                dir = scatter_direction(sf, T.d, r);
+                atten = atten * sf.rgb; o = sf.point; --remain;
+            } else {
+                camera_ray(A.cam, P, px, py, pixel, sample, r, &o, &dir);
+                atten = mk(1, 1, 1); color = mk(0, 0, 0); remain = P.max_bounces; alive = true;
+            }
+            trav_begin<COUNT>(T, S, o, normalized(dir), P.t_min, &ec);      // Ray::new normalises, ray.rs:12-14
+            ++n_rays;
+            // an empty scene (or, when counting, a ray that misses the root box) is finished at once: T.cur stays INVALID
+            // and the lane re-enters S on the next pass with T.best = miss.
+        }
+        if (__all_sync(0xFFFFFFFFu, done)) break;
+    }
+    unsigned long long r = n_rays, pth = n_paths;
+    for (int off = 16; off; off >>= 1) { r += __shfl_xor_sync(0xFFFFFFFFu, r, off); pth += __shfl_xor_sync(0xFFFFFFFFu, pth, off); }
+    if (lane == 0) { atomicAdd(A.counters, r); atomicAdd(A.counters + 1, pth); }
+    if (COUNT) {
+        unsigned long long a = ec.node_visits, b = ec.sphere_tests, c = ec.quad_tests;
+        for (int off = 16; off; off >>= 1) { a += __shfl_xor_sync(0xFFFFFFFFu, a, off); b += __shfl_xor_sync(0xFFFFFFFFu, b, off); c += __shfl_xor_sync(0xFFFFFFFFu, c, off); }
+        if (lane == 0) { atomicAdd(A.counters + 2, a); atomicAdd(A.counters + 3, b); atomicAdd(A.counters + 4, c); }
+    }
 }
-__global__ void __launch_bounds__(MEGA_THREADS, 3) k_render_mega_flat(const __grid_constant__ MegaArgs A, const __grid_constant__ FlatList L) {
+
+template <int KIND, bool SMEM, bool COUNT>
+__global__ void __launch_bounds__(MEGA_THREADS, TRT_MEGA_MIN_BLOCKS) k_render_mega(const __grid_constant__ MegaArgs A) {
+    if (A.regen_min >= 32u) mega_body<KIND, SMEM, COUNT>(A, nullptr);
+    else mega_body_async<KIND, SMEM, COUNT>(A);
+}
+__global__ void __launch_bounds__(MEGA_THREADS, TRT_MEGA_MIN_BLOCKS) k_render_mega_flat(const __grid_constant__ MegaArgs A, const __grid_constant__ FlatList L) {
     mega_body<2, true, false>(A, L.prim);
 }
 
@@ -282,6 +396,12 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     MegaArgs A;
     A.scene = dev_scene(v); A.cam = dev_camera(cam); A.p = dev_params(p);
     A.sum64 = d_sum64; A.counters = d_counters; A.next_item = d_next_item;
+    // shade/regenerate threshold: trees of a few dozen nodes cost ~7 steps per ray and S is ~800 instructions, so S must run
+    // for the whole warp; big trees cost ~50 steps per ray and waiting for the slowest of 32 rays wastes 3/4 of the lanes.
+    uint32_t regen = (p.flags >> 8) & 0xFFu;
+    // measured (B200, regen sweep): Cornell 17 nodes, glass Cornell 33, final scene 486: 32 best; 1 M spheres: 16 best (+25 %)
+    if (regen == 0) regen = v.n_nodes <= 4096 ? 32u : 16u;
+    A.regen_min = regen > 32u ? 32u : regen;
     size_t smem = scene_smem_bytes(v);
     bool use_smem = smem <= 64 * 1024;
     if (v.kind == 2 && (!use_smem || v.n_flat > TRT_FLAT_MAX || !v.flat_host)) return cudaErrorInvalidValue;
