@@ -146,6 +146,19 @@ int trt_render_aov(trt_ctx* ctx, trt_scene* scene, const trt_camera* cam, const 
 int trt_sample_batch(trt_ctx* ctx, trt_scene* scene, const trt_sample_point* in, size_t n, const trt_params* p,
                      trt_sampled_color* out);
 
+/* Streaming form of the same adapter: what MetalSampler::add_command / sampling do with command
+ * buffers (renderer/sampler/metal/sampler.rs:43-88,107-130). Two slots of pinned host + device buffers on two streams:
+ * submit() queues H2D copy + kernel + D2H copy of one batch (<= batch_capacity samples; the reference's batch is 10 240,
+ * metal/sampler.rs:11) and returns; collect() waits for the OLDEST batch in flight and returns its colours in submission
+ * order. At most two batches are in flight: a third submit() fails with TRT_ERR_INVALID until one is collected.
+ * Item i of the whole stream uses the RNG stream (pixel, sample = params.sample_offset + i), so streaming equals one
+ * trt_sample_batch call over the concatenated input. */
+typedef struct trt_sampler trt_sampler;
+int trt_sampler_create(trt_ctx* ctx, trt_scene* scene, const trt_params* p, size_t batch_capacity, trt_sampler** out);
+int trt_sampler_submit(trt_sampler* sampler, const trt_sample_point* in, size_t n);
+int trt_sampler_collect(trt_sampler* sampler, trt_sampled_color* out, size_t* n_out);
+int trt_sampler_destroy(trt_sampler* sampler);
+
 /* Closest hit for arbitrary rays (Hittable::hit on the BVH, hittable/bvh.rs:25-27), HOST buffers, directions as given. */
 int trt_trace_rays(trt_ctx* ctx, trt_scene* scene, size_t n, const float* origins, const float* dirs, float t_min,
                    uint32_t* prim_id, float* t);

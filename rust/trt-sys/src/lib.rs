@@ -5,6 +5,7 @@ use std::os::raw::{c_char, c_int, c_void};
 
 #[repr(C)] pub struct trt_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct trt_scene { _p: [u8; 0] }
+#[repr(C)] pub struct trt_sampler { _p: [u8; 0] }
 
 pub const TRT_OK: c_int = 0;
 pub const TRT_BVH_REFERENCE: c_int = 0;
@@ -69,6 +70,10 @@ extern "C" {
                           prim_id: *mut u32, t: *mut f32, radiance: *mut f32, n_rays: *mut u32) -> c_int;
     pub fn trt_sample_batch(ctx: *mut trt_ctx, scene: *mut trt_scene, input: *const trt_sample_point, n: usize,
                             p: *const trt_params, out: *mut trt_sampled_color) -> c_int;
+    pub fn trt_sampler_create(ctx: *mut trt_ctx, scene: *mut trt_scene, p: *const trt_params, batch_capacity: usize, out: *mut *mut trt_sampler) -> c_int;
+    pub fn trt_sampler_submit(sampler: *mut trt_sampler, input: *const trt_sample_point, n: usize) -> c_int;
+    pub fn trt_sampler_collect(sampler: *mut trt_sampler, out: *mut trt_sampled_color, n_out: *mut usize) -> c_int;
+    pub fn trt_sampler_destroy(sampler: *mut trt_sampler) -> c_int;
     pub fn trt_trace_rays(ctx: *mut trt_ctx, scene: *mut trt_scene, n: usize, origins: *const f32, dirs: *const f32, t_min: f32,
                           prim_id: *mut u32, t: *mut f32) -> c_int;
     pub fn trt_debug_math(ctx: *mut trt_ctx, n: usize, u: *const f32, sin2pi: *mut f32, cos2pi: *mut f32, cbrt_out: *mut f32) -> c_int;

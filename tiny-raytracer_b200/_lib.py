@@ -78,6 +78,10 @@ SYMBOLS = {
     "trt_finalize": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, C.POINTER(Stats)]),
     "trt_render_aov": (C.c_int, [_P, _P, C.POINTER(Camera), C.POINTER(Params), _P, _P, _P, _P]),
     "trt_sample_batch": (C.c_int, [_P, _P, _P, C.c_size_t, C.POINTER(Params), _P]),
+    "trt_sampler_create": (C.c_int, [_P, _P, C.POINTER(Params), C.c_size_t, C.POINTER(_P)]),
+    "trt_sampler_submit": (C.c_int, [_P, _P, C.c_size_t]),
+    "trt_sampler_collect": (C.c_int, [_P, _P, C.POINTER(C.c_size_t)]),
+    "trt_sampler_destroy": (C.c_int, [_P]),
     "trt_trace_rays": (C.c_int, [_P, _P, C.c_size_t, _P, _P, C.c_float, _P, _P]),
     "trt_debug_math": (C.c_int, [_P, C.c_size_t, _P, _P, _P, _P]),
     "trt_debug_philox": (C.c_int, [_P, C.c_size_t, _P, _U32P, _P]),

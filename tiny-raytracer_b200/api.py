@@ -209,6 +209,50 @@ class Scene:
         return prim, t
 
 
+class SamplerStream:
+    """Streaming `Sampler` adapter (trt_sampler_*): `sampling(batches)` consumes an iterable of SamplePoint arrays and
+    yields the SampledColor arrays in order, keeping two batches in flight (copy/compute overlap on two streams) — the
+    shape of `Sampler::sampling(world, in_channel, out_channel)` (renderer/sampler/mod.rs:9-16) with channels replaced
+    by an iterator. The adapter ends when the input ends, as the reference's samplers do when `in_channel` closes."""
+
+    def __init__(self, ctx: Context, scene: "Scene", params: L.Params, batch_capacity: int = 10240):
+        self._lib = L.load()
+        h = C.c_void_p()
+        L.check(self._lib.trt_sampler_create(ctx._h, scene._h, C.byref(params), int(batch_capacity), C.byref(h)))
+        self._h, self.capacity = h, int(batch_capacity)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.trt_sampler_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def submit(self, points: np.ndarray):
+        pts = np.ascontiguousarray(points, SAMPLE_POINT_DTYPE)
+        L.check(self._lib.trt_sampler_submit(self._h, _ptr(pts), int(pts.shape[0])))
+
+    def collect(self):
+        out = np.empty(self.capacity, SAMPLED_COLOR_DTYPE)
+        n = C.c_size_t()
+        L.check(self._lib.trt_sampler_collect(self._h, _ptr(out), C.byref(n)))
+        return out[:n.value]
+
+    def sampling(self, batches):
+        in_flight = 0
+        for b in batches:
+            for lo in range(0, max(len(b), 1), self.capacity):
+                if in_flight == 2:
+                    yield self.collect(); in_flight -= 1
+                self.submit(b[lo:lo + self.capacity]); in_flight += 1
+        while in_flight:
+            yield self.collect(); in_flight -= 1
+
+
 SAMPLE_POINT_DTYPE = np.dtype([("x", np.uint32), ("y", np.uint32), ("origin", np.float32, 3), ("direction", np.float32, 3)])
 SAMPLED_COLOR_DTYPE = np.dtype([("x", np.uint32), ("y", np.uint32), ("color", np.float32, 3)])
 assert SAMPLE_POINT_DTYPE.itemsize == 32 and SAMPLED_COLOR_DTYPE.itemsize == 20

@@ -358,6 +358,87 @@ int trt_sample_batch(trt_ctx* c, trt_scene* s, const trt_sample_point* in, size_
     return TRT_OK;
 }
 
+// ---- streaming Sampler adapter: two slots of pinned host + device buffers on two streams, so that the H2D copy of batch
+//      i+1 and the D2H copy of batch i-1 overlap the kernel of batch i (the reference's MetalSampler keeps every command
+//      buffer in flight and waits at the end, metal/sampler.rs:107-130; here at most two batches are in flight).
+struct SamplerSlot {
+    cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
+    trt_sample_point* h_in = nullptr; trt_sampled_color* h_out = nullptr; void* d_in = nullptr; void* d_out = nullptr;
+    size_t n = 0; bool busy = false;
+};
+struct trt_sampler {
+    trt_ctx* ctx; trt_scene* scene; trt_params params; size_t capacity; uint32_t next_sample;
+    SamplerSlot slot[2]; int head = 0, tail = 0, in_flight = 0;   // FIFO over the two slots
+};
+
+int trt_sampler_create(trt_ctx* c, trt_scene* s, const trt_params* p, size_t batch_capacity, trt_sampler** out) {
+    if (!c || !s || !p || !out || batch_capacity == 0) return fail(TRT_ERR_INVALID, "trt_sampler_create: bad argument");
+    if (!s->host.committed) return fail(TRT_ERR_INVALID, "trt_sampler_create: scene not committed (call trt_scene_commit)");
+    CU(cudaSetDevice(c->device));
+    int rc; if ((rc = trt_scene_upload(c, s))) return rc;
+    trt_sampler* a = new (std::nothrow) trt_sampler();
+    if (!a) return fail(TRT_ERR_OOM, "trt_sampler_create: host allocation failed");
+    a->ctx = c; a->scene = s; a->params = *p; a->capacity = batch_capacity; a->next_sample = p->sample_offset;
+    for (SamplerSlot& k : a->slot) {
+        cudaError_t e = cudaStreamCreateWithFlags(&k.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&k.done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&k.h_in, batch_capacity * sizeof(trt_sample_point));
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&k.h_out, batch_capacity * sizeof(trt_sampled_color));
+        if (e == cudaSuccess) e = cudaMalloc(&k.d_in, batch_capacity * sizeof(trt_sample_point));
+        if (e == cudaSuccess) e = cudaMalloc(&k.d_out, batch_capacity * sizeof(trt_sampled_color));
+        if (e != cudaSuccess) { trt_sampler_destroy(a); return fail_cuda("trt_sampler_create", e); }
+    }
+    *out = a;
+    return TRT_OK;
+}
+int trt_sampler_destroy(trt_sampler* a) {
+    if (!a) return TRT_OK;
+    cudaSetDevice(a->ctx->device);
+    for (SamplerSlot& k : a->slot) {
+        if (k.stream) cudaStreamSynchronize(k.stream);
+        if (k.h_in) cudaFreeHost(k.h_in);
+        if (k.h_out) cudaFreeHost(k.h_out);
+        if (k.d_in) cudaFree(k.d_in);
+        if (k.d_out) cudaFree(k.d_out);
+        if (k.done) cudaEventDestroy(k.done);
+        if (k.stream) cudaStreamDestroy(k.stream);
+    }
+    delete a;
+    return TRT_OK;
+}
+// Queues one batch (n <= capacity). Returns TRT_ERR_INVALID if both slots are in flight: collect first.
+int trt_sampler_submit(trt_sampler* a, const trt_sample_point* in, size_t n) {
+    if (!a || (n && !in)) return fail(TRT_ERR_INVALID, "trt_sampler_submit: null argument");
+    if (n > a->capacity) return fail(TRT_ERR_INVALID, "trt_sampler_submit: batch larger than the adapter's capacity");
+    if (a->in_flight == 2) return fail(TRT_ERR_INVALID, "trt_sampler_submit: two batches in flight, call trt_sampler_collect first");
+    CU(cudaSetDevice(a->ctx->device));
+    SamplerSlot& k = a->slot[a->head];
+    const trtk::SceneView& v = a->scene->on_device[a->ctx->device].view;
+    if (n) std::memcpy(k.h_in, in, n * sizeof(trt_sample_point));
+    trt_params p = a->params; p.sample_offset = a->next_sample;        // item i of the whole stream uses sample_offset + i
+    if (n) CU(cudaMemcpyAsync(k.d_in, k.h_in, n * sizeof(trt_sample_point), cudaMemcpyHostToDevice, k.stream));
+    CU(trtk::launch_sample_batch(v, p, (const trt_sample_point_pod*)k.d_in, n, (trt_sampled_color_pod*)k.d_out, k.stream));
+    if (n) CU(cudaMemcpyAsync(k.h_out, k.d_out, n * sizeof(trt_sampled_color), cudaMemcpyDeviceToHost, k.stream));
+    CU(cudaEventRecord(k.done, k.stream));
+    k.n = n; k.busy = true;
+    a->next_sample += (uint32_t)n; a->head ^= 1; a->in_flight++;
+    return TRT_OK;
+}
+// Waits for the oldest batch in flight and copies its colours out (same order as submitted). *n_out = 0 when nothing is in flight.
+int trt_sampler_collect(trt_sampler* a, trt_sampled_color* out, size_t* n_out) {
+    if (!a || !n_out) return fail(TRT_ERR_INVALID, "trt_sampler_collect: null argument");
+    *n_out = 0;
+    if (a->in_flight == 0) return TRT_OK;
+    CU(cudaSetDevice(a->ctx->device));
+    SamplerSlot& k = a->slot[a->tail];
+    CU(cudaEventSynchronize(k.done));
+    if (k.n && !out) return fail(TRT_ERR_INVALID, "trt_sampler_collect: out is null");
+    if (k.n) std::memcpy(out, k.h_out, k.n * sizeof(trt_sampled_color));
+    *n_out = k.n; k.busy = false;
+    a->tail ^= 1; a->in_flight--;
+    return TRT_OK;
+}
+
 int trt_trace_rays(trt_ctx* c, trt_scene* s, size_t n, const float* origins, const float* dirs, float t_min, uint32_t* prim_id, float* t) {
     if (!c || !s || (n && (!origins || !dirs || !prim_id || !t))) return fail(TRT_ERR_INVALID, "trt_trace_rays: null argument");
     if (!s->host.committed) return fail(TRT_ERR_INVALID, "trt_trace_rays: scene not committed (call trt_scene_commit)");
