@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c1s", "c2", "c3", "c4", "c5"])
     ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel (0 = BASELINE value)")
-    ap.add_argument("--bvh", default="auto", choices=["auto", "sah", "reference", "flat"])
+    ap.add_argument("--bvh", default="auto", choices=["auto", "sah", "reference", "flat", "lbvh"])
     ap.add_argument("--variant", default="megakernel", choices=["megakernel", "wavefront"])
     ap.add_argument("--ref-spp", type=int, default=4, help="--impl reference: samples per pixel per step (bounded sample)")
     ap.add_argument("--warmup-ref", type=int, default=1)
@@ -185,7 +185,7 @@ def main():
 
     desc = workload_desc(args.workload, args.spp or None)
     c = desc.camera; W, H, SPP = c["width"], c["height"], desc.spp
-    kind = {"auto": trt.BVH_AUTO, "sah": trt.BVH_SAH, "reference": trt.BVH_REFERENCE, "flat": trt.BVH_FLAT}[args.bvh]
+    kind = {"auto": trt.BVH_AUTO, "sah": trt.BVH_SAH, "reference": trt.BVH_REFERENCE, "flat": trt.BVH_FLAT, "lbvh": trt.BVH_LBVH_DEVICE}[args.bvh]
     variant = trt.VARIANT_MEGAKERNEL if args.variant == "megakernel" else trt.VARIANT_WAVEFRONT
     ctx = trt.Context(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)   # same stream as torch's events and the NCCL reduce

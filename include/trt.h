@@ -35,7 +35,9 @@ typedef enum trt_bvh_kind {
     TRT_BVH_REFERENCE = 0,   /* the reference's median-split topology, traversed left-first: reference results by construction */
     TRT_BVH_SAH = 1,         /* binned-SAH topology, near-child-first traversal, ties broken by reference leaf order */
     TRT_BVH_FLAT = 2,        /* no tree: <= 48 primitives as a list in reference leaf order; reference results by construction */
-    TRT_BVH_AUTO = 3         /* REFERENCE when the scene has <= 64 primitives (as fast there, exact by construction), else SAH */
+    TRT_BVH_AUTO = 3,        /* REFERENCE when the scene has <= 64 primitives (as fast there, exact by construction), else SAH */
+    TRT_BVH_LBVH_DEVICE = 4  /* built on the GPU during trt_scene_upload (Morton codes + radix sort + Karras), walked like SAH;
+                                no host tree: exact-t ties between different primitives go to the lower prim_id */
 } trt_bvh_kind;
 
 /* Which kernel family renders. */
@@ -114,6 +116,9 @@ int trt_scene_commit(trt_scene* scene, int bvh_kind);
 /* left-to-right leaf order of the reference-topology tree, indexed by prim_id (after commit) */
 int trt_scene_leaf_ranks(trt_scene* scene, uint32_t* rank_of_prim);
 int trt_scene_bvh_info(trt_scene* scene, uint32_t* n_nodes, uint32_t* max_depth, float* sah_cost);
+/* Seconds-scale costs of the last commit / upload: host build time of trt_scene_commit and, for TRT_BVH_LBVH_DEVICE, the
+ * CUDA-event time of the build on the GPU (0 until uploaded). */
+int trt_scene_build_times(trt_scene* scene, float* host_commit_ms, float* device_build_ms);
 /* Copies the flattened scene into the GPU's HBM (replaces MetalAccelerationStructure::new, metal/accelstructure.rs:17-75). */
 int trt_scene_upload(trt_ctx* ctx, trt_scene* scene);
 

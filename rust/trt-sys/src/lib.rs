@@ -12,6 +12,7 @@ pub const TRT_BVH_REFERENCE: c_int = 0;
 pub const TRT_BVH_SAH: c_int = 1;
 pub const TRT_BVH_FLAT: c_int = 2;
 pub const TRT_BVH_AUTO: c_int = 3;
+pub const TRT_BVH_LBVH_DEVICE: c_int = 4;
 pub const TRT_VARIANT_MEGAKERNEL: u32 = 0;
 pub const TRT_VARIANT_WAVEFRONT: u32 = 1;
 
@@ -57,6 +58,7 @@ extern "C" {
     pub fn trt_scene_commit(scene: *mut trt_scene, bvh_kind: c_int) -> c_int;
     pub fn trt_scene_leaf_ranks(scene: *mut trt_scene, rank_of_prim: *mut u32) -> c_int;
     pub fn trt_scene_bvh_info(scene: *mut trt_scene, n_nodes: *mut u32, max_depth: *mut u32, sah_cost: *mut f32) -> c_int;
+    pub fn trt_scene_build_times(scene: *mut trt_scene, host_commit_ms: *mut f32, device_build_ms: *mut f32) -> c_int;
     pub fn trt_scene_upload(ctx: *mut trt_ctx, scene: *mut trt_scene) -> c_int;
     pub fn trt_camera_make(focus_distance: f32, defocus_angle: f32, position: *const f32, look_at: *const f32, up: *const f32,
                            vertical_fov: f32, width: u32, height: u32, out: *mut trt_camera) -> c_int;

@@ -441,3 +441,36 @@ def test_streaming_sampler_adapter(trt, orc, ctx):
     with pytest.raises(trt.TrtError):
         st.submit(pts[:200])                                             # larger than the capacity
     st.close()
+
+
+def test_device_built_bvh(trt, orc, ctx):
+    """TRT_BVH_LBVH_DEVICE: the tree is built on the GPU (Morton + radix sort + Karras) and walked like
+    the SAH tree. Closest-hit t must equal the oracle's bit for bit; the primitive id may differ only where two different
+    primitives are hit at exactly the same t (no host reference tree -> ties go to the lower prim_id) or in the
+    grazing-hit class of DESIGN.md §4.3 (rate bounded)."""
+    for desc, n_rays in ((trt.scenes.random_spheres(200_000, 64, 64, 1, 3), 300_000), (trt.scenes.random_mixed(3000, 17), 200_000),
+                         (trt.scenes.final_scene(), 200_000), (trt.scenes.cornell(), 100_000)):
+        osc = orc.Scene.from_desc(desc)
+        sc = trt.Scene.from_desc(desc, trt.BVH_LBVH_DEVICE)
+        sc.upload(ctx)
+        info, times = sc.bvh_info(), sc.build_times()
+        assert info["nodes"] == desc.n_prims - 1 and 0 < info["max_depth"] <= 64 and times["device_build_ms"] > 0
+        rng = np.random.default_rng(7)
+        lo = np.maximum(desc.prim_data[:, :3].min(0) - 3, -120); hi = np.minimum(desc.prim_data[:, :3].max(0) + 3, 120)
+        o = rng.uniform(lo, hi, (n_rays, 3)).astype(np.float32)
+        d = rng.normal(size=(n_rays, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+        prim, t = sc.trace_rays(ctx, o, d, 0.001)
+        oprim, ot = osc.trace_rays(o, d, 0.001, use_bvh=True)
+        t_bad = bits(t) != bits(ot)
+        assert t_bad.sum() <= max(2, int(2e-5 * n_rays)), "%s: %d t mismatches" % (desc.name, int(t_bad.sum()))
+        tie = (prim != oprim) & ~t_bad
+        assert ((prim[tie] != 0xFFFFFFFF) & (oprim[tie] != 0xFFFFFFFF)).all() and (prim[tie] < oprim[tie]).all() or not tie.any()
+        assert (prim != 0xFFFFFFFF).mean() > 0.02
+    # and a whole render through the megakernel on the device-built tree
+    desc = trt.scenes.random_spheres(50_000, 160, 90, 4, 12)
+    osc, ocam, cam = both(trt, orc, desc)
+    p, op = params(trt, orc, desc)
+    olin, ou8, ost, _ = osc.render(ocam, op)
+    lin, u8, st = trt.Scene.from_desc(desc, trt.BVH_LBVH_DEVICE).render(ctx, cam, p)
+    assert st.paths == ost.paths and abs(int(st.rays) - int(ost.rays)) <= 64
+    assert (ulp_diff(lin, olin) > 1).any(axis=2).sum() <= 2 and psnr8(u8, ou8) >= PSNR_MIN_DB

@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TRT_B200_LIB") or os.path.join(_HERE, "libtrt_b200.so")   # override: A/B builds of the same ABI
 
 TRT_OK = 0
-BVH_REFERENCE, BVH_SAH, BVH_FLAT, BVH_AUTO = 0, 1, 2, 3
+BVH_REFERENCE, BVH_SAH, BVH_FLAT, BVH_AUTO, BVH_LBVH_DEVICE = 0, 1, 2, 3, 4
 VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT = 0, 1
 FLAG_COUNT_EVENTS = 1
 
@@ -71,6 +71,7 @@ SYMBOLS = {
     "trt_scene_commit": (C.c_int, [_P, C.c_int]),
     "trt_scene_leaf_ranks": (C.c_int, [_P, _P]),
     "trt_scene_bvh_info": (C.c_int, [_P, _U32P, _U32P, _F3]),
+    "trt_scene_build_times": (C.c_int, [_P, _F3, _F3]),
     "trt_scene_upload": (C.c_int, [_P, _P]),
     "trt_camera_make": (C.c_int, [C.c_float, C.c_float, _F3, _F3, _F3, C.c_float, C.c_uint32, C.c_uint32, C.POINTER(Camera)]),
     "trt_render": (C.c_int, [_P, _P, C.POINTER(Camera), C.POINTER(Params), _P, _P, C.POINTER(Stats)]),

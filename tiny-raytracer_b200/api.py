@@ -20,7 +20,7 @@ import numpy as np
 from . import _lib as L
 from .scenes import SceneDesc, LAMBERTIAN, METAL, DIELECTRIC, LIGHT, SPHERE, QUAD
 
-BVH_REFERENCE, BVH_SAH, BVH_FLAT, BVH_AUTO = L.BVH_REFERENCE, L.BVH_SAH, L.BVH_FLAT, L.BVH_AUTO
+BVH_REFERENCE, BVH_SAH, BVH_FLAT, BVH_AUTO, BVH_LBVH_DEVICE = L.BVH_REFERENCE, L.BVH_SAH, L.BVH_FLAT, L.BVH_AUTO, L.BVH_LBVH_DEVICE
 VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT = L.VARIANT_MEGAKERNEL, L.VARIANT_WAVEFRONT
 
 
@@ -169,6 +169,11 @@ class Scene:
 
     def upload(self, ctx: Context):
         L.check(self._lib.trt_scene_upload(ctx._h, self._h))
+
+    def build_times(self):
+        h, d = C.c_float(), C.c_float()
+        L.check(self._lib.trt_scene_build_times(self._h, C.byref(h), C.byref(d)))
+        return {"host_commit_ms": h.value, "device_build_ms": d.value}
 
     # ---- rendering entry points (HOST buffers)
     def render(self, ctx: Context, cam: L.Camera, params: L.Params, want_linear=True, want_rgb8=True):

@@ -11,7 +11,8 @@ DEVFLAGS="${TRT_EXTRA_DEVFLAGS:-} -std=c++17 -O3 -lineinfo -gencode arch=compute
 HOSTFLAGS="-std=c++17 -O2 -fPIC -ffp-contract=off -fno-fast-math -Wall -pthread"
 $NVCC $DEVFLAGS -Xcompiler -fPIC,-ffp-contract=off ${TRT_PTXAS_V:+-Xptxas -v} -c trt_kernels.cu -o trt_kernels.o
 $NVCC $DEVFLAGS -Xcompiler -fPIC,-ffp-contract=off ${TRT_PTXAS_V:+-Xptxas -v} -c trt_wavefront.cu -o trt_wavefront.o
+$NVCC $DEVFLAGS -Xcompiler -fPIC -c trt_lbvh.cu -o trt_lbvh.o
 $CXX $HOSTFLAGS -I$CUDA/include -c trt_capi.cpp -o trt_capi.o
 $CXX $HOSTFLAGS -c trt_scene.cpp -o trt_scene.o
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT trt_kernels.o trt_wavefront.o trt_capi.o trt_scene.o -Xcompiler -pthread -cudart shared
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT trt_kernels.o trt_wavefront.o trt_lbvh.o trt_capi.o trt_scene.o -Xcompiler -pthread -cudart shared
 echo "built $(realpath $OUT)"

@@ -3,6 +3,7 @@
 #include "../../include/trt.h"
 #include "trt_kernels.h"
 #include "trt_scene.hpp"
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -153,13 +154,22 @@ int trt_scene_num_prims(trt_scene* s, uint32_t* out) { if (!s || !out) return fa
 int trt_scene_commit(trt_scene* s, int bvh_kind) {
     if (!s) return fail(TRT_ERR_INVALID, "trt_scene_commit: null scene");
     std::string err;
-    if (!s->host.commit(bvh_kind, &err)) return fail(bvh_kind >= 0 && bvh_kind <= 3 ? TRT_ERR_UNSUPPORTED : TRT_ERR_INVALID, err);
+    auto t0 = std::chrono::steady_clock::now();
+    if (!s->host.commit(bvh_kind, &err)) return fail(bvh_kind >= 0 && bvh_kind <= 4 ? TRT_ERR_UNSUPPORTED : TRT_ERR_INVALID, err);
+    s->host.host_commit_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    s->host.device_build_ms = 0.f;
     return TRT_OK;
 }
 int trt_scene_leaf_ranks(trt_scene* s, uint32_t* rank) {
     if (!s || !rank) return fail(TRT_ERR_INVALID, "trt_scene_leaf_ranks: null argument");
     if (!s->host.committed) return fail(TRT_ERR_INVALID, "trt_scene_leaf_ranks: scene not committed");
     std::memcpy(rank, s->host.leaf_rank.data(), s->host.leaf_rank.size() * sizeof(uint32_t));
+    return TRT_OK;
+}
+int trt_scene_build_times(trt_scene* s, float* host_commit_ms, float* device_build_ms) {
+    if (!s) return fail(TRT_ERR_INVALID, "trt_scene_build_times: null scene");
+    if (host_commit_ms) *host_commit_ms = s->host.host_commit_ms;
+    if (device_build_ms) *device_build_ms = s->host.device_build_ms;
     return TRT_OK;
 }
 int trt_scene_bvh_info(trt_scene* s, uint32_t* n_nodes, uint32_t* max_depth, float* sah_cost) {
@@ -180,19 +190,34 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
     DeviceCopy& dc = s->on_device[c->device];
     if (dc.buf && dc.version == s->host.version) return TRT_OK;
     const trt::FlatScene& f = s->host.flat;
-    size_t sz[7] = {f.nodes.size() * 16, f.spheres.size() * 16, f.quads.size() * 16, f.sphere_meta.size() * 16, f.quad_meta.size() * 16, f.materials.size() * 16, f.flat.size() * 16};
+    const bool device_build = f.bvh_kind == TRT_BVH_LBVH_DEVICE;
+    const size_t n_prims = s->host.prims.size();
+    size_t sz[7] = {device_build ? 64 * (n_prims - 1) : f.nodes.size() * 16, f.spheres.size() * 16, f.quads.size() * 16, f.sphere_meta.size() * 16, f.quad_meta.size() * 16, f.materials.size() * 16, f.flat.size() * 16};
     const void* src[7] = {f.nodes.data(), f.spheres.data(), f.quads.data(), f.sphere_meta.data(), f.quad_meta.data(), f.materials.data(), f.flat.data()};
     size_t off[7], total = 0;
     for (int i = 0; i < 7; ++i) { off[i] = total; total += align_up(sz[i] ? sz[i] : 16); }
     if (dc.buf && dc.bytes < total) { cudaFree(dc.buf); dc.buf = nullptr; }
     if (!dc.buf) { CU(cudaMalloc(&dc.buf, total)); dc.bytes = total; }
-    for (int i = 0; i < 7; ++i) if (sz[i]) CU(cudaMemcpyAsync((char*)dc.buf + off[i], src[i], sz[i], cudaMemcpyHostToDevice, c->stream));
+    for (int i = 0; i < 7; ++i) if (sz[i] && !(device_build && i == 0)) CU(cudaMemcpyAsync((char*)dc.buf + off[i], src[i], sz[i], cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (device_build) {
+        // Node::new on the GPU: Morton codes + radix sort + Karras hierarchy + bottom-up boxes (trt_lbvh.cu)
+        void *d_boxes = nullptr, *d_tmp = nullptr;
+        CU(cudaMalloc(&d_boxes, f.lbvh_boxes.size() * 16));
+        cudaError_t e = cudaMalloc(&d_tmp, trtk::lbvh_tmp_bytes((uint32_t)n_prims));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_boxes, f.lbvh_boxes.data(), f.lbvh_boxes.size() * 16, cudaMemcpyHostToDevice, c->stream);
+        uint32_t depth = 0; float ms = 0.f;
+        if (e == cudaSuccess) e = trtk::build_lbvh(d_boxes, (uint32_t)n_prims, (char*)dc.buf + off[0], d_tmp, &depth, &ms, c->stream);
+        cudaFree(d_boxes); if (d_tmp) cudaFree(d_tmp);
+        if (e != cudaSuccess) return fail_cuda("trt_scene_upload: device BVH build", e);
+        s->host.flat.max_depth = depth; s->host.device_build_ms = ms;
+        if (depth > TRT_MAX_STACK) return fail(TRT_ERR_UNSUPPORTED, "trt_scene_upload: device-built tree deeper than the traversal stack; commit with TRT_BVH_SAH");
+    }
     trtk::SceneView& v = dc.view;
     char* b = (char*)dc.buf;
     v.nodes = b + off[0]; v.spheres = b + off[1]; v.quads = b + off[2]; v.sphere_meta = b + off[3]; v.quad_meta = b + off[4]; v.materials = b + off[5];
     v.root = f.root; v.n_nodes = f.n_nodes; v.n_spheres = (uint32_t)f.spheres.size(); v.n_quads = (uint32_t)f.quad_meta.size();
-    v.n_materials = (uint32_t)(f.materials.size() / 2); v.kind = (uint32_t)f.bvh_kind;
+    v.n_materials = (uint32_t)(f.materials.size() / 2); v.kind = device_build ? 1u : (uint32_t)f.bvh_kind;   // the device-built tree is walked near-child-first like SAH
     v.flat = f.flat.empty() ? nullptr : b + off[6]; v.flat_host = f.flat.empty() ? nullptr : f.flat.data(); v.n_flat = (uint32_t)(f.flat.size() / 6);
     const float inf = std::numeric_limits<float>::infinity();
     for (int i = 0; i < 3; ++i) { v.root_min[i] = inf; v.root_max[i] = -inf; }

@@ -1,0 +1,213 @@
+// trt_lbvh.cu — BVH construction on the GPU (TRT_BVH_LBVH_DEVICE).
+//
+// Replaces the host builders for big scenes: BVH::new / Node::new (hittable/bvh.rs:12-21,42-84) is O(n log^2 n) on one
+// core and the host SAH build of 10^6 primitives takes ~1 s, as long as rendering them. Here:
+//   1. k_lbvh_bounds   bounds of the primitive-box centroids (block reduction + ordered-int atomics)
+//   2. k_lbvh_morton   30-bit Morton code of every centroid
+//   3. cub::DeviceRadixSort::SortPairs (code, primitive)
+//   4. k_lbvh_karras   Karras 2012: every interior node finds its range and split from the sorted codes, in parallel
+//   5. k_lbvh_refit    bottom-up boxes: the second child to arrive at a node merges (atomic flag per node)
+//   6. k_lbvh_emit     the 64-byte node records of trt_layout.h (both children's boxes + child refs in the parent);
+//                      also the tree depth (needed: the traversal stack holds TRT_MAX_STACK entries)
+// The leaf boxes are the primitives' own padded boxes computed on the host with the reference's arithmetic
+// (hittable/aabb.rs:13-20), interior boxes are exact min/max unions, so the culling argument of DESIGN.md §4.2 holds
+// unchanged; the tree is walked near-child-first like the SAH tree.
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <stdint.h>
+#include "trt_layout.h"
+#include "trt_kernels.h"
+
+namespace {
+
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+struct LbvhBounds { int mn[3], mx[3]; unsigned int depth; unsigned int pad; };
+
+__global__ void k_lbvh_init(LbvhBounds* b) {
+    for (int i = 0; i < 3; ++i) { b->mn[i] = 0x7FFFFFFF; b->mx[i] = (int)0x80000000; }
+    b->depth = 0; b->pad = 0;
+}
+
+__global__ void k_lbvh_bounds(const float4* __restrict__ boxes, uint32_t n, LbvhBounds* b) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float c[3] = {0.f, 0.f, 0.f};
+    bool ok = i < n;
+    if (ok) {
+        float4 lo = boxes[2 * (size_t)i], hi = boxes[2 * (size_t)i + 1];
+        c[0] = 0.5f * (lo.x + hi.x); c[1] = 0.5f * (lo.y + hi.y); c[2] = 0.5f * (lo.z + hi.z);
+    }
+    for (int a = 0; a < 3; ++a) {
+        int mn = ok ? f2ord(c[a]) : 0x7FFFFFFF, mx = ok ? f2ord(c[a]) : (int)0x80000000;
+        for (int off = 16; off; off >>= 1) { mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, off)); mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, off)); }
+        if ((threadIdx.x & 31) == 0) { atomicMin(&b->mn[a], mn); atomicMax(&b->mx[a], mx); }
+    }
+}
+
+__device__ __forceinline__ uint32_t expand10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu; v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u; v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__global__ void k_lbvh_morton(const float4* __restrict__ boxes, uint32_t n, const LbvhBounds* b, uint32_t* keys, uint32_t* vals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 lo = boxes[2 * (size_t)i], hi = boxes[2 * (size_t)i + 1];
+    float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
+    uint32_t q[3];
+    for (int a = 0; a < 3; ++a) {
+        float mn = ord2f(b->mn[a]), mx = ord2f(b->mx[a]);
+        float ext = mx - mn;
+        float u = ext > 0.f ? (c[a] - mn) / ext : 0.f;
+        u = fminf(fmaxf(u * 1024.f, 0.f), 1023.f);
+        q[a] = (uint32_t)u;
+    }
+    keys[i] = (expand10(q[0]) << 2) | (expand10(q[1]) << 1) | expand10(q[2]);
+    vals[i] = i;
+}
+
+// common-prefix length of sorted keys i and j (index breaks ties), -1 outside the array
+__device__ __forceinline__ int lbvh_delta(const uint32_t* __restrict__ k, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint32_t a = k[i], b = k[j];
+    return a != b ? __clz(a ^ b) : 32 + __clz((uint32_t)i ^ (uint32_t)j);
+}
+
+// child encoding inside the builder: bit31 = leaf (index into the sorted order), else interior node index
+__global__ void k_lbvh_karras(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* left, uint32_t* right,
+                              uint32_t* parent_of_node, uint32_t* parent_of_leaf, unsigned int* flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int ni = (int)n - 1;
+    if (i >= ni) return;
+    flags[i] = 0;
+    int nn = (int)n;
+    int d = lbvh_delta(keys, nn, i, i + 1) - lbvh_delta(keys, nn, i, i - 1) >= 0 ? 1 : -1;
+    int dmin = lbvh_delta(keys, nn, i, i - d);
+    int lmax = 2;
+    while (lbvh_delta(keys, nn, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1) if (lbvh_delta(keys, nn, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = lbvh_delta(keys, nn, i, j);
+    int s = 0;
+    for (int t = (l + 1) >> 1; ; t = (t + 1) >> 1) {
+        if (lbvh_delta(keys, nn, i, i + (s + t) * d) > dnode) s += t;
+        if (t <= 1) break;
+    }
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    uint32_t L = (lo == gamma) ? (0x80000000u | (uint32_t)gamma) : (uint32_t)gamma;
+    uint32_t R = (hi == gamma + 1) ? (0x80000000u | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
+    left[i] = L; right[i] = R;
+    if (L & 0x80000000u) parent_of_leaf[L & 0x7FFFFFFFu] = (uint32_t)i; else parent_of_node[L] = (uint32_t)i;
+    if (R & 0x80000000u) parent_of_leaf[R & 0x7FFFFFFFu] = (uint32_t)i; else parent_of_node[R] = (uint32_t)i;
+    if (i == 0) parent_of_node[0] = 0xFFFFFFFFu;
+}
+
+__global__ void k_lbvh_refit(const float4* __restrict__ boxes, const uint32_t* __restrict__ order, uint32_t n,
+                             const uint32_t* __restrict__ left, const uint32_t* __restrict__ right,
+                             const uint32_t* __restrict__ parent_of_node, const uint32_t* __restrict__ parent_of_leaf,
+                             unsigned int* flags, float4* node_min, float4* node_max, LbvhBounds* b) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t cur = parent_of_leaf[i];
+    {   // tree depth in levels = longest leaf-to-root chain (the traversal stack holds TRT_MAX_STACK entries)
+        unsigned int depth = 1;
+        for (uint32_t a = cur; a != 0xFFFFFFFFu; a = parent_of_node[a]) ++depth;
+        const unsigned am = __activemask();
+        depth = __reduce_max_sync(am, depth);
+        if ((threadIdx.x & 31u) == (unsigned)(__ffs(am) - 1)) atomicMax(&b->depth, depth);
+    }
+    while (cur != 0xFFFFFFFFu) {
+        __threadfence();
+        if (atomicAdd(&flags[cur], 1u) == 0u) return;       // first child to arrive: the sibling finishes this node
+        __threadfence();
+        float4 mn, mx;
+        uint32_t ch[2] = {left[cur], right[cur]};
+        for (int c = 0; c < 2; ++c) {
+            float4 a, z;
+            if (ch[c] & 0x80000000u) { uint32_t p = order[ch[c] & 0x7FFFFFFFu]; a = boxes[2 * (size_t)p]; z = boxes[2 * (size_t)p + 1]; }
+            else { a = __ldcg(&node_min[ch[c]]); z = __ldcg(&node_max[ch[c]]); }   // written by another SM: read through L2
+            if (c == 0) { mn = a; mx = z; }
+            else { mn.x = fminf(mn.x, a.x); mn.y = fminf(mn.y, a.y); mn.z = fminf(mn.z, a.z); mx.x = fmaxf(mx.x, z.x); mx.y = fmaxf(mx.y, z.y); mx.z = fmaxf(mx.z, z.z); }
+        }
+        node_min[cur] = mn; node_max[cur] = mx;
+        cur = parent_of_node[cur];
+    }
+}
+
+__global__ void k_lbvh_emit(const float4* __restrict__ boxes, const uint32_t* __restrict__ order, uint32_t n,
+                            const uint32_t* __restrict__ left, const uint32_t* __restrict__ right,
+                            const float4* __restrict__ node_min, const float4* __restrict__ node_max, float4* nodes) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    uint32_t ch[2] = {left[i], right[i]};
+    float4 mn[2], mx[2]; uint32_t ref[2];
+    for (int c = 0; c < 2; ++c) {
+        if (ch[c] & 0x80000000u) {
+            uint32_t p = order[ch[c] & 0x7FFFFFFFu];
+            mn[c] = boxes[2 * (size_t)p]; mx[c] = boxes[2 * (size_t)p + 1];
+            ref[c] = __float_as_uint(mn[c].w);                  // the primitive's leaf ref travels in bmin.w
+        } else { mn[c] = node_min[ch[c]]; mx[c] = node_max[ch[c]]; ref[c] = ch[c]; }
+    }
+    float4* rec = nodes + 4 * (size_t)i;
+    rec[0] = make_float4(mn[0].x, mn[0].y, mn[0].z, mx[0].x);
+    rec[1] = make_float4(mx[0].y, mx[0].z, mn[1].x, mn[1].y);
+    rec[2] = make_float4(mn[1].z, mx[1].x, mx[1].y, mx[1].z);
+    rec[3] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), 0.f, 0.f);
+}
+
+} // namespace
+
+namespace trtk {
+
+static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t lbvh_tmp_bytes(uint32_t n) {
+    size_t sort_tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 30);
+    // keys x2, vals x2, left, right, parent_of_node, parent_of_leaf, flags: 9 arrays of n u32; node_min/max: 2 arrays of n float4
+    return al(sizeof(LbvhBounds)) + 9 * al(4ull * n) + 2 * al(16ull * n) + al(sort_tmp);
+}
+
+// d_boxes: 2 float4 per primitive (bmin.xyz + leaf-ref bits, bmax.xyz). d_nodes: 4 float4 per interior node (n - 1 nodes).
+cudaError_t build_lbvh(const void* d_boxes, uint32_t n, void* d_nodes, void* d_tmp, uint32_t* h_depth, float* h_ms, cudaStream_t st) {
+    if (n < 2) return cudaErrorInvalidValue;
+    char* p = (char*)d_tmp;
+    LbvhBounds* b = (LbvhBounds*)p; p += al(sizeof(LbvhBounds));
+    uint32_t* arr[9];
+    for (int i = 0; i < 9; ++i) { arr[i] = (uint32_t*)p; p += al(4ull * n); }
+    float4* node_min = (float4*)p; p += al(16ull * n);
+    float4* node_max = (float4*)p; p += al(16ull * n);
+    void* sort_tmp = p;
+    size_t sort_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 30);
+    uint32_t *keys = arr[0], *keys_s = arr[1], *vals = arr[2], *order = arr[3], *left = arr[4], *right = arr[5], *pn = arr[6], *pl = arr[7];
+    unsigned int* flags = arr[8];
+    const float4* boxes = (const float4*)d_boxes;
+    cudaEvent_t e0, e1; cudaError_t e;
+    if ((e = cudaEventCreate(&e0)) != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&e1)) != cudaSuccess) { cudaEventDestroy(e0); return e; }
+    unsigned g = (n + 255) / 256;
+    cudaEventRecord(e0, st);
+    k_lbvh_init<<<1, 1, 0, st>>>(b);
+    k_lbvh_bounds<<<g, 256, 0, st>>>(boxes, n, b);
+    k_lbvh_morton<<<g, 256, 0, st>>>(boxes, n, b, keys, vals);
+    e = cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys, keys_s, vals, order, (int)n, 0, 30, st);
+    if (e == cudaSuccess) {
+        k_lbvh_karras<<<g, 256, 0, st>>>(keys_s, n, left, right, pn, pl, flags);
+        k_lbvh_refit<<<g, 256, 0, st>>>(boxes, order, n, left, right, pn, pl, flags, node_min, node_max, b);
+        k_lbvh_emit<<<g, 256, 0, st>>>(boxes, order, n, left, right, node_min, node_max, (float4*)d_nodes);
+        cudaEventRecord(e1, st);
+        LbvhBounds hb;
+        e = cudaMemcpyAsync(&hb, b, sizeof hb, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e == cudaSuccess) { *h_depth = hb.depth; float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); *h_ms = ms; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return e;
+}
+
+} // namespace trtk

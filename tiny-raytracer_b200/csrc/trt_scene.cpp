@@ -278,8 +278,9 @@ static void flatten(const std::vector<TNode>& t, const std::vector<HostPrim>& pr
 }
 
 bool HostScene::commit(int bvh_kind, std::string* err) {
-    if (bvh_kind < 0 || bvh_kind > 3) { *err = "trt_scene_commit: unknown bvh_kind"; return false; }
+    if (bvh_kind < 0 || bvh_kind > 4) { *err = "trt_scene_commit: unknown bvh_kind"; return false; }
     size_t n = prims.size();
+    if (bvh_kind == 4 && n < 2) bvh_kind = 0;                    // nothing to build on the device
     // TRT_BVH_AUTO: on trees this small the reference topology is as fast as SAH (measured: Cornell 10.3 vs 9.7 Grays/s)
     // and reproduces the reference by construction; larger scenes need SAH (1 M spheres: 5x faster).
     if (bvh_kind == 3) bvh_kind = (n <= 64) ? 0 : 1;
@@ -290,10 +291,23 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
     leaf_rank.assign(n, 0);
     flat = FlatScene(); flat.bvh_kind = bvh_kind;
 
-    std::vector<TNode> ref_tree(n ? 2 * n - 1 : 0), sah_tree;
+    const bool device_build = bvh_kind == 4;
+    std::vector<TNode> ref_tree(n && !device_build ? 2 * n - 1 : 0), sah_tree;
     std::vector<uint32_t> order(n);
     for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
-    if (n) {
+    if (device_build) {
+        // TRT_BVH_LBVH_DEVICE: no host tree at all. Ties are broken by prim_id instead of the reference's leaf order
+        // (which only a host build of the reference tree could give), and the node array is produced by trt_lbvh.cu
+        // during trt_scene_upload from these per-primitive boxes.
+        for (size_t i = 0; i < n; ++i) leaf_rank[i] = (uint32_t)i;
+        flat.lbvh_boxes.resize(2 * n);
+        for (size_t i = 0; i < n; ++i) {
+            const HostPrim& p = prims[i];
+            flat.lbvh_boxes[2 * i] = {p.bmin[0], p.bmin[1], p.bmin[2], as_float(leaf_ref(p))};
+            flat.lbvh_boxes[2 * i + 1] = {p.bmax[0], p.bmax[1], p.bmax[2], 0.f};
+        }
+        flat.root = 0; flat.n_nodes = (uint32_t)(n - 1); flat.max_depth = 0; flat.sah_cost = 0.f;
+    } else if (n) {
         RefBuilder rb{prims, ref_tree, order, {}};
         for (int a = 0; a < 3; ++a) { rb.key[a].resize(n); for (size_t i = 0; i < n; ++i) rb.key[a][i] = total_order_key(prims[i].bmin[a]); }
         rb.build(0, n, 0, 3);
@@ -308,7 +322,7 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
         sb.build(0, n, 0, 1, 3);
         tree = &sah_tree;
     }
-    flatten(*tree, prims, flat);
+    if (!device_build) flatten(*tree, prims, flat);
     if (flat.max_depth > TRT_MAX_STACK) { *err = "trt_scene_commit: tree deeper than the traversal stack"; return false; }
 
     flat.spheres.resize(ns); flat.sphere_meta.resize(ns); flat.quads.resize(4 * (size_t)nq); flat.quad_meta.resize(nq);

@@ -26,6 +26,7 @@ struct FlatScene {
     std::vector<trt_u4> sphere_meta, quad_meta;
     std::vector<trt_f4> materials;     // 2 per material
     std::vector<trt_f4> flat;          // TRT_BVH_FLAT: 6 per primitive, reference leaf order (trt_layout.h)
+    std::vector<trt_f4> lbvh_boxes;    // TRT_BVH_LBVH_DEVICE: 2 per primitive, (bmin, leaf-ref bits), (bmax, 0): input of the device builder
     uint32_t root = TRT_REF_INVALID;   // interior node 0, or INVALID for an empty scene
     uint32_t n_nodes = 0, max_depth = 0;
     float sah_cost = 0.f;
@@ -42,6 +43,8 @@ struct HostScene {
     std::vector<uint32_t> leaf_rank;    // reference-topology leaf order per prim_id (after commit)
     FlatScene flat;
     bool committed = false;
+    float host_commit_ms = 0.f;         // wall time of the last commit (host tree builds + flattening)
+    float device_build_ms = 0.f;        // TRT_BVH_LBVH_DEVICE: time of the last build on the GPU (CUDA events)
     uint64_t version = 0;               // bumped by every commit; the device copy remembers which one it holds
 
     uint32_t add_material(uint32_t kind, const float rgb[3], float param);
