@@ -68,7 +68,7 @@ typedef struct trt_params {
 } trt_params;
 #define TRT_FLAG_COUNT_EVENTS 1u   /* also count node visits / primitive tests (slower; for roofline accounting) */
 /* bits 8..15 of flags: megakernel tuning override, the number of lanes of a warp (1..32) that must have finished their ray
- * before the shade/regenerate block runs; 0 = chosen from the tree size (32 for tiny trees, 8 for big ones). Results do not
+ * before the shade/regenerate block runs; 0 = chosen from the tree size (32 up to 4096 nodes, 16 above). Results do not
  * depend on it. */
 #define TRT_FLAG_REGEN_MIN(n) (((uint32_t)(n) & 0xFFu) << 8)
 
