@@ -34,8 +34,8 @@ typedef struct trt_scene trt_scene;   /* replaces hittable::world::World (hittab
 typedef enum trt_bvh_kind {
     TRT_BVH_REFERENCE = 0,   /* the reference's median-split topology, traversed left-first: reference results by construction */
     TRT_BVH_SAH = 1,         /* binned-SAH topology, near-child-first traversal, ties broken by reference leaf order */
-    TRT_BVH_FLAT = 2,        /* no tree: <= 48 primitives as a list in reference leaf order; reference results by construction */
-    TRT_BVH_AUTO = 3,        /* REFERENCE when the scene has <= 64 primitives (as fast there, exact by construction), else SAH */
+    TRT_BVH_FLAT = 2,        /* no tree: <= 64 primitives as a list in reference leaf order; reference results by construction */
+    TRT_BVH_AUTO = 3,        /* FLAT when the scene has <= 64 primitives (fastest there, exact by construction), else SAH */
     TRT_BVH_LBVH_DEVICE = 4  /* built on the GPU during trt_scene_upload (Morton codes + radix sort + Karras), walked like SAH;
                                 no host tree: exact-t ties between different primitives go to the lower prim_id */
 } trt_bvh_kind;

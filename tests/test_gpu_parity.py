@@ -241,7 +241,7 @@ def test_big_tree_render_matches_oracle(trt, orc, ctx):
         assert psnr8(u8, ou8) >= PSNR_MIN_DB
 
 
-@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("kind", [0, 1, 3])
 @pytest.mark.parametrize("case", ["c1", "c1s", "final_small", "glass_small", "ragged", "tiny"])
 def test_wavefront_render_matches_oracle(trt, orc, ctx, kind, case):
     """TRT_VARIANT_WAVEFRONT traces the same paths (same Philox keys) through queues in HBM; only the order of the f64

@@ -270,7 +270,6 @@ static int render_into(trt_ctx* c, trt_scene* s, const trt_camera* cam, const tr
     int rc = trt_scene_upload(c, s); if (rc) return rc;
     const trtk::SceneView& v = s->on_device[c->device].view;
     if (p->variant == TRT_VARIANT_WAVEFRONT) {
-        if (v.kind == TRT_BVH_FLAT) return fail(TRT_ERR_UNSUPPORTED, "wavefront variant needs a tree: commit with TRT_BVH_REFERENCE or TRT_BVH_SAH");
         if (p->max_bounces > 0xFFFFu) return fail(TRT_ERR_UNSUPPORTED, "wavefront variant: max_bounces above 65535");
         uint32_t n_slots = 1u << 20;                       // 68 B per slot: 68 MB of path state, L2-resident on B200
         if (const char* e = std::getenv("TRT_WF_SLOTS")) { long x = std::atol(e); if (x >= 1024 && x <= (1l << 26)) n_slots = (uint32_t)x & ~31u; }

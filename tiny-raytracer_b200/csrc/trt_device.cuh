@@ -434,19 +434,50 @@ TRT_DEV bool shade(const DevScene& S, const DevParams& P, Hit h, uint32_t pixel,
 // For scenes of at most TRT_FLAT_MAX primitives the tree is replaced by the list of primitives in the reference tree's
 // left-to-right leaf order. The reference's Node::hit is then exactly a scan of that list with the running closest hit
 // as range end (every ancestor box contains the leaf box, so only the leaf's own box test can cull).
-// A SIMT machine runs that scan with zero control divergence, because every lane tests primitive i in iteration i:
-//   phase A  (uniform loop, data from the kernel-parameter bank): the ray parameter t_i of every primitive — plane t of a
-//            quad, near/far root of a sphere — or +inf when out of [t_min, inf); kept in a per-thread shared-memory column.
-//   phase B  (per lane): take candidates in increasing (t, rank) order; the first one that also passes the inside test
-//            (quad.rs:39-41) and its own padded-box test (bvh.rs:89) is the (t, rank)-smallest valid primitive W.
-//            If W's box entry does not exceed its t — always, except for fp-cancellation on grazing hits — the
+// A SIMT machine runs the box half of that scan with zero control divergence, because every lane tests box i in iteration i:
+//   phase A  (uniform loop, box data from the kernel-parameter constant bank): the slab test of every primitive's own
+//            padded box against [t_min, inf) (bvh.rs:89 with an open range end); the passing ones form a 64-bit mask.
+//   phase B  (per lane): the primitive test (quad.rs:33-41 / sphere.rs:29-45) of the set bits in rank order, keeping the
+//            smallest t (a tie keeps the lower rank). That is the (t, rank)-smallest VALID primitive W — valid = its
+//            own box is crossed and it is hit — because no candidate is culled by distance.
+//   check    if W's box entry does not exceed its t — always, except for fp cancellation on grazing hits — the
 //            reference's scan returns W whatever it visited before (nothing valid is closer; a tie is lower-ranked);
-//            otherwise the lane replays the reference's scan literally (flat_scan_reference).
+//            otherwise, and for rays whose slab arithmetic can produce NaN, the lane replays the reference's scan
+//            literally (flat_scan_reference). Exact by construction.
 struct FlatPrim { float4 g0, g1, g2, g3, b0, b1; };   // geometry as in trt_layout.h; b0 = (bmin, ref bits), b1 = (bmax, 0)
 
 template <bool DSMEM> TRT_DEV float4 ldf(const float4* p) { return ld4<DSMEM>(p); }
 
-// the reference's scan, literally: used only when the closest valid primitive is culled-or-not depending on the range end
+// one primitive against [t_min, hi): returns t or false. hi_cut only feeds the quad pre-reject (see quad_hit).
+template <bool DSMEM>
+TRT_DEV bool flat_prim_hit(const float4* p, uint32_t ref, V3 o, V3 d, float t_min, float hi, float hi_cut, float* t_out) {
+    float4 g0 = ldf<DSMEM>(p);
+    float t;
+    if (ref & TRT_REF_QUAD) {
+        V3 nrm = mk(g0.x, g0.y, g0.z);
+        float dn = dot(d, nrm), num = g0.w - dot(o, nrm);
+        float ta = num * rcp_approx(dn);
+        if (ta < t_min - fabsf(t_min) * 1e-6f || ta > hi_cut + fabsf(hi_cut) * 1e-6f) return false;
+        t = num / dn;
+        if (!(t_min <= t && t < hi)) return false;
+        float4 g1 = ldf<DSMEM>(p + 1), g2 = ldf<DSMEM>(p + 2), g3 = ldf<DSMEM>(p + 3);
+        V3 pp = ray_at(o, d, t) - mk(g1.x, g1.y, g1.z);
+        V3 w = mk(g1.w, g2.w, g3.w);
+        float px = dot(cross(pp, mk(g3.x, g3.y, g3.z)), w), py = dot(cross(mk(g2.x, g2.y, g2.z), pp), w);
+        if (!(0.0f <= px && px < 1.0f && 0.0f <= py && py < 1.0f)) return false;
+    } else {
+        V3 oc = o - mk(g0.x, g0.y, g0.z);
+        float a = dot(d, d), half_b = dot(oc, d), c = dot(oc, oc) - g0.w * g0.w;
+        float disc = half_b * half_b - a * c;
+        if (disc < 0.0f) return false;
+        float sq = sqrtf(disc);
+        t = (-half_b - sq) / a;
+        if (!(t_min <= t && t < hi)) { t = (-half_b + sq) / a; if (!(t_min <= t && t < hi)) return false; }
+    }
+    *t_out = t; return true;
+}
+
+// the reference's scan, literally (bvh.rs:88-107 on the leaf list)
 template <bool DSMEM>
 TRT_DEV Hit flat_scan_reference(const FlatPrim* Dv, uint32_t n, V3 o, V3 d, V3 inv, float t_min) {
     Hit best; best.t = TRT_INF; best.ref = TRT_REF_INVALID;
@@ -457,102 +488,51 @@ TRT_DEV Hit flat_scan_reference(const FlatPrim* Dv, uint32_t n, V3 o, V3 d, V3 i
         slab(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, o, inv, t_min, &s, &e);
         if (!(e > s && best.t > s)) continue;
         uint32_t ref = __float_as_uint(b0.w);
-        float4 g0 = ldf<DSMEM>(p);
         float t;
-        if (ref & TRT_REF_QUAD) {
-            V3 nrm = mk(g0.x, g0.y, g0.z);
-            t = (g0.w - dot(o, nrm)) / dot(d, nrm);
-            if (!(t_min <= t && t < best.t)) continue;
-            float4 g1 = ldf<DSMEM>(p + 1), g2 = ldf<DSMEM>(p + 2), g3 = ldf<DSMEM>(p + 3);
-            V3 pp = ray_at(o, d, t) - mk(g1.x, g1.y, g1.z);
-            V3 w = mk(g1.w, g2.w, g3.w);
-            float px = dot(cross(pp, mk(g3.x, g3.y, g3.z)), w), py = dot(cross(mk(g2.x, g2.y, g2.z), pp), w);
-            if (!(0.0f <= px && px < 1.0f && 0.0f <= py && py < 1.0f)) continue;
-        } else {
-            V3 oc = o - mk(g0.x, g0.y, g0.z);
-            float a = dot(d, d), half_b = dot(oc, d), c = dot(oc, oc) - g0.w * g0.w;
-            float disc = half_b * half_b - a * c;
-            if (disc < 0.0f) continue;
-            float sq = sqrtf(disc);
-            t = (-half_b - sq) / a;
-            if (!(t_min <= t && t < best.t)) { t = (-half_b + sq) / a; if (!(t_min <= t && t < best.t)) continue; }
-        }
-        best.t = t; best.ref = ref;
+        if (flat_prim_hit<DSMEM>(p, ref, o, d, t_min, best.t, best.t, &t)) { best.t = t; best.ref = ref; }
     }
     return best;
 }
 
-// U: the list as seen by uniform (same-address) loads; Dv: the same list for per-lane indexed loads; tt: this thread's
-// scratch column, element i at tt[i * tt_stride].
+// U: the list as seen by uniform (same-address) loads; Dv: the same list for per-lane indexed loads.
 template <bool DSMEM>
-TRT_DEV Hit closest_hit_flat(const FlatPrim* __restrict__ U, const FlatPrim* Dv, uint32_t n, float* tt, uint32_t tt_stride,
-                             V3 o, V3 d, float t_min) {
+TRT_DEV Hit closest_hit_flat(const FlatPrim* __restrict__ U, const FlatPrim* Dv, uint32_t n, V3 o, V3 d, float t_min) {
     Hit best; best.t = TRT_INF; best.ref = TRT_REF_INVALID;
-    const float a = dot(d, d);                       // sphere.rs:31, the same for every sphere
-    float m = TRT_INF; uint32_t mi = 0;
-    // ---- phase A
-    for (uint32_t i = 0; i < n; ++i) {
-        const float4 g0 = U[i].g0;
-        const uint32_t ref = __float_as_uint(U[i].b0.w);
-        float t;
-        if (ref & TRT_REF_QUAD) {                    // quad.rs:34-36
-            V3 nrm = mk(g0.x, g0.y, g0.z);
-            t = (g0.w - dot(o, nrm)) / dot(d, nrm);
-            if (!(t_min <= t && t < TRT_INF)) t = TRT_INF;
-        } else {                                     // sphere.rs:30-45 with an open range end
-            V3 oc = o - mk(g0.x, g0.y, g0.z);
-            float half_b = dot(oc, d), c = dot(oc, oc) - g0.w * g0.w;
-            float disc = half_b * half_b - a * c;
-            t = TRT_INF;
-            if (!(disc < 0.0f)) {
-                float sq = sqrtf(disc);
-                float t0 = (-half_b - sq) / a;
-                if (t_min <= t0 && t0 < TRT_INF) t = t0;
-                else { float t1 = (-half_b + sq) / a; if (t_min <= t1 && t1 < TRT_INF) t = t1; }
-            }
-        }
-        tt[i * tt_stride] = t;
-        if (t < m) { m = t; mi = i; }                // ties keep the lower rank
-    }
-    if (!(m < TRT_INF)) return best;
-    // ---- phase B
     const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    for (;;) {
-        const float4* p = (const float4*)(Dv + mi);
-        float4 b0 = ldf<DSMEM>(p + 4), b1 = ldf<DSMEM>(p + 5);
-        uint32_t ref = __float_as_uint(b0.w);
-        bool valid = true;
-        if (ref & TRT_REF_QUAD) {                    // quad.rs:38-41
-            float4 g1 = ldf<DSMEM>(p + 1), g2 = ldf<DSMEM>(p + 2), g3 = ldf<DSMEM>(p + 3);
-            V3 pp = ray_at(o, d, m) - mk(g1.x, g1.y, g1.z);
-            V3 w = mk(g1.w, g2.w, g3.w);
-            float px = dot(cross(pp, mk(g3.x, g3.y, g3.z)), w), py = dot(cross(mk(g2.x, g2.y, g2.z), pp), w);
-            valid = 0.0f <= px && px < 1.0f && 0.0f <= py && py < 1.0f;
-        }
-        if (valid) {
-            float s, e;
-            slab(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, o, inv, t_min, &s, &e);   // the leaf's own box (bvh.rs:89)
-            if (e > s) {
-                if (s > m) return flat_scan_reference<DSMEM>(Dv, n, o, d, inv, t_min);
-                best.t = m; best.ref = ref;
-                return best;
-            }
-        }
-        tt[mi * tt_stride] = TRT_INF;                // not a hit: next candidate in (t, rank) order
-        m = TRT_INF;
-        for (uint32_t i = 0; i < n; ++i) { float t = tt[i * tt_stride]; if (t < m) { m = t; mi = i; } }
-        if (!(m < TRT_INF)) return best;
+    if (!ray_is_tame(o, inv)) return flat_scan_reference<DSMEM>(Dv, n, o, d, inv, t_min);
+    // ---- phase A: which boxes does the ray cross at all
+    unsigned long long mask = 0ull;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float4 b0 = U[i].b0, b1 = U[i].b1;
+        float s, e;
+        slab_tame(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, o, inv, t_min, &s, &e);
+        if (e > s) mask |= 1ull << i;
     }
+    // ---- phase B: primitive tests of the candidates, in rank order
+    uint32_t best_i = 0;
+    while (mask) {
+        const uint32_t i = (uint32_t)__ffsll((long long)mask) - 1u;
+        mask &= mask - 1ull;
+        const float4* p = (const float4*)(Dv + i);
+        const uint32_t ref = __float_as_uint(ldf<DSMEM>(p + 4).w);
+        float t;
+        if (flat_prim_hit<DSMEM>(p, ref, o, d, t_min, TRT_INF, best.t, &t) && t < best.t) { best.t = t; best.ref = ref; best_i = i; }
+    }
+    if (best.ref == TRT_REF_INVALID) return best;
+    // ---- check: the winner's own box entry against its t
+    const float4* p = (const float4*)(Dv + best_i);
+    float4 b0 = ldf<DSMEM>(p + 4), b1 = ldf<DSMEM>(p + 5);
+    float s, e;
+    slab_tame(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, o, inv, t_min, &s, &e);
+    if (s > best.t) return flat_scan_reference<DSMEM>(Dv, n, o, d, inv, t_min);
+    return best;
 }
 
 // One whole path: CpuSampler::single_point_sampling, renderer/sampler/cpu.rs:39-65
 // KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH, 2 = TRT_BVH_FLAT
 template <int KIND, bool SMEM, bool COUNT>
 TRT_DEV Hit closest_hit_any(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
-    if (KIND == 2) {
-        float tt[TRT_FLAT_MAX];
-        return closest_hit_flat<false>(S.flat, S.flat, S.n_flat, tt, 1u, o, d, t_min);
-    }
+    if (KIND == 2) return closest_hit_flat<false>(S.flat, S.flat, S.n_flat, o, d, t_min);
     return closest_hit<KIND == 1, SMEM, COUNT>(S, o, d, t_min, ec);
 }
 

@@ -95,7 +95,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& A, const FlatPrim* U) 
         // ---- T: cpu.rs:48
         Hit h; h.t = TRT_INF; h.ref = TRT_REF_INVALID;
         if (alive) {
-            if (KIND == 2) h = closest_hit_flat<true>(U, S.flat, S.n_flat, tt, MEGA_THREADS, o, d, P.t_min);
+            if (KIND == 2) h = closest_hit_flat<true>(U, S.flat, S.n_flat, o, d, P.t_min);
             else h = closest_hit<KIND == 1, SMEM, COUNT>(S, o, d, P.t_min, &ec);
             ++n_rays;
         }
@@ -376,7 +376,6 @@ namespace trtk {
 
 size_t scene_smem_bytes(const SceneView& v) {
     size_t b = 16ull * (4ull * v.n_nodes + v.n_spheres + 4ull * v.n_quads + v.n_spheres + v.n_quads + 2ull * v.n_materials + 6ull * v.n_flat);
-    if (v.kind == 2) b += 4ull * MEGA_THREADS * v.n_flat;     // phase-A columns
     return b;
 }
 

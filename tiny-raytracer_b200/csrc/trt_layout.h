@@ -33,7 +33,7 @@
 #define TRT_MAT_LIGHT 3u
 
 #define TRT_MAX_STACK 64   /* traversal stack entries; trt_scene_commit rejects deeper trees */
-#define TRT_FLAT_MAX 48    /* TRT_BVH_FLAT: largest primitive count handled as a flat list (6 float4 = 96 B each:
+#define TRT_FLAT_MAX 64    /* TRT_BVH_FLAT: largest primitive count handled as a flat list (6 float4 = 96 B each:
                               the four geometry float4 above, then (bmin.xyz, child-ref bits), (bmax.xyz, 0)) */
 
 struct trt_f4 { float x, y, z, w; };

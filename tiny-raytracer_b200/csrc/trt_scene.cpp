@@ -281,10 +281,10 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
     if (bvh_kind < 0 || bvh_kind > 4) { *err = "trt_scene_commit: unknown bvh_kind"; return false; }
     size_t n = prims.size();
     if (bvh_kind == 4 && n < 2) bvh_kind = 0;                    // nothing to build on the device
-    // TRT_BVH_AUTO: on trees this small the reference topology is as fast as SAH (measured: Cornell 10.3 vs 9.7 Grays/s)
-    // and reproduces the reference by construction; larger scenes need SAH (1 M spheres: 5x faster).
-    if (bvh_kind == 3) bvh_kind = (n <= 64) ? 0 : 1;
-    if (bvh_kind == 2 && (n < 1 || n > TRT_FLAT_MAX)) { *err = "trt_scene_commit: TRT_BVH_FLAT takes 1..48 primitives"; return false; }
+    // TRT_BVH_AUTO: up to TRT_FLAT_MAX primitives the flat list beats any tree on a SIMT machine (measured: Cornell 15.8 vs
+    // 10.8 Grays/s, glass Cornell 9.8 vs 6.3) and reproduces the reference by construction; larger scenes need SAH.
+    if (bvh_kind == 3) bvh_kind = (n >= 1 && n <= TRT_FLAT_MAX) ? 2 : (n == 0 ? 0 : 1);
+    if (bvh_kind == 2 && (n < 1 || n > TRT_FLAT_MAX)) { *err = "trt_scene_commit: TRT_BVH_FLAT takes 1..64 primitives"; return false; }
     // per-type arrays in insertion order (what World::get_geometries::<T>() returns, hittable/world.rs:47-55)
     uint32_t ns = 0, nq = 0;
     for (auto& p : prims) p.type_index = p.type ? nq++ : ns++;

@@ -244,7 +244,7 @@ size_t wavefront_scratch_bytes(uint32_t n_slots) {
 cudaError_t launch_render_wavefront(const SceneView& v, const trt_camera& cam, const trt_params& p, double* d_sum64,
                                     void* d_scratch, uint32_t n_slots, void* d_ctl, int sm_count, cudaStream_t st,
                                     unsigned long long* h_rays_paths, uint32_t* launches_out) {
-    if (v.kind == 2) return cudaErrorInvalidValue;   // the flat list is a megakernel layout; commit with another kind
+    // a TRT_BVH_FLAT scene also carries its reference-topology tree (trt_scene.cpp): the wavefront walks that one
     WfArgs A;
     A.scene = dev_scene(v); A.cam = dev_camera(cam); A.p = dev_params(p);
     char* b = (char*)d_scratch;
