@@ -116,6 +116,7 @@ struct FlatPrim;
 struct DevScene {
     const float4* nodes; const float4* spheres; const float4* quads;
     const uint4* sphere_meta; const uint4* quad_meta; const float4* materials;
+    const float4* quad_nn;                      // unit normal of every quad, precomputed on the host with HitRecord::new's operations
     const FlatPrim* flat; uint32_t n_flat;      // TRT_BVH_FLAT: primitives in reference leaf order (else null / 0)
     uint32_t root, n_nodes, n_spheres, n_quads, n_materials, ordered;
     float root_min[3], root_max[3];   // the root's own padded box (only consulted when counting events)
@@ -184,10 +185,11 @@ TRT_DEV void slab_tame(float mnx, float mny, float mnz, float mxx, float mxy, fl
     *start_out = fmaxf(fmaxf(t_min, fminf(ax, bx)), fmaxf(fminf(ay, by), fminf(az, bz)));
     *end_out = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
 }
-TRT_DEV bool finite_nonzero(float x) { float a = fabsf(x); return a > 0.0f && a < TRT_INF; }
 TRT_DEV bool ray_is_tame(V3 o, V3 inv) {
-    return finite_nonzero(inv.x) && finite_nonzero(inv.y) && finite_nonzero(inv.z) &&
-           fabsf(o.x) < TRT_INF && fabsf(o.y) < TRT_INF && fabsf(o.z) < TRT_INF;
+    // all six finite (a NaN or inf makes the sum NaN or inf) and no 1/d component zero
+    float si = (fabsf(inv.x) + fabsf(inv.y)) + fabsf(inv.z), so = (fabsf(o.x) + fabsf(o.y)) + fabsf(o.z);
+    float mi = fminf(fminf(fabsf(inv.x), fabsf(inv.y)), fabsf(inv.z));
+    return si < TRT_INF && so < TRT_INF && mi > 0.0f;
 }
 TRT_DEV float rcp_approx(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
@@ -382,7 +384,9 @@ TRT_DEV Surface hit_record(const DevScene& S, Hit h, V3 o, V3 d) {
         mat = ld4u<SMEM>(S.sphere_meta + idx).x;
     }
     sf.front = dot(d, outward) < 0.0f;
-    V3 nn = normalized(outward);
+    V3 nn;
+    if (h.ref & TRT_REF_QUAD) { float4 q = ld4<SMEM>(S.quad_nn + idx); nn = mk(q.x, q.y, q.z); }   // n / |n| never changes: host-side, same ops
+    else nn = normalized(outward);
     sf.normal = sf.front ? nn : -nn;
     float4 m0 = ld4<SMEM>(S.materials + 2 * (size_t)mat);
     sf.kind = __float_as_uint(m0.w);
@@ -501,22 +505,33 @@ TRT_DEV Hit closest_hit_flat(const FlatPrim* __restrict__ U, const FlatPrim* Dv,
     const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     if (!ray_is_tame(o, inv)) return flat_scan_reference<DSMEM>(Dv, n, o, d, inv, t_min);
     // ---- phase A: which boxes does the ray cross at all
-    unsigned long long mask = 0ull;
-    for (uint32_t i = 0; i < n; ++i) {
+    uint32_t mask[2] = {0u, 0u};                       // primitives 0..31 and 32..63
+    const uint32_t n_lo = n < 32u ? n : 32u;
+    for (uint32_t i = 0; i < n_lo; ++i) {
         const float4 b0 = U[i].b0, b1 = U[i].b1;
         float s, e;
         slab_tame(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, o, inv, t_min, &s, &e);
-        if (e > s) mask |= 1ull << i;
+        if (e > s) mask[0] |= 1u << i;
+    }
+    for (uint32_t i = 32u; i < n; ++i) {
+        const float4 b0 = U[i].b0, b1 = U[i].b1;
+        float s, e;
+        slab_tame(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, o, inv, t_min, &s, &e);
+        if (e > s) mask[1] |= 1u << (i - 32u);
     }
     // ---- phase B: primitive tests of the candidates, in rank order
     uint32_t best_i = 0;
-    while (mask) {
-        const uint32_t i = (uint32_t)__ffsll((long long)mask) - 1u;
-        mask &= mask - 1ull;
-        const float4* p = (const float4*)(Dv + i);
-        const uint32_t ref = __float_as_uint(ldf<DSMEM>(p + 4).w);
-        float t;
-        if (flat_prim_hit<DSMEM>(p, ref, o, d, t_min, TRT_INF, best.t, &t) && t < best.t) { best.t = t; best.ref = ref; best_i = i; }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t m = mask[half];
+        while (m) {
+            const uint32_t i = (uint32_t)__ffs((int)m) - 1u + 32u * half;
+            m &= m - 1u;
+            const float4* p = (const float4*)(Dv + i);
+            const uint32_t ref = __float_as_uint(ldf<DSMEM>(p + 4).w);
+            float t;
+            if (flat_prim_hit<DSMEM>(p, ref, o, d, t_min, TRT_INF, best.t, &t) && t < best.t) { best.t = t; best.ref = ref; best_i = i; }
+        }
     }
     if (best.ref == TRT_REF_INVALID) return best;
     // ---- check: the winner's own box entry against its t

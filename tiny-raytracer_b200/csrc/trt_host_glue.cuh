@@ -10,7 +10,7 @@ using namespace trtd;
 inline DevScene dev_scene(const SceneView& v) {
     DevScene s;
     s.nodes = (const float4*)v.nodes; s.spheres = (const float4*)v.spheres; s.quads = (const float4*)v.quads;
-    s.sphere_meta = (const uint4*)v.sphere_meta; s.quad_meta = (const uint4*)v.quad_meta; s.materials = (const float4*)v.materials;
+    s.sphere_meta = (const uint4*)v.sphere_meta; s.quad_meta = (const uint4*)v.quad_meta; s.quad_nn = (const float4*)v.quad_nn; s.materials = (const float4*)v.materials;
     s.flat = (const FlatPrim*)v.flat; s.n_flat = v.n_flat;
     s.root = v.root; s.n_nodes = v.n_nodes; s.n_spheres = v.n_spheres; s.n_quads = v.n_quads; s.n_materials = v.n_materials;
     s.ordered = v.kind == 1 ? 1u : 0u;

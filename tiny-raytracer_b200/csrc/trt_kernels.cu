@@ -23,6 +23,9 @@ using namespace trtd;
 #ifndef TRT_MEGA_MIN_BLOCKS
 #define TRT_MEGA_MIN_BLOCKS 4      // 64 registers, ~120 B of spills that stay in L1: measured +6 % (Cornell) and +14 % (1 M spheres) over 3 blocks at 80 registers
 #endif
+#ifndef TRT_FLAT_MIN_BLOCKS
+#define TRT_FLAT_MIN_BLOCKS 3   // 80 registers, no spills: measured equal to 4 blocks with spills, and ahead of 5
+#endif
 #define MEGA_THREADS TRT_MEGA_THREADS
 
 // ------------------------------------------------------------------ shared-memory staging of small scenes
@@ -45,6 +48,7 @@ __device__ __forceinline__ DevScene stage_scene(const DevScene& G, float** tt_ou
     S.quads = copy(G.quads, 4 * G.n_quads);
     S.sphere_meta = (const uint4*)copy((const float4*)G.sphere_meta, G.n_spheres);
     S.quad_meta = (const uint4*)copy((const float4*)G.quad_meta, G.n_quads);
+    S.quad_nn = copy(G.quad_nn, G.n_quads);
     S.materials = copy(G.materials, 2 * G.n_materials);
     S.flat = (const FlatPrim*)copy((const float4*)G.flat, 6 * G.n_flat);
     *tt_out = (float*)(smem_f4 + off) + threadIdx.x;     // column of this thread, stride blockDim.x
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, TRT_MEGA_MIN_BLOCKS) k_render_me
     if (A.regen_min >= 32u) mega_body<KIND, SMEM, COUNT>(A, nullptr);
     else mega_body_async<KIND, SMEM, COUNT>(A);
 }
-__global__ void __launch_bounds__(MEGA_THREADS, TRT_MEGA_MIN_BLOCKS) k_render_mega_flat(const __grid_constant__ MegaArgs A, const __grid_constant__ FlatList L) {
+__global__ void __launch_bounds__(MEGA_THREADS, TRT_FLAT_MIN_BLOCKS) k_render_mega_flat(const __grid_constant__ MegaArgs A, const __grid_constant__ FlatList L) {
     mega_body<2, true, false>(A, L.prim);
 }
 
@@ -375,7 +379,7 @@ __global__ void k_debug_philox(size_t n, const uint32_t* ctr, uint32_t k0, uint3
 namespace trtk {
 
 size_t scene_smem_bytes(const SceneView& v) {
-    size_t b = 16ull * (4ull * v.n_nodes + v.n_spheres + 4ull * v.n_quads + v.n_spheres + v.n_quads + 2ull * v.n_materials + 6ull * v.n_flat);
+    size_t b = 16ull * (4ull * v.n_nodes + v.n_spheres + 4ull * v.n_quads + v.n_spheres + 2ull * v.n_quads + 2ull * v.n_materials + 6ull * v.n_flat);
     return b;
 }
 

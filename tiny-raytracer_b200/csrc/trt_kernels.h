@@ -11,7 +11,7 @@ struct trt_sampled_color_pod { uint32_t x, y; float c[3]; };        // == trt_sa
 namespace trtk {
 
 struct SceneView {   // device copy of trt::FlatScene
-    const void* nodes; const void* spheres; const void* quads; const void* sphere_meta; const void* quad_meta; const void* materials;
+    const void* nodes; const void* spheres; const void* quads; const void* sphere_meta; const void* quad_meta; const void* materials; const void* quad_nn;
     const void* flat;          // device copy of the flat list (6 float4 per primitive, reference leaf order) or null
     const void* flat_host;     // the same list on the host: copied into the kernel parameters of k_render_mega_flat
     uint32_t n_flat;

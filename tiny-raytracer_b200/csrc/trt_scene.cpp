@@ -325,7 +325,7 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
     if (!device_build) flatten(*tree, prims, flat);
     if (flat.max_depth > TRT_MAX_STACK) { *err = "trt_scene_commit: tree deeper than the traversal stack"; return false; }
 
-    flat.spheres.resize(ns); flat.sphere_meta.resize(ns); flat.quads.resize(4 * (size_t)nq); flat.quad_meta.resize(nq);
+    flat.spheres.resize(ns); flat.sphere_meta.resize(ns); flat.quads.resize(4 * (size_t)nq); flat.quad_nn.resize(nq); flat.quad_meta.resize(nq);
     for (size_t i = 0; i < n; ++i) {
         const HostPrim& p = prims[i];
         trt_u4 meta = {p.mat, leaf_rank[i], (uint32_t)i, 0u};
@@ -339,6 +339,9 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
             q[2] = {p.b[0], p.b[1], p.b[2], p.w[1]};
             q[3] = {p.c[0], p.c[1], p.c[2], p.w[2]};
             flat.quad_meta[p.type_index] = meta;
+            // outward_normal.normalized() of hittable/mod.rs:36-40 for this quad: v / sqrt(v.v), true divisions (vec3.rs:45-47)
+            float len = std::sqrt(p.n[0] * p.n[0] + p.n[1] * p.n[1] + p.n[2] * p.n[2]);
+            flat.quad_nn[p.type_index] = {p.n[0] / len, p.n[1] / len, p.n[2] / len, 0.f};
         }
     }
     if (bvh_kind == 2) {

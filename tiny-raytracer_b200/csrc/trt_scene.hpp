@@ -24,6 +24,7 @@ struct FlatScene {
     std::vector<trt_f4> spheres;
     std::vector<trt_f4> quads;         // 4 per quad
     std::vector<trt_u4> sphere_meta, quad_meta;
+    std::vector<trt_f4> quad_nn;       // per quad: n / |n| (what HitRecord::new computes at every hit, hittable/mod.rs:36-40), same IEEE ops
     std::vector<trt_f4> materials;     // 2 per material
     std::vector<trt_f4> flat;          // TRT_BVH_FLAT: 6 per primitive, reference leaf order (trt_layout.h)
     std::vector<trt_f4> lbvh_boxes;    // TRT_BVH_LBVH_DEVICE: 2 per primitive, (bmin, leaf-ref bits), (bmax, 0): input of the device builder

@@ -66,6 +66,7 @@ __device__ __forceinline__ DevScene wf_stage_scene(const DevScene& G) {
     S.quads = copy(G.quads, 4 * G.n_quads);
     S.sphere_meta = (const uint4*)copy((const float4*)G.sphere_meta, G.n_spheres);
     S.quad_meta = (const uint4*)copy((const float4*)G.quad_meta, G.n_quads);
+    S.quad_nn = copy(G.quad_nn, G.n_quads);
     S.materials = copy(G.materials, 2 * G.n_materials);
     __syncthreads();
     return S;
@@ -263,7 +264,7 @@ cudaError_t launch_render_wavefront(const SceneView& v, const trt_camera& cam, c
     uint32_t n_start = (uint32_t)(A.total_paths < n_slots ? A.total_paths : n_slots);
     n_start = (n_start + 31u) & ~31u; if (n_start > n_slots) n_start = n_slots;
     k_wf_init<<<(n_slots + 255) / 256, 256, 0, st>>>(A.queue[0], A.rk, n_slots, A.ctl, n_start); ++launches;
-    size_t smem = 16ull * (4ull * v.n_nodes + v.n_spheres + 4ull * v.n_quads + v.n_spheres + v.n_quads + 2ull * v.n_materials);
+    size_t smem = 16ull * (4ull * v.n_nodes + v.n_spheres + 4ull * v.n_quads + v.n_spheres + 2ull * v.n_quads + 2ull * v.n_materials);
     bool use_smem = smem <= 64 * 1024;
     if (!use_smem) smem = 0;
     bool ordered = v.kind == 1;
