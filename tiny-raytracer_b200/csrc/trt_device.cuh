@@ -448,7 +448,7 @@ TRT_DEV bool shade(const DevScene& S, const DevParams& P, Hit h, uint32_t pixel,
 //            reference's scan returns W whatever it visited before (nothing valid is closer; a tie is lower-ranked);
 //            otherwise, and for rays whose slab arithmetic can produce NaN, the lane replays the reference's scan
 //            literally (flat_scan_reference). Exact by construction.
-struct FlatPrim { float4 g0, g1, g2, g3, b0, b1; };   // geometry as in trt_layout.h; b0 = (bmin, ref bits), b1 = (bmax, 0)
+struct FlatPrim { float4 g0, g1, g2, g3, b0, b1; };   // geometry as in trt_layout.h; b0 = (bmin.xyz, bmax.x), b1 = (bmax.yz, ref bits, 0)
 
 template <bool DSMEM> TRT_DEV float4 ldf(const float4* p) { return ld4<DSMEM>(p); }
 
@@ -489,9 +489,9 @@ TRT_DEV Hit flat_scan_reference(const FlatPrim* Dv, uint32_t n, V3 o, V3 d, V3 i
         const float4* p = (const float4*)(Dv + i);
         float4 b0 = ldf<DSMEM>(p + 4), b1 = ldf<DSMEM>(p + 5);
         float s, e;
-        slab(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, o, inv, t_min, &s, &e);
+        slab(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, o, inv, t_min, &s, &e);
         if (!(e > s && best.t > s)) continue;
-        uint32_t ref = __float_as_uint(b0.w);
+        uint32_t ref = __float_as_uint(b1.z);
         float t;
         if (flat_prim_hit<DSMEM>(p, ref, o, d, t_min, best.t, best.t, &t)) { best.t = t; best.ref = ref; }
     }
@@ -510,13 +510,13 @@ TRT_DEV Hit closest_hit_flat(const FlatPrim* __restrict__ U, const FlatPrim* Dv,
     for (uint32_t i = 0; i < n_lo; ++i) {
         const float4 b0 = U[i].b0, b1 = U[i].b1;
         float s, e;
-        slab_tame(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, o, inv, t_min, &s, &e);
+        slab_tame(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, o, inv, t_min, &s, &e);
         if (e > s) mask[0] |= 1u << i;
     }
     for (uint32_t i = 32u; i < n; ++i) {
         const float4 b0 = U[i].b0, b1 = U[i].b1;
         float s, e;
-        slab_tame(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, o, inv, t_min, &s, &e);
+        slab_tame(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, o, inv, t_min, &s, &e);
         if (e > s) mask[1] |= 1u << (i - 32u);
     }
     // ---- phase B: primitive tests of the candidates, in rank order
@@ -528,7 +528,7 @@ TRT_DEV Hit closest_hit_flat(const FlatPrim* __restrict__ U, const FlatPrim* Dv,
             const uint32_t i = (uint32_t)__ffs((int)m) - 1u + 32u * half;
             m &= m - 1u;
             const float4* p = (const float4*)(Dv + i);
-            const uint32_t ref = __float_as_uint(ldf<DSMEM>(p + 4).w);
+            const uint32_t ref = __float_as_uint(ldf<DSMEM>(p + 5).z);
             float t;
             if (flat_prim_hit<DSMEM>(p, ref, o, d, t_min, TRT_INF, best.t, &t) && t < best.t) { best.t = t; best.ref = ref; best_i = i; }
         }
@@ -538,7 +538,7 @@ TRT_DEV Hit closest_hit_flat(const FlatPrim* __restrict__ U, const FlatPrim* Dv,
     const float4* p = (const float4*)(Dv + best_i);
     float4 b0 = ldf<DSMEM>(p + 4), b1 = ldf<DSMEM>(p + 5);
     float s, e;
-    slab_tame(b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, o, inv, t_min, &s, &e);
+    slab_tame(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, o, inv, t_min, &s, &e);
     if (s > best.t) return flat_scan_reference<DSMEM>(Dv, n, o, d, inv, t_min);
     return best;
 }

@@ -34,7 +34,7 @@
 
 #define TRT_MAX_STACK 64   /* traversal stack entries; trt_scene_commit rejects deeper trees */
 #define TRT_FLAT_MAX 64    /* TRT_BVH_FLAT: largest primitive count handled as a flat list (6 float4 = 96 B each:
-                              the four geometry float4 above, then (bmin.xyz, child-ref bits), (bmax.xyz, 0)) */
+                              the four geometry float4 above, then (bmin.xyz, bmax.x), (bmax.yz, child-ref bits, 0)) */
 
 struct trt_f4 { float x, y, z, w; };
 struct trt_u4 { uint32_t x, y, z, w; };

@@ -352,8 +352,8 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
             trt_f4* f = &flat.flat[6 * (size_t)leaf_rank[i]];
             if (p.type == 0) { f[0] = {p.a[0], p.a[1], p.a[2], p.r}; f[1] = f[2] = f[3] = {0.f, 0.f, 0.f, 0.f}; }
             else { for (int k = 0; k < 4; ++k) f[k] = flat.quads[4 * (size_t)p.type_index + k]; }
-            f[4] = {p.bmin[0], p.bmin[1], p.bmin[2], as_float(leaf_ref(p))};
-            f[5] = {p.bmax[0], p.bmax[1], p.bmax[2], 0.f};
+            f[4] = {p.bmin[0], p.bmin[1], p.bmin[2], p.bmax[0]};
+            f[5] = {p.bmax[1], p.bmax[2], as_float(leaf_ref(p)), 0.f};
         }
     }
     flat.materials.resize(2 * materials.size());
