@@ -474,3 +474,23 @@ def test_device_built_bvh(trt, orc, ctx):
     lin, u8, st = trt.Scene.from_desc(desc, trt.BVH_LBVH_DEVICE).render(ctx, cam, p)
     assert st.paths == ost.paths and abs(int(st.rays) - int(ost.rays)) <= 64
     assert (ulp_diff(lin, olin) > 1).any(axis=2).sum() <= 2 and psnr8(u8, ou8) >= PSNR_MIN_DB
+
+
+@pytest.mark.parametrize("n", [2, 31, 32, 33, 63, 64])
+def test_flat_list_mask_boundaries(trt, orc, ctx, n):
+    """TRT_BVH_FLAT keeps its candidates in two 32-bit masks: primitive counts around 32 and at the limit of 64, on a
+    scene full of coplanar and duplicate primitives (exact-t ties), whole paths bit-exact; 65 primitives are refused."""
+    desc = trt.scenes.random_mixed(n, 1, 96, 64, 3, 10)
+    assert desc.n_prims == n
+    osc, ocam, cam = both(trt, orc, desc)
+    sc = trt.Scene.from_desc(desc, trt.BVH_FLAT)
+    p, op = params(trt, orc, desc)
+    prim, t, rad, nr = sc.render_aov(ctx, cam, p, True, True)
+    oprim, ot, orad, onr = osc.render_aov(ocam, op, True, True)
+    assert np.array_equal(prim, oprim) and np.array_equal(bits(t), bits(ot)) and np.array_equal(nr, onr) and np.array_equal(bits(rad), bits(orad))
+    lin, u8, st = sc.render(ctx, cam, p)
+    olin, ou8, ost, _ = osc.render(ocam, op)
+    assert st.rays == ost.rays and ulp_diff(lin, olin).max() <= 1
+    with pytest.raises(trt.TrtError):
+        trt.Scene.from_desc(trt.scenes.random_mixed(65, 1), trt.BVH_FLAT)
+    assert trt.Scene.from_desc(trt.scenes.random_mixed(65, 1), trt.BVH_AUTO).bvh_info()["nodes"] == 64
