@@ -187,6 +187,9 @@ def main():
     c = desc.camera; W, H, SPP = c["width"], c["height"], desc.spp
     kind = {"auto": trt.BVH_AUTO, "sah": trt.BVH_SAH, "reference": trt.BVH_REFERENCE, "flat": trt.BVH_FLAT, "lbvh": trt.BVH_LBVH_DEVICE}[args.bvh]
     variant = trt.VARIANT_MEGAKERNEL if args.variant == "megakernel" else trt.VARIANT_WAVEFRONT
+    flat = args.bvh == "flat" or (args.bvh == "auto" and 1 <= desc.n_prims <= 64)          # TRT_BVH_AUTO's rule (trt_scene.cpp)
+    bvh_resolved = "flat" if flat else ("sah" if args.bvh == "auto" else args.bvh)
+    kernel_name = "k_wf_shade + k_wf_extend" if variant != 0 else ("k_render_mega_flat" if flat else "k_render_mega")
     ctx = trt.Context(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)   # same stream as torch's events and the NCCL reduce
     cam = trt.make_camera(**c)
@@ -316,7 +319,7 @@ def main():
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(args.workload)
         roofline = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": traffic,
-                    "kernel": "k_render_mega" if variant == 0 else "k_wavefront_*", "kernel_ms": kern_avg_ms, "peak_source": peak_src,
+                    "kernel": kernel_name, "kernel_ms": kern_avg_ms, "peak_source": peak_src,
                     "algorithmic_bytes_per_ray": per_ray["bytes"], "events_per_ray": {k: per_ray[k] for k in ("V", "Ps", "Pq", "H")},
                     "events_source": per_ray_src,
                     "note": "scene is cache-resident for Cornell-sized workloads: the binding bound is fp32 issue, see roofline_issue"}
@@ -329,7 +332,7 @@ def main():
     out = {"metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "mpaths_per_s": mpaths, "rays_per_step": rays, "paths_per_step": paths,
-           "config": {"workload": workload_string(desc), "bvh": args.bvh, "variant": args.variant,
+           "config": {"workload": workload_string(desc), "bvh": args.bvh, "bvh_resolved": bvh_resolved, "kernel": kernel_name, "variant": args.variant,
                       "parallelism": "spp-partitioned x%d + NCCL reduce(f64 sum)" % world if world > 1 else "single GPU",
                       "l2": "256 MiB memset between timed steps (outside the events)", "timing": "per-step CUDA events on the launch stream, max over ranks"},
            "clocks": clk,
