@@ -494,3 +494,26 @@ def test_flat_list_mask_boundaries(trt, orc, ctx, n):
     with pytest.raises(trt.TrtError):
         trt.Scene.from_desc(trt.scenes.random_mixed(65, 1), trt.BVH_FLAT)
     assert trt.Scene.from_desc(trt.scenes.random_mixed(65, 1), trt.BVH_AUTO).bvh_info()["nodes"] == 64
+
+
+@pytest.mark.parametrize("kind", [0, 1, 3])
+def test_cuda_matches_committed_golden_fixtures(trt, ctx, kind):
+    """The CUDA path against tests/golden/golden_small.npz (oracle outputs committed with their generator): no oracle run
+    is involved here, so this also holds if the oracle library cannot be built on the GPU box."""
+    import importlib.util, os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(gdir, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    g = np.load(os.path.join(gdir, "golden_small.npz"))
+    for name, mk in mg.CASES.items():
+        d = mk(trt.scenes); c = d.camera
+        sc = trt.Scene.from_desc(d, kind)
+        cam = trt.make_camera(**c)
+        p = trt.make_params(c["width"], c["height"], d.spp, d.max_bounces, d.background, d.seed)
+        prim, t, rad, nr = sc.render_aov(ctx, cam, p, True, True)
+        lin, u8, st = sc.render(ctx, cam, p)
+        assert np.array_equal(prim, g[name + "/prim"]) and np.array_equal(bits(t), bits(g[name + "/t"])), name
+        assert np.array_equal(bits(rad), bits(g[name + "/rad"])) and np.array_equal(nr, g[name + "/nr"]), name
+        assert ulp_diff(lin, g[name + "/lin"]).max() <= 1 and np.abs(u8.astype(int) - g[name + "/u8"].astype(int)).max() <= 1, name
+        assert (st.paths, st.rays) == (int(g[name + "/counts"][0]), int(g[name + "/counts"][1])), name
+        assert np.array_equal(sc.leaf_ranks(), g[name + "/ranks"]), name
