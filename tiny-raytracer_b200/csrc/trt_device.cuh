@@ -507,17 +507,17 @@ TRT_DEV Hit closest_hit_flat(const FlatPrim* __restrict__ U, const FlatPrim* Dv,
     // ---- phase A: which boxes does the ray cross at all
     uint32_t mask[2] = {0u, 0u};                       // primitives 0..31 and 32..63
     const uint32_t n_lo = n < 32u ? n : 32u;
-    for (uint32_t i = 0; i < n_lo; ++i) {
+    for (uint32_t i = 0, bit = 1u; i < n_lo; ++i, bit += bit) {       // `bit` is uniform: one add, one predicated or
         const float4 b0 = U[i].b0, b1 = U[i].b1;
         float s, e;
         slab_tame(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, o, inv, t_min, &s, &e);
-        if (e > s) mask[0] |= 1u << i;
+        if (e > s) mask[0] |= bit;
     }
-    for (uint32_t i = 32u; i < n; ++i) {
+    for (uint32_t i = 32u, bit = 1u; i < n; ++i, bit += bit) {
         const float4 b0 = U[i].b0, b1 = U[i].b1;
         float s, e;
         slab_tame(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, o, inv, t_min, &s, &e);
-        if (e > s) mask[1] |= 1u << (i - 32u);
+        if (e > s) mask[1] |= bit;
     }
     // ---- phase B: primitive tests of the candidates, in rank order
     uint32_t best_i = 0;
