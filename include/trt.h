@@ -67,6 +67,9 @@ typedef struct trt_params {
     uint32_t flags;              /* TRT_FLAG_* */
 } trt_params;
 #define TRT_FLAG_COUNT_EVENTS 1u   /* also count node visits / primitive tests (slower; for roofline accounting) */
+#define TRT_FLAG_NO_TAIL_SPLIT 2u  /* megakernel: hand out whole pixels only (every pixel summed by one lane in sample order ->
+                                    * run-to-run bit-identical f64 sums); default splits the last pixels into sample chunks
+                                    * added with f64 atomics (tail balance; the f32 image can move by <= 1 ulp) */
 /* bits 8..15 of flags: megakernel tuning override, the number of lanes of a warp (1..32) that must have finished their ray
  * before the shade/regenerate block runs; 0 = chosen from the tree size (32 up to 4096 nodes, 16 above). Results do not
  * depend on it. */

@@ -15,6 +15,7 @@ ap.add_argument("--kinds", default="0,1")
 ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--c4n", type=int, default=1_000_000)
+ap.add_argument("--flags", type=int, default=0, help="extra trt_params.flags bits (2 = no tail split)")
 ap.add_argument("--regen", default="0", help="comma list of regen_min overrides (0 = auto)")
 a = ap.parse_args()
 
@@ -34,7 +35,7 @@ for wl in a.workloads.split(","):
         acc = torch.zeros(h * w * 3, dtype=torch.float64, device="cuda:0")
         torch.cuda.synchronize()
         for regen in [int(x) for x in a.regen.split(",")]:
-            p = trt.make_params(w, h, a.spp, desc.max_bounces, desc.background, desc.seed, spp_total=a.spp, variant=a.variant, flags=(regen & 255) << 8)
+            p = trt.make_params(w, h, a.spp, desc.max_bounces, desc.background, desc.seed, spp_total=a.spp, variant=a.variant, flags=((regen & 255) << 8) | a.flags)
             best = None
             for r in range(a.reps):
                 acc.zero_(); torch.cuda.synchronize()

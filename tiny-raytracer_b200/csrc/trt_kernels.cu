@@ -63,18 +63,26 @@ struct MegaArgs {
     unsigned long long* counters;  // [0] rays [1] paths [2] node_visits [3] sphere_tests [4] quad_tests
     unsigned int* next_item;       // work counter
     uint32_t chunk, n_chunks, tiles_x, tiles_y, n_items;
+    uint32_t tiles_whole;          // the first tiles_whole tiles are handed out as whole pixels (all samples, plain store);
+                                   // the remaining tiles as n_chunks items of `chunk` samples each (f64 atomicAdd): small
+                                   // items at the end of the job, so that lanes do not idle behind the last whole pixel
     uint32_t regen_min;            // lanes that must be waiting before the shade/regenerate block runs (32 = T-then-S)
 };
 struct FlatList { FlatPrim prim[TRT_FLAT_MAX]; };
 
-// item -> (pixel, sample range). Items are ordered chunk-major over 8x4 pixel tiles, 32 consecutive items = one tile.
-__device__ __forceinline__ bool decode_item(const MegaArgs& A, uint32_t item, uint32_t* x, uint32_t* y, uint32_t* s0, uint32_t* s1) {
-    uint32_t lane = item & 31u, t = item >> 5;
-    uint32_t n_tiles = A.tiles_x * A.tiles_y;
-    uint32_t chunk = t / n_tiles, tile = t - chunk * n_tiles;
+// item -> (pixel, sample range). 32 consecutive items = one 8x4 pixel tile. `exclusive` = this lane alone adds to the pixel.
+__device__ __forceinline__ bool decode_item(const MegaArgs& A, uint32_t item, uint32_t* x, uint32_t* y, uint32_t* s0, uint32_t* s1, bool* exclusive) {
+    uint32_t lane = item & 31u, t = item >> 5, tile;
+    if (t < A.tiles_whole) { tile = t; *s0 = 0; *s1 = A.p.spp; *exclusive = true; }
+    else {
+        uint32_t r = t - A.tiles_whole, tiles_rest = A.tiles_x * A.tiles_y - A.tiles_whole;
+        uint32_t chunk = r / tiles_rest;                      // chunk-major over the remaining tiles
+        tile = A.tiles_whole + (r - chunk * tiles_rest);
+        *s0 = chunk * A.chunk; uint32_t e = *s0 + A.chunk; *s1 = e < A.p.spp ? e : A.p.spp;
+        *exclusive = A.n_chunks == 1;
+    }
     uint32_t ty = tile / A.tiles_x, tx = tile - ty * A.tiles_x;
     *x = tx * 8 + (lane & 7u); *y = ty * 4 + (lane >> 3);
-    *s0 = chunk * A.chunk; uint32_t e = *s0 + A.chunk; *s1 = e < A.p.spp ? e : A.p.spp;
     return *x < A.p.width && *y < A.p.height;
 }
 
@@ -91,7 +99,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& A, const FlatPrim* U) 
     V3 o = mk(0, 0, 0), d = mk(0, 0, 1), atten = mk(1, 1, 1), color = mk(0, 0, 0);
     uint32_t pixel = 0, px = 0, py = 0, s_cur = 0, s_end = 0, remain = 0, k = 0;
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-    bool alive = false, done = false, has_item = false;
+    bool alive = false, done = false, has_item = false, exclusive = true;
     uint32_t n_rays = 0, n_paths = 0;
     EventCounters ec; ec.node_visits = ec.sphere_tests = ec.quad_tests = 0;
 
@@ -127,7 +135,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& A, const FlatPrim* U) 
         if (m) {
             if (need_item && has_item) {
                 double* dst = A.sum64 + 3 * (size_t)pixel;
-                if (A.n_chunks == 1) { dst[0] += acc0; dst[1] += acc1; dst[2] += acc2; }   // pixel owned by this lane alone
+                if (exclusive) { dst[0] += acc0; dst[1] += acc1; dst[2] += acc2; }   // pixel owned by this lane alone
                 else { atomicAdd(dst, acc0); atomicAdd(dst + 1, acc1); atomicAdd(dst + 2, acc2); }
                 has_item = false;
             }
@@ -139,7 +147,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& A, const FlatPrim* U) 
                 uint32_t item = base + __popc(m & ((1u << lane) - 1u));
                 if (item < A.n_items) {
                     uint32_t s0, s1;
-                    if (decode_item(A, item, &px, &py, &s0, &s1)) {
+                    if (decode_item(A, item, &px, &py, &s0, &s1, &exclusive)) {
                         pixel = py * P.width + px; s_cur = s0; s_end = s1; has_item = true;
                         acc0 = acc1 = acc2 = 0.0;
                         if (P.max_bounces == 0) { n_paths += s1 - s0; s_cur = s1; }      // no ray is ever cast (cpu.rs:47)
@@ -194,7 +202,7 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
     V3 atten = mk(1, 1, 1), color = mk(0, 0, 0);
     uint32_t pixel = 0, px = 0, py = 0, s_cur = 0, s_end = 0, remain = 0, k = 0;
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-    bool alive = false, done = false, has_item = false;     // alive: the lane carries a path; T.cur != INVALID: its ray is still being traced
+    bool alive = false, done = false, has_item = false, exclusive = true;     // alive: the lane carries a path; T.cur != INVALID: its ray is still being traced
     uint32_t n_rays = 0, n_paths = 0;
     EventCounters ec; ec.node_visits = ec.sphere_tests = ec.quad_tests = 0;
     const int regen_min = (int)A.regen_min;
@@ -231,7 +239,7 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
         if (m) {
             if (need_item && has_item) {
                 double* dst = A.sum64 + 3 * (size_t)pixel;
-                if (A.n_chunks == 1) { dst[0] += acc0; dst[1] += acc1; dst[2] += acc2; }
+                if (exclusive) { dst[0] += acc0; dst[1] += acc1; dst[2] += acc2; }
                 else { atomicAdd(dst, acc0); atomicAdd(dst + 1, acc1); atomicAdd(dst + 2, acc2); }
                 has_item = false;
             }
@@ -243,7 +251,7 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
                 uint32_t item = base + __popc(m & ((1u << lane) - 1u));
                 if (item < A.n_items) {
                     uint32_t s0, s1;
-                    if (decode_item(A, item, &px, &py, &s0, &s1)) {
+                    if (decode_item(A, item, &px, &py, &s0, &s1, &exclusive)) {
                         pixel = py * P.width + px; s_cur = s0; s_end = s1; has_item = true;
                         acc0 = acc1 = acc2 = 0.0;
                         if (P.max_bounces == 0) { n_paths += s1 - s0; s_cur = s1; }
@@ -428,18 +436,26 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     int grid = sm_count * blocks_per_sm;
     uint64_t resident = (uint64_t)grid * MEGA_THREADS;
     uint64_t pixels = (uint64_t)p.width * p.height;
-    // chunk of samples per work item: whole pixels when there are plenty of them, otherwise split so that the
-    // persistent lanes see >= ~8 items each (tail balance); never below 4 samples per item.
+    // work items: whole pixels (all samples, plain store) while there are plenty of them; the LAST tiles of the list are
+    // split into chunks of samples so that no lane idles behind one long final pixel (at 1024 spp a pixel is 1/14 of a
+    // lane's whole job). With few pixels everything is split so that the lanes see >= ~8 items each. Never < 4 samples.
     uint32_t chunk = p.spp ? p.spp : 1;
+    A.tiles_x = (p.width + 7) / 8; A.tiles_y = (p.height + 3) / 4;
+    uint64_t n_tiles = (uint64_t)A.tiles_x * A.tiles_y, tiles_rest = n_tiles;
     if (pixels < 8 * resident) {
         uint64_t want_chunks = (8 * resident + pixels - 1) / (pixels ? pixels : 1);
         uint64_t c = (p.spp + want_chunks - 1) / want_chunks;
         if (c < 4) c = 4;
         if (c < chunk) chunk = (uint32_t)c;
+    } else if (p.spp >= 32 && !(p.flags & TRT_FLAG_NO_TAIL_SPLIT)) {
+        tiles_rest = (2 * resident + 31) / 32;                 // ~2 pixels per lane are handed out in pieces
+        if (tiles_rest > n_tiles) tiles_rest = n_tiles;
+        chunk = (p.spp + 7) / 8; if (chunk < 4) chunk = 4;
     }
     A.chunk = chunk; A.n_chunks = p.spp ? (p.spp + chunk - 1) / chunk : 0;
-    A.tiles_x = (p.width + 7) / 8; A.tiles_y = (p.height + 3) / 4;
-    uint64_t n_items = (uint64_t)A.tiles_x * A.tiles_y * 32ull * A.n_chunks;
+    A.tiles_whole = (uint32_t)(n_tiles - tiles_rest);
+    uint64_t n_items = 32ull * (A.tiles_whole + tiles_rest * A.n_chunks);
+    if (p.spp == 0) n_items = 0;
     if (n_items > 0xFFFFFFF0ull - resident) return cudaErrorInvalidValue;
     A.n_items = (uint32_t)n_items;
     if (v.kind == 2) {
