@@ -118,6 +118,7 @@ struct DevScene {
     const uint4* sphere_meta; const uint4* quad_meta; const float4* materials;
     const float4* quad_nn;                      // unit normal of every quad, precomputed on the host with HitRecord::new's operations
     const FlatPrim* flat; uint32_t n_flat;      // TRT_BVH_FLAT: primitives in reference leaf order (else null / 0)
+    const float4* flat_cbox; float flat_bound;  // TRT_BVH_FLAT: conservative centre/half-width boxes (phase A), largest |coordinate|
     uint32_t root, n_nodes, n_spheres, n_quads, n_materials, ordered;
     float root_min[3], root_max[3];   // the root's own padded box (only consulted when counting events)
 };
@@ -439,16 +440,41 @@ TRT_DEV bool shade(const DevScene& S, const DevParams& P, Hit h, uint32_t pixel,
 // left-to-right leaf order. The reference's Node::hit is then exactly a scan of that list with the running closest hit
 // as range end (every ancestor box contains the leaf box, so only the leaf's own box test can cull).
 // A SIMT machine runs the box half of that scan with zero control divergence, because every lane tests box i in iteration i:
-//   phase A  (uniform loop, box data from the kernel-parameter constant bank): the slab test of every primitive's own
-//            padded box against [t_min, inf) (bvh.rs:89 with an open range end); the passing ones form a 64-bit mask.
+//   phase A  (uniform loop, box data from the kernel-parameter constant bank): a conservative slab test of every
+//            primitive's own padded box against [t_min, inf); the passing ones — a superset of the boxes bvh.rs:89
+//            accepts with an open range end — form a 64-bit mask.
 //   phase B  (per lane): the primitive test (quad.rs:33-41 / sphere.rs:29-45) of the set bits in rank order, keeping the
-//            smallest t (a tie keeps the lower rank). That is the (t, rank)-smallest VALID primitive W — valid = its
-//            own box is crossed and it is hit — because no candidate is culled by distance.
-//   check    if W's box entry does not exceed its t — always, except for fp cancellation on grazing hits — the
-//            reference's scan returns W whatever it visited before (nothing valid is closer; a tie is lower-ranked);
-//            otherwise, and for rays whose slab arithmetic can produce NaN, the lane replays the reference's scan
-//            literally (flat_scan_reference). Exact by construction.
+//            smallest t (a tie keeps the lower rank): W', the (t, rank)-smallest hit candidate.
+//   check    W's own box is tested exactly. If it is crossed, W' is the (t, rank)-smallest VALID primitive W (valid =
+//            own box crossed and hit; W is a candidate too and nothing hit is smaller than W'). If moreover W's box
+//            entry does not exceed its t — always, except for fp cancellation on grazing hits — the reference's scan
+//            returns W whatever it visited before (nothing valid is closer; a tie is lower-ranked). Otherwise, and for
+//            rays whose slab arithmetic can overflow or produce NaN, the lane replays the reference's scan literally
+//            (flat_scan_reference). No hit candidate at all means no valid primitive: a miss. Exact by construction.
 struct FlatPrim { float4 g0, g1, g2, g3, b0, b1; };   // geometry as in trt_layout.h; b0 = (bmin.xyz, bmax.x), b1 = (bmax.yz, ref bits, 0)
+
+// Phase A does not need the exact box test: a SUPERSET of the crossed boxes gives the same winner as long as the winner's
+// own box is then tested exactly (the check below), because a primitive that is not the closest valid one never decides
+// anything. So phase A runs a cheaper conservative test on the centre/half-width form of the box,
+//     m = mid*inv - o*inv,   near = m - half*|inv|,   far = m + half*|inv|      (one FMA each, 9 per box instead of 6+6)
+// issued as packed FFMA2 (sm_100 `fma.rn.f32x2`, two boxes per group), and accepts when far + E > near, where
+// E = 2.5 * 2^-21 * max_axis (bound + |o|)*|inv| dominates the rounding difference between this form and the reference's
+// `(b - o) * inv` (both are within 5.1 * 2^-24 * (bound + |o|)*|inv| of the real value per axis; the host
+// rounds `half` up so that [mid - half, mid + half] contains the box). Only taken for rays with |1/d| < 2^64 and
+// |o| < 2^30 on every axis and scenes with bound <= 2^30 (no overflow, no NaN); every other ray replays the literal scan.
+// Layout: 3 float4 per PAIR of primitives (2j, 2j+1): (m0.x m1.x m0.y m1.y) (m0.z m1.z h0.x h1.x) (h0.y h1.y h0.z h1.z),
+// padded with NaN (never accepted) to TRT_FLAT_MAX primitives.
+#define TRT_FLAT_CBOX_F4 (3 * TRT_FLAT_MAX / 2)
+#define TRT_FLAT_EPS 1.1920929e-6f      /* 2.5 * 2^-21 */
+typedef unsigned long long f32x2;
+TRT_DEV f32x2 pk2(float lo, float hi) { f32x2 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d; }
+TRT_DEV void upk2(f32x2 v, float* lo, float* hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(*lo), "=f"(*hi) : "l"(v)); }
+TRT_DEV f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+TRT_DEV bool ray_is_flat_fast(V3 o, V3 inv) {
+    float si = (fabsf(inv.x) + fabsf(inv.y)) + fabsf(inv.z), so = (fabsf(o.x) + fabsf(o.y)) + fabsf(o.z);   // NaN/inf fail both
+    float mi = fminf(fminf(fabsf(inv.x), fabsf(inv.y)), fabsf(inv.z));
+    return si < 1.8446744e19f && so < 1.0737418e9f && mi > 0.0f;
+}
 
 template <bool DSMEM> TRT_DEV float4 ldf(const float4* p) { return ld4<DSMEM>(p); }
 
@@ -498,26 +524,42 @@ TRT_DEV Hit flat_scan_reference(const FlatPrim* Dv, uint32_t n, V3 o, V3 d, V3 i
     return best;
 }
 
-// U: the list as seen by uniform (same-address) loads; Dv: the same list for per-lane indexed loads.
+// CB: the conservative boxes as seen by uniform (same-address) loads — kernel parameters in the megakernel;
+// Dv: the primitive list for per-lane indexed loads.
 template <bool DSMEM>
-TRT_DEV Hit closest_hit_flat(const FlatPrim* __restrict__ U, const FlatPrim* Dv, uint32_t n, V3 o, V3 d, float t_min) {
+TRT_DEV Hit closest_hit_flat(const float4* __restrict__ CB, float bound, const FlatPrim* Dv, uint32_t n, V3 o, V3 d, float t_min) {
     Hit best; best.t = TRT_INF; best.ref = TRT_REF_INVALID;
     const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    if (!ray_is_tame(o, inv)) return flat_scan_reference<DSMEM>(Dv, n, o, d, inv, t_min);
-    // ---- phase A: which boxes does the ray cross at all
+    if (!(ray_is_flat_fast(o, inv) && bound >= 0.0f)) return flat_scan_reference<DSMEM>(Dv, n, o, d, inv, t_min);
+    // ---- phase A: which boxes can the ray cross at all (superset)
+    const float aix = fabsf(inv.x), aiy = fabsf(inv.y), aiz = fabsf(inv.z);
+    const float E = fmaxf(fmaxf((bound + fabsf(o.x)) * aix, (bound + fabsf(o.y)) * aiy), (bound + fabsf(o.z)) * aiz) * TRT_FLAT_EPS + 1e-30f;
+    const float cx = -(o.x * inv.x), cy = -(o.y * inv.y), cz = -(o.z * inv.z);
+    // every per-ray operand is a scalar broadcast to both halves (pk2(v, v)); the pairs are the two boxes of a group
+    const f32x2 ix2 = pk2(inv.x, inv.x), iy2 = pk2(inv.y, inv.y), iz2 = pk2(inv.z, inv.z);
+    const f32x2 cx2 = pk2(cx, cx), cy2 = pk2(cy, cy), cz2 = pk2(cz, cz);
+    const f32x2 px2 = pk2(aix, aix), py2 = pk2(aiy, aiy), pz2 = pk2(aiz, aiz);
+    const f32x2 nx2 = pk2(-aix, -aix), ny2 = pk2(-aiy, -aiy), nz2 = pk2(-aiz, -aiz);
     uint32_t mask[2] = {0u, 0u};                       // primitives 0..31 and 32..63
-    const uint32_t n_lo = n < 32u ? n : 32u;
-    for (uint32_t i = 0, bit = 1u; i < n_lo; ++i, bit += bit) {       // `bit` is uniform: one add, one predicated or
-        const float4 b0 = U[i].b0, b1 = U[i].b1;
-        float s, e;
-        slab_tame(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, o, inv, t_min, &s, &e);
-        if (e > s) mask[0] |= bit;
-    }
-    for (uint32_t i = 32u, bit = 1u; i < n; ++i, bit += bit) {
-        const float4 b0 = U[i].b0, b1 = U[i].b1;
-        float s, e;
-        slab_tame(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, o, inv, t_min, &s, &e);
-        if (e > s) mask[1] |= bit;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        if (half == 1 && n <= 32u) break;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {                 // pair j of this half; static indices -> constant-bank operands
+            const int pr = 16 * half + j;
+            if ((j & 1) == 0 && 2u * pr >= n) break;   // n is padded to a multiple of 4 with NaN boxes
+            const float4 a = CB[3 * pr], b = CB[3 * pr + 1], c = CB[3 * pr + 2];
+            const f32x2 hx = pk2(b.z, b.w), hy = pk2(c.x, c.y), hz = pk2(c.z, c.w);
+            const f32x2 mx = fma2(pk2(a.x, a.y), ix2, cx2), my = fma2(pk2(a.z, a.w), iy2, cy2), mz = fma2(pk2(b.x, b.y), iz2, cz2);
+            float n0x, f0x, n0y, f0y, n0z, f0z, n1x, f1x, n1y, f1y, n1z, f1z;
+            upk2(fma2(hx, nx2, mx), &n0x, &n1x); upk2(fma2(hx, px2, mx), &f0x, &f1x);
+            upk2(fma2(hy, ny2, my), &n0y, &n1y); upk2(fma2(hy, py2, my), &f0y, &f1y);
+            upk2(fma2(hz, nz2, mz), &n0z, &n1z); upk2(fma2(hz, pz2, mz), &f0z, &f1z);
+            const float s0 = fmaxf(fmaxf(t_min, n0x), fmaxf(n0y, n0z)), e0 = fminf(fminf(f0x, f0y), f0z);
+            const float s1 = fmaxf(fmaxf(t_min, n1x), fmaxf(n1y, n1z)), e1 = fminf(fminf(f1x, f1y), f1z);
+            if (e0 + E > s0) mask[half] |= 1u << (2 * j);
+            if (e1 + E > s1) mask[half] |= 2u << (2 * j);
+        }
     }
     // ---- phase B: primitive tests of the candidates, in rank order
     uint32_t best_i = 0;
@@ -534,12 +576,12 @@ TRT_DEV Hit closest_hit_flat(const FlatPrim* __restrict__ U, const FlatPrim* Dv,
         }
     }
     if (best.ref == TRT_REF_INVALID) return best;
-    // ---- check: the winner's own box entry against its t
+    // ---- check: the winner's own box, exactly (bvh.rs:89), and its entry against its t
     const float4* p = (const float4*)(Dv + best_i);
     float4 b0 = ldf<DSMEM>(p + 4), b1 = ldf<DSMEM>(p + 5);
     float s, e;
     slab_tame(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, o, inv, t_min, &s, &e);
-    if (s > best.t) return flat_scan_reference<DSMEM>(Dv, n, o, d, inv, t_min);
+    if (!(e > s) || s > best.t) return flat_scan_reference<DSMEM>(Dv, n, o, d, inv, t_min);
     return best;
 }
 
@@ -547,7 +589,7 @@ TRT_DEV Hit closest_hit_flat(const FlatPrim* __restrict__ U, const FlatPrim* Dv,
 // KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH, 2 = TRT_BVH_FLAT
 template <int KIND, bool SMEM, bool COUNT>
 TRT_DEV Hit closest_hit_any(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
-    if (KIND == 2) return closest_hit_flat<false>(S.flat, S.flat, S.n_flat, o, d, t_min);
+    if (KIND == 2) return closest_hit_flat<false>(S.flat_cbox, S.flat_bound, S.flat, S.n_flat, o, d, t_min);
     return closest_hit<KIND == 1, SMEM, COUNT>(S, o, d, t_min, ec);
 }
 

@@ -68,7 +68,7 @@ struct MegaArgs {
                                    // items at the end of the job, so that lanes do not idle behind the last whole pixel
     uint32_t regen_min;            // lanes that must be waiting before the shade/regenerate block runs (32 = T-then-S)
 };
-struct FlatList { FlatPrim prim[TRT_FLAT_MAX]; };
+struct FlatList { float4 cbox[TRT_FLAT_CBOX_F4]; };   // phase-A boxes of the flat list, read as kernel parameters (constant bank)
 
 // item -> (pixel, sample range). 32 consecutive items = one 8x4 pixel tile. `exclusive` = this lane alone adds to the pixel.
 __device__ __forceinline__ bool decode_item(const MegaArgs& A, uint32_t item, uint32_t* x, uint32_t* y, uint32_t* s0, uint32_t* s1, bool* exclusive) {
@@ -89,9 +89,9 @@ __device__ __forceinline__ bool decode_item(const MegaArgs& A, uint32_t item, ui
 // Loop body = T (one ray segment for every live lane) then S (shade-or-regenerate, fused so that the scattering lanes
 // and the lanes starting a new path share ONE Philox call, ONE normalisation and the work-fetch point; every lane that
 // still has work leaves S with a live ray, so T always runs with full lanes until the work counter runs dry).
-// KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH, 2 = TRT_BVH_FLAT (U = the list in the constant bank).
+// KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH, 2 = TRT_BVH_FLAT (U = the phase-A boxes in the constant bank).
 template <int KIND, bool SMEM, bool COUNT>
-__device__ __forceinline__ void mega_body(const MegaArgs& A, const FlatPrim* U) {
+__device__ __forceinline__ void mega_body(const MegaArgs& A, const float4* U) {
     float* tt;
     const DevScene S = stage_scene<SMEM>(A.scene, &tt);
     const DevParams& P = A.p;
@@ -107,7 +107,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& A, const FlatPrim* U) 
         // ---- T: cpu.rs:48
         Hit h; h.t = TRT_INF; h.ref = TRT_REF_INVALID;
         if (alive) {
-            if (KIND == 2) h = closest_hit_flat<true>(U, S.flat, S.n_flat, o, d, P.t_min);
+            if (KIND == 2) h = closest_hit_flat<true>(U, S.flat_bound, S.flat, S.n_flat, o, d, P.t_min);
             else h = closest_hit<KIND == 1, SMEM, COUNT>(S, o, d, P.t_min, &ec);
             ++n_rays;
         }
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, TRT_MEGA_MIN_BLOCKS) k_render_me
     else mega_body_async<KIND, SMEM, COUNT>(A);
 }
 __global__ void __launch_bounds__(MEGA_THREADS, TRT_FLAT_MIN_BLOCKS) k_render_mega_flat(const __grid_constant__ MegaArgs A, const __grid_constant__ FlatList L) {
-    mega_body<2, true, false>(A, L.prim);
+    mega_body<2, true, false>(A, L.cbox);
 }
 
 // ------------------------------------------------------------------ AOV / sample batch / trace
@@ -415,7 +415,7 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     A.regen_min = regen > 32u ? 32u : regen;
     size_t smem = scene_smem_bytes(v);
     bool use_smem = smem <= 64 * 1024;
-    if (v.kind == 2 && (!use_smem || v.n_flat > TRT_FLAT_MAX || !v.flat_host)) return cudaErrorInvalidValue;
+    if (v.kind == 2 && (!use_smem || v.n_flat > TRT_FLAT_MAX || !v.flat_cbox_host)) return cudaErrorInvalidValue;
     if (!use_smem) smem = 0;
     bool count = (p.flags & 1u) != 0;
     const void* fn = nullptr; int blocks_per_sm = 0; cudaError_t e;
@@ -459,10 +459,8 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     if (n_items > 0xFFFFFFF0ull - resident) return cudaErrorInvalidValue;
     A.n_items = (uint32_t)n_items;
     if (v.kind == 2) {
-        static_assert(sizeof(FlatList) == 96 * TRT_FLAT_MAX, "FlatPrim must be 6 float4");
         FlatList L;
-        memset(&L, 0, sizeof L);
-        memcpy(&L, v.flat_host, 96ull * v.n_flat);
+        memcpy(&L, v.flat_cbox_host, sizeof L);
         void* args[] = {(void*)&A, (void*)&L};
         return cudaLaunchKernel(fn, dim3(grid), dim3(MEGA_THREADS), args, smem, st);
     }

@@ -355,6 +355,32 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
             f[4] = {p.bmin[0], p.bmin[1], p.bmin[2], p.bmax[0]};
             f[5] = {p.bmax[1], p.bmax[2], as_float(leaf_ref(p)), 0.f};
         }
+        // phase-A boxes: [mid - half, mid + half] must contain the padded box in real arithmetic, so `half` is computed in
+        // double from the rounded float `mid` and then rounded up (two float steps cover the double rounding as well)
+        const float nan = std::numeric_limits<float>::quiet_NaN();
+        std::vector<float> mid(3 * TRT_FLAT_MAX, nan), half(3 * TRT_FLAT_MAX, nan);
+        double bound = 0.0; bool finite = true;
+        for (size_t i = 0; i < n; ++i) {
+            const HostPrim& p = prims[i];
+            const size_t r = leaf_rank[i];
+            for (int k = 0; k < 3; ++k) {
+                const double lo = p.bmin[k], hi = p.bmax[k];
+                const float m = (float)(0.5 * (lo + hi));
+                float h = (float)std::max((double)m - lo, hi - (double)m);
+                h = std::nextafter(std::nextafter(h, std::numeric_limits<float>::infinity()), std::numeric_limits<float>::infinity());
+                mid[3 * r + k] = m; half[3 * r + k] = h;
+                if (!std::isfinite(lo) || !std::isfinite(hi) || !std::isfinite(h)) finite = false;
+                bound = std::max(bound, std::max(std::fabs(lo), std::fabs(hi)));
+            }
+        }
+        flat.flat_cbox.resize(3 * TRT_FLAT_MAX / 2);
+        for (size_t j = 0; j < TRT_FLAT_MAX / 2; ++j) {
+            const float *m0 = &mid[6 * j], *m1 = &mid[6 * j + 3], *h0 = &half[6 * j], *h1 = &half[6 * j + 3];
+            flat.flat_cbox[3 * j] = {m0[0], m1[0], m0[1], m1[1]};
+            flat.flat_cbox[3 * j + 1] = {m0[2], m1[2], h0[0], h1[0]};
+            flat.flat_cbox[3 * j + 2] = {h0[1], h1[1], h0[2], h1[2]};
+        }
+        flat.flat_bound = (finite && bound <= 1073741824.0) ? (float)bound : -1.f;
     }
     flat.materials.resize(2 * materials.size());
     for (size_t m = 0; m < materials.size(); ++m) {
