@@ -122,7 +122,8 @@ struct DevScene {
     uint32_t root, n_nodes, n_spheres, n_quads, n_materials, ordered;
     float root_min[3], root_max[3];   // the root's own padded box (only consulted when counting events)
 };
-struct DevCamera { V3 position, upper_left, horizontal, vertical, du, dv; uint32_t width, height; };
+struct DevCamera { V3 position, upper_left, horizontal, vertical, du, dv; uint32_t width, height;
+                   uint32_t pinhole; };   // du == dv == 0 and no -0 in position: the lens sample cannot change the origin
 struct DevParams {
     uint32_t width, height, spp, sample_offset, max_bounces;
     float bg[3]; uint32_t seed_lo, seed_hi; float t_min;
@@ -348,14 +349,18 @@ TRT_DEV void camera_ray(const DevCamera& C, const DevParams& P, uint32_t x, uint
                         V3* o_out, V3* dir_out) {
     float u = ((float)x + u01(r.x)) / (float)(C.width - 1);
     float v = ((float)y + u01(r.y)) / (float)(C.height - 1);
-    float a = u11(r.z), b = u11(r.w);
-    uint32_t block = 1;
-    while (!(a * a + b * b + 0.0f * 0.0f < 1.0f)) {       // squared_length of (a, b, 0)
-        U4 e = philox4x32_10(pixel, sample, 0u, block++, P.seed_lo, P.seed_hi);
-        a = u11(e.x); b = u11(e.y);
-        if (!(a * a + b * b + 0.0f * 0.0f < 1.0f)) { a = u11(e.z); b = u11(e.w); }
-    }
-    V3 origin = C.position + a * C.du + b * C.dv;
+    V3 origin = C.position;
+    if (!C.pinhole) {
+        float a = u11(r.z), b = u11(r.w);
+        uint32_t block = 1;
+        while (!(a * a + b * b + 0.0f * 0.0f < 1.0f)) {       // squared_length of (a, b, 0)
+            U4 e = philox4x32_10(pixel, sample, 0u, block++, P.seed_lo, P.seed_hi);
+            a = u11(e.x); b = u11(e.y);
+            if (!(a * a + b * b + 0.0f * 0.0f < 1.0f)) { a = u11(e.z); b = u11(e.w); }
+        }
+        origin = C.position + a * C.du + b * C.dv;
+    }   // else: position + a*0 + b*0 == position bit for bit for every finite (a, b); the stream is counter-based, so
+        // not drawing the lens sample shifts nothing else
     *o_out = origin;
     *dir_out = C.upper_left + (u * C.horizontal) - (v * C.vertical) - origin;
 }

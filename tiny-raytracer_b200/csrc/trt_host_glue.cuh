@@ -1,6 +1,7 @@
 // trt_host_glue.cuh — host-side conversion of the C-ABI structs into the kernels' argument structs (shared by the
 // megakernel and wavefront translation units).
 #pragma once
+#include <cmath>
 #include "trt_device.cuh"
 #include "trt_kernels.h"
 
@@ -26,6 +27,12 @@ inline DevCamera dev_camera(const trt_camera& c) {
     d.du = mk(c.defocus_disk_u[0], c.defocus_disk_u[1], c.defocus_disk_u[2]);
     d.dv = mk(c.defocus_disk_v[0], c.defocus_disk_v[1], c.defocus_disk_v[2]);
     d.width = c.width; d.height = c.height;
+    bool pin = true;
+    for (int i = 0; i < 3; ++i) {
+        if (c.defocus_disk_u[i] != 0.0f || c.defocus_disk_v[i] != 0.0f) pin = false;
+        if (c.position[i] == 0.0f && std::signbit(c.position[i])) pin = false;     // -0 + (+0) = +0 but -0 + (-0) = -0
+    }
+    d.pinhole = pin ? 1u : 0u;
     return d;
 }
 inline DevParams dev_params(const trt_params& p) {
