@@ -496,6 +496,37 @@ def test_flat_list_mask_boundaries(trt, orc, ctx, n):
     assert trt.Scene.from_desc(trt.scenes.random_mixed(65, 1), trt.BVH_AUTO).bvh_info()["nodes"] == 64
 
 
+@pytest.mark.parametrize("log2_scale", [-20, 0, 20, 28, 40])
+@pytest.mark.parametrize("scene", ["cornell_spheres", "mixed40"])
+def test_flat_list_conservative_box_phase_extremes(trt, orc, ctx, scene, log2_scale):
+    """Phase A of TRT_BVH_FLAT is a conservative box test (centre/half-width, FMA) that is only taken while nothing can
+    overflow: |coordinate| <= 2^30, |origin| < 2^30, |1/d| < 2^64; everything else replays the reference scan. Scenes
+    scaled by powers of two (exact) across those limits, with rays whose 1/d is huge, must stay bit-exact."""
+    S = trt.scenes
+    base = S.cornell_spheres() if scene == "cornell_spheres" else S.random_mixed(40, 9)
+    f = np.float32(2.0 ** log2_scale)
+    desc = S.SceneDesc(base.name, base.materials, base.prim_type, (base.prim_data * f).astype(np.float32), base.prim_mat,
+                       dict(base.camera), base.spp, base.max_bounces, base.background, base.seed)
+    osc = orc.Scene.from_desc(desc)
+    rng = np.random.default_rng(107 + log2_scale)
+    n = 60_000
+    lo = base.prim_data[:, :3].min(0) - 3; hi = base.prim_data[:, :3].max(0) + 3
+    o = (rng.uniform(lo, hi, (n, 3)).astype(np.float32) * f).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    d[:3000, 0] = np.float32(1e-22); d[3000:6000, 1] = np.float32(-3e-30); d[6000:7000, 2] = np.float32(1e-40)   # |1/d| up to inf
+    d[7000:8000, 0] = 0.0
+    o[8000:9000] = np.float32(3e9)                                                                            # |o| > 2^30
+    o[9000:12000] = np.round(o[9000:12000] / f) * f                                                           # origins on planes
+    t_min = np.float32(0.001) * f
+    oprim, ot = osc.trace_rays(o, d, float(t_min), use_bvh=True)
+    for kind in (trt.BVH_FLAT, trt.BVH_REFERENCE):
+        prim, t = trt.Scene.from_desc(desc, kind).trace_rays(ctx, o, d, float(t_min))
+        assert np.array_equal(prim, oprim), "kind %d: %d prim mismatches" % (kind, int((prim != oprim).sum()))
+        assert np.array_equal(bits(t), bits(ot))
+    assert (oprim != 0xFFFFFFFF).sum() > n // 50
+
+
 @pytest.mark.parametrize("kind", [0, 1, 3])
 def test_cuda_matches_committed_golden_fixtures(trt, ctx, kind):
     """The CUDA path against tests/golden/golden_small.npz (oracle outputs committed with their generator): no oracle run
