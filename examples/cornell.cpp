@@ -26,7 +26,7 @@ int main(int argc, char** argv) {
         trt::Camera camera(140.0f, 0.6f, {50, 50, -140}, {50, 50, 0}, {0, 1, 0}, 40.0f, 300, 300);   // main.rs:8-16
         trt::Renderer instance(300, 8, 20, true, trt::Vec3::new_diagonal(0.001f));                   // main.rs:17
         trt::Image image = instance.render(camera, world);
-        image.save_ppm(argc > 1 ? argv[1] : "output.ppm");
+        image.save(argc > 1 ? argv[1] : "output.png");                                                  // main.rs:19-20
         std::printf("%llu paths, %llu rays, %.2f ms on the device (%.1f Mrays/s)\n", (unsigned long long)instance.last_stats.paths,
                     (unsigned long long)instance.last_stats.rays, instance.last_stats.device_ms,
                     instance.last_stats.rays / (instance.last_stats.device_ms * 1e3));

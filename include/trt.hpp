@@ -16,6 +16,7 @@
 // Errors: the reference panics (`.expect`, world.rs:29-31); this mirror throws trt::Error carrying the C ABI's status and
 // message, so nothing unwinds across the C boundary.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -103,6 +104,51 @@ struct Image {                                                  // utils/image.r
         if (!f) throw Error(TRT_ERR_INVALID, "cannot open " + filename);
         std::fprintf(f, "P6\n%u %u\n255\n", width, height);
         std::fwrite(rgb8.data(), 1, rgb8.size(), f); std::fclose(f);
+    }
+    // Image::save, utils/image.rs:66-90 (the reference writes an 8-bit RGB PNG through the `image` crate). Self-contained:
+    // one IDAT of stored (uncompressed) deflate blocks, so no zlib is needed; any PNG reader decodes it.
+    void save(const std::string& filename) const {
+        std::vector<uint8_t> raw;                               // filter byte 0 + one RGB scanline, per row
+        raw.reserve((size_t)height * (3 * (size_t)width + 1));
+        for (uint32_t y = 0; y < height; ++y) {
+            raw.push_back(0);
+            raw.insert(raw.end(), rgb8.begin() + 3 * (size_t)width * y, rgb8.begin() + 3 * (size_t)width * (y + 1));
+        }
+        std::vector<uint8_t> z = {0x78, 0x01};
+        uint32_t a = 1, b = 0;                                  // adler32 of raw
+        for (uint8_t v : raw) { a = (a + v) % 65521u; b = (b + a) % 65521u; }
+        for (size_t off = 0; off < raw.size() || off == 0; off += 65535) {
+            size_t n = raw.size() - off < 65535 ? raw.size() - off : 65535;
+            z.push_back(off + n >= raw.size() ? 1 : 0);
+            z.push_back(n & 255); z.push_back(n >> 8); z.push_back(~n & 255); z.push_back((~n >> 8) & 255);
+            z.insert(z.end(), raw.begin() + off, raw.begin() + off + n);
+            if (raw.empty()) break;
+        }
+        uint32_t adler = (b << 16) | a;
+        for (int i = 3; i >= 0; --i) z.push_back((adler >> (8 * i)) & 255);
+        FILE* f = std::fopen(filename.c_str(), "wb");
+        if (!f) throw Error(TRT_ERR_INVALID, "cannot open " + filename);
+        auto be32 = [](uint32_t v, uint8_t* o) { o[0] = v >> 24; o[1] = v >> 16; o[2] = v >> 8; o[3] = v; };
+        auto chunk = [&](const char tag[5], const std::vector<uint8_t>& data) {
+            std::vector<uint8_t> c(8 + data.size() + 4);
+            be32((uint32_t)data.size(), c.data());
+            for (int i = 0; i < 4; ++i) c[4 + i] = (uint8_t)tag[i];
+            std::copy(data.begin(), data.end(), c.begin() + 8);
+            uint32_t crc = 0xFFFFFFFFu;                          // crc32 over tag + data
+            for (size_t i = 4; i < 8 + data.size(); ++i) {
+                crc ^= c[i];
+                for (int k = 0; k < 8; ++k) crc = (crc >> 1) ^ (0xEDB88320u & (0u - (crc & 1u)));
+            }
+            be32(~crc, c.data() + 8 + data.size());
+            std::fwrite(c.data(), 1, c.size(), f);
+        };
+        const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+        std::fwrite(sig, 1, 8, f);
+        std::vector<uint8_t> ihdr(13);
+        be32(width, ihdr.data()); be32(height, ihdr.data() + 4);
+        ihdr[8] = 8; ihdr[9] = 2; ihdr[10] = 0; ihdr[11] = 0; ihdr[12] = 0;
+        chunk("IHDR", ihdr); chunk("IDAT", z); chunk("IEND", {});
+        std::fclose(f);
     }
 };
 

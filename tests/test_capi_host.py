@@ -130,5 +130,31 @@ def test_cpp_mirror_compiles_and_fails_loudly_without_gpu(trt, tmp_path):
                            os.path.join(ROOT, "examples", "cornell.cpp"), "-o", exe, "-L" + pkg, "-ltrt_b200", "-Wl,-rpath," + pkg])
     import torch
     if not torch.cuda.is_available():
-        r = subprocess.run([exe, str(tmp_path / "o.ppm")], capture_output=True, text=True)
+        r = subprocess.run([exe, str(tmp_path / "o.png")], capture_output=True, text=True)
         assert r.returncode == 1 and "no CPU path" in r.stderr
+
+
+def test_cpp_image_save_writes_a_valid_png(tmp_path):
+    """trt::Image::save (utils/image.rs:66-90 writes a PNG): signature, chunk CRCs, zlib stream and pixels round-trip."""
+    import struct, zlib
+    src = tmp_path / "png.cpp"
+    src.write_text('#include "trt.hpp"\nint main(int, char** v) { trt::Image im; im.width = 301; im.height = 219;\n'
+                   '  im.rgb8.resize(301 * 219 * 3); for (size_t i = 0; i < im.rgb8.size(); ++i) im.rgb8[i] = (uint8_t)((i * 7) ^ (i >> 8));\n'
+                   '  im.save(v[1]); return 0; }\n')
+    exe, out, pkg = str(tmp_path / "png"), str(tmp_path / "o.png"), os.path.join(ROOT, "tiny-raytracer_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe,
+                           "-L" + pkg, "-ltrt_b200", "-Wl,-rpath," + pkg])
+    subprocess.check_call([exe, out])
+    b = open(out, "rb").read()
+    assert b[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, size = 8, b"", None
+    while pos < len(b):
+        n, = struct.unpack(">I", b[pos:pos + 4]); tag = b[pos + 4:pos + 8]; data = b[pos + 8:pos + 8 + n]
+        assert zlib.crc32(tag + data) == struct.unpack(">I", b[pos + 8 + n:pos + 12 + n])[0]
+        if tag == b"IHDR": size = struct.unpack(">IIBBBBB", data)
+        if tag == b"IDAT": idat += data
+        pos += 12 + n
+    assert size == (301, 219, 8, 2, 0, 0, 0)
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(219, 1 + 3 * 301)
+    i = np.arange(301 * 219 * 3)
+    assert (rows[:, 0] == 0).all() and np.array_equal(rows[:, 1:].reshape(-1), ((i * 7) ^ (i >> 8)).astype(np.uint8))
