@@ -147,6 +147,16 @@ template <bool SMEM> TRT_DEV uint4 ld4u(const uint4* p) {
 
 struct EventCounters { uint32_t node_visits, sphere_tests, quad_tests; };
 
+// ------------------------------------------------------------------ packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2)
+// Each half is an ordinary IEEE round-to-nearest operation (denormals kept), so a packed add or mul gives exactly the bits
+// of the two scalar instructions it replaces; only the issue slot is shared.
+typedef unsigned long long f32x2;
+TRT_DEV f32x2 pk2(float lo, float hi) { f32x2 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d; }
+TRT_DEV void upk2(f32x2 v, float* lo, float* hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(*lo), "=f"(*hi) : "l"(v)); }
+TRT_DEV f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+TRT_DEV f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+TRT_DEV f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 // ------------------------------------------------------------------ AABB slab test, hittable/aabb.rs:36-61
 // Returns entry (`start`) and exit (`end`) of the range [t_min, +inf) clipped by the three slabs, updated with the
 // reference's exact compare/select sequence (NaN from 0*inf leaves the range untouched; swap only when t1 < t0).
@@ -192,6 +202,20 @@ TRT_DEV bool ray_is_tame(V3 o, V3 inv) {
     float si = (fabsf(inv.x) + fabsf(inv.y)) + fabsf(inv.z), so = (fabsf(o.x) + fabsf(o.y)) + fabsf(o.z);
     float mi = fminf(fminf(fabsf(inv.x), fabsf(inv.y)), fabsf(inv.z));
     return si < TRT_INF && so < TRT_INF && mi > 0.0f;
+}
+// Both children of one node at once (the node stores (left, right) pairs per coordinate, trt_layout.h): the reference's
+// `(b - o) * inv` for the two boxes in one FADD2 + one FMUL2 per plane, then slab_tame's min/max per child. Bit-identical.
+TRT_DEV void slab2_tame(float4 n0, float4 n1, float4 n2, V3 o, V3 inv, float t_min, float* sl, float* el, float* sr, float* er) {
+    const f32x2 ox = pk2(o.x, o.x), oy = pk2(o.y, o.y), oz = pk2(o.z, o.z);
+    const f32x2 ix = pk2(inv.x, inv.x), iy = pk2(inv.y, inv.y), iz = pk2(inv.z, inv.z);
+    float axl, axr, bxl, bxr, ayl, ayr, byl, byr, azl, azr, bzl, bzr;
+    upk2(mul2(sub2(pk2(n0.x, n0.y), ox), ix), &axl, &axr); upk2(mul2(sub2(pk2(n1.z, n1.w), ox), ix), &bxl, &bxr);
+    upk2(mul2(sub2(pk2(n0.z, n0.w), oy), iy), &ayl, &ayr); upk2(mul2(sub2(pk2(n2.x, n2.y), oy), iy), &byl, &byr);
+    upk2(mul2(sub2(pk2(n1.x, n1.y), oz), iz), &azl, &azr); upk2(mul2(sub2(pk2(n2.z, n2.w), oz), iz), &bzl, &bzr);
+    *sl = fmaxf(fmaxf(t_min, fminf(axl, bxl)), fmaxf(fminf(ayl, byl), fminf(azl, bzl)));
+    *el = fminf(fminf(fmaxf(axl, bxl), fmaxf(ayl, byl)), fmaxf(azl, bzl));
+    *sr = fmaxf(fmaxf(t_min, fminf(axr, bxr)), fmaxf(fminf(ayr, byr), fminf(azr, bzr)));
+    *er = fminf(fminf(fmaxf(axr, bxr), fmaxf(ayr, byr)), fmaxf(azr, bzr));
 }
 TRT_DEV float rcp_approx(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
@@ -284,11 +308,10 @@ TRT_DEV void trav_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* s
         uint32_t lref = __float_as_uint(n3.x), rref = __float_as_uint(n3.y);
         float sl, el, sr, er;
         if (T.tame) {
-            slab_tame(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, &sl, &el);
-            slab_tame(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, &sr, &er);
+            slab2_tame(n0, n1, n2, o, inv, t_min, &sl, &el, &sr, &er);
         } else {
-            slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, &sl, &el);
-            slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, &sr, &er);
+            slab(n0.x, n0.z, n1.x, n1.z, n2.x, n2.z, o, inv, t_min, &sl, &el);
+            slab(n0.y, n0.w, n1.y, n1.w, n2.y, n2.w, o, inv, t_min, &sr, &er);
         }
         if (COUNT) ec->node_visits += (rref == TRT_REF_INVALID) ? 0u : 2u;   // left.hit + right.hit
         bool pl, pr;
@@ -471,10 +494,6 @@ struct FlatPrim { float4 g0, g1, g2, g3, b0, b1; };   // geometry as in trt_layo
 // padded with NaN (never accepted) to TRT_FLAT_MAX primitives.
 #define TRT_FLAT_CBOX_F4 (3 * TRT_FLAT_MAX / 2)
 #define TRT_FLAT_EPS 1.1920929e-6f      /* 2.5 * 2^-21 */
-typedef unsigned long long f32x2;
-TRT_DEV f32x2 pk2(float lo, float hi) { f32x2 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d; }
-TRT_DEV void upk2(f32x2 v, float* lo, float* hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(*lo), "=f"(*hi) : "l"(v)); }
-TRT_DEV f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 TRT_DEV bool ray_is_flat_fast(V3 o, V3 inv) {
     float si = (fabsf(inv.x) + fabsf(inv.y)) + fabsf(inv.z), so = (fabsf(o.x) + fabsf(o.y)) + fabsf(o.z);   // NaN/inf fail both
     float mi = fminf(fminf(fabsf(inv.x), fabsf(inv.y)), fabsf(inv.z));

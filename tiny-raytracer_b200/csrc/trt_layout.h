@@ -4,9 +4,9 @@
 // node costs four 128-bit loads from one 64-byte-aligned segment (half a 128-byte line):
 //
 //   node n (float4 nodes[4n .. 4n+3]):
-//     [0] = ( lmin.x, lmin.y, lmin.z, lmax.x )      left child's padded AABB  (hittable/aabb.rs:5-10 is 24 B {min,max})
-//     [1] = ( lmax.y, lmax.z, rmin.x, rmin.y )
-//     [2] = ( rmin.z, rmax.x, rmax.y, rmax.z )      right child's padded AABB
+//     [0] = ( lmin.x, rmin.x, lmin.y, rmin.y )      the two children's padded AABBs (hittable/aabb.rs:5-10 is 24 B {min,max}),
+//     [1] = ( lmin.z, rmin.z, lmax.x, rmax.x )      interleaved as (left, right) pairs per coordinate: each 64-bit half of a
+//     [2] = ( lmax.y, rmax.y, lmax.z, rmax.z )      load is one operand of a packed FADD2/FMUL2 (both slab tests at once)
 //     [3] = ( left_ref, right_ref, 0, 0 ) as bits
 //   child ref: bit31 = leaf, bit30 = primitive type (0 sphere, 1 quad), bits0..29 = index into that type's array;
 //              otherwise the index of an interior node; TRT_REF_INVALID = absent child (single-primitive scene).

@@ -152,9 +152,9 @@ __global__ void k_lbvh_emit(const float4* __restrict__ boxes, const uint32_t* __
         } else { mn[c] = node_min[ch[c]]; mx[c] = node_max[ch[c]]; ref[c] = ch[c]; }
     }
     float4* rec = nodes + 4 * (size_t)i;
-    rec[0] = make_float4(mn[0].x, mn[0].y, mn[0].z, mx[0].x);
-    rec[1] = make_float4(mx[0].y, mx[0].z, mn[1].x, mn[1].y);
-    rec[2] = make_float4(mn[1].z, mx[1].x, mx[1].y, mx[1].z);
+    rec[0] = make_float4(mn[0].x, mn[1].x, mn[0].y, mn[1].y);       // (left, right) pairs per coordinate, trt_layout.h
+    rec[1] = make_float4(mn[0].z, mn[1].z, mx[0].x, mx[1].x);
+    rec[2] = make_float4(mx[0].y, mx[1].y, mx[0].z, mx[1].z);
     rec[3] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), 0.f, 0.f);
 }
 

@@ -235,9 +235,9 @@ static void flatten(const std::vector<TNode>& t, const std::vector<HostPrim>& pr
         float lmn[3] = {inf, inf, inf}, lmx[3] = {-inf, -inf, -inf}, rmn[3] = {inf, inf, inf}, rmx[3] = {-inf, -inf, -inf};
         if (l) for (int i = 0; i < 3; ++i) { lmn[i] = l->bmin[i]; lmx[i] = l->bmax[i]; }
         if (r) for (int i = 0; i < 3; ++i) { rmn[i] = r->bmin[i]; rmx[i] = r->bmax[i]; }
-        rec[0] = {lmn[0], lmn[1], lmn[2], lmx[0]};
-        rec[1] = {lmx[1], lmx[2], rmn[0], rmn[1]};
-        rec[2] = {rmn[2], rmx[0], rmx[1], rmx[2]};
+        rec[0] = {lmn[0], rmn[0], lmn[1], rmn[1]};       // (left, right) pairs per coordinate, trt_layout.h
+        rec[1] = {lmn[2], rmn[2], lmx[0], rmx[0]};
+        rec[2] = {lmx[1], rmx[1], lmx[2], rmx[2]};
     };
     if (n_leaves == 1) {   // a lone primitive: pseudo-node whose right child is absent
         out.nodes.resize(4);
