@@ -129,6 +129,10 @@ struct DevParams {
     float bg[3]; uint32_t seed_lo, seed_hi; float t_min;
 };
 
+// The per-hit records (meta, materials, quad normals) are read once per ray segment, through GENERIC loads: they sit in
+// shared memory when they are small and stay in global memory (L1/L2) when staging them would cost occupancy.
+TRT_DEV float4 ld4a(const float4* p) { return *p; }
+TRT_DEV uint4 ld4ua(const uint4* p) { return *p; }
 // SMEM = scene staged in shared memory (small scenes): ld.shared.v4; otherwise read-only global path.
 template <bool SMEM> TRT_DEV float4 ld4(const float4* p) {
     if (SMEM) {
@@ -339,9 +343,9 @@ TRT_DEV void trav_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* s
             else if (t < T.best.t) { T.best.t = t; T.best.ref = cur; T.best_rank = 0xFFFFFFFFu; }
             else if (t == T.best.t) {
                 if (T.best_rank == 0xFFFFFFFFu)
-                    T.best_rank = (T.best.ref & TRT_REF_QUAD) ? ld4u<SMEM>(S.quad_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y
-                                                              : ld4u<SMEM>(S.sphere_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y;
-                uint32_t rk = (cur & TRT_REF_QUAD) ? ld4u<SMEM>(S.quad_meta + idx).y : ld4u<SMEM>(S.sphere_meta + idx).y;
+                    T.best_rank = (T.best.ref & TRT_REF_QUAD) ? ld4ua(S.quad_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y
+                                                              : ld4ua(S.sphere_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y;
+                uint32_t rk = (cur & TRT_REF_QUAD) ? ld4ua(S.quad_meta + idx).y : ld4ua(S.sphere_meta + idx).y;
                 if (rk < T.best_rank) { T.best.ref = cur; T.best_rank = rk; }
             }
         }
@@ -406,21 +410,21 @@ TRT_DEV Surface hit_record(const DevScene& S, Hit h, V3 o, V3 d) {
     if (h.ref & TRT_REF_QUAD) {
         float4 q0 = ld4<SMEM>(S.quads + 4 * (size_t)idx);
         outward = mk(q0.x, q0.y, q0.z);                                       // quad.rs:45: the unnormalised n
-        mat = ld4u<SMEM>(S.quad_meta + idx).x;
+        mat = ld4ua(S.quad_meta + idx).x;
     } else {
         float4 s = ld4<SMEM>(S.spheres + idx);
         outward = sf.point - mk(s.x, s.y, s.z);                               // sphere.rs:46-50
-        mat = ld4u<SMEM>(S.sphere_meta + idx).x;
+        mat = ld4ua(S.sphere_meta + idx).x;
     }
     sf.front = dot(d, outward) < 0.0f;
     V3 nn;
-    if (h.ref & TRT_REF_QUAD) { float4 q = ld4<SMEM>(S.quad_nn + idx); nn = mk(q.x, q.y, q.z); }   // n / |n| never changes: host-side, same ops
+    if (h.ref & TRT_REF_QUAD) { float4 q = ld4a(S.quad_nn + idx); nn = mk(q.x, q.y, q.z); }   // n / |n| never changes: host-side, same ops
     else nn = normalized(outward);
     sf.normal = sf.front ? nn : -nn;
-    float4 m0 = ld4<SMEM>(S.materials + 2 * (size_t)mat);
+    float4 m0 = ld4a(S.materials + 2 * (size_t)mat);
     sf.kind = __float_as_uint(m0.w);
     sf.rgb = mk(m0.x, m0.y, m0.z);
-    sf.param = (sf.kind == TRT_MAT_METAL || sf.kind == TRT_MAT_DIELECTRIC) ? ld4<SMEM>(S.materials + 2 * (size_t)mat + 1).x : 0.0f;
+    sf.param = (sf.kind == TRT_MAT_METAL || sf.kind == TRT_MAT_DIELECTRIC) ? ld4a(S.materials + 2 * (size_t)mat + 1).x : 0.0f;
     return sf;
 }
 // Un-normalised scattered direction for the three scattering materials; `r` is Philox block 0 of (pixel, sample, k).

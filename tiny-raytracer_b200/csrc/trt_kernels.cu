@@ -29,6 +29,11 @@ using namespace trtd;
 #define MEGA_THREADS TRT_MEGA_THREADS
 
 // ------------------------------------------------------------------ shared-memory staging of small scenes
+// The traversal data (nodes, primitives, flat list) are staged whenever they fit; the per-hit records (meta, materials,
+// quad normals: one access per ray segment) only while they are small — the final scene has one material per sphere, and
+// staging its 31 KB of per-hit records would cap the kernel at 3 CTAs per SM instead of 4.
+#define TRT_AUX_SMEM_F4 512u       /* 8 KB */
+__host__ __device__ inline uint32_t aux_f4(uint32_t n_spheres, uint32_t n_quads, uint32_t n_materials) { return n_spheres + 2u * n_quads + 2u * n_materials; }
 // layout: [nodes | spheres | quads | sphere_meta | quad_meta | materials | flat list | per-thread phase-A columns]
 template <bool SMEM>
 __device__ __forceinline__ DevScene stage_scene(const DevScene& G, float** tt_out) {
@@ -46,10 +51,12 @@ __device__ __forceinline__ DevScene stage_scene(const DevScene& G, float** tt_ou
     S.nodes = copy(G.nodes, 4 * G.n_nodes);
     S.spheres = copy(G.spheres, G.n_spheres);
     S.quads = copy(G.quads, 4 * G.n_quads);
-    S.sphere_meta = (const uint4*)copy((const float4*)G.sphere_meta, G.n_spheres);
-    S.quad_meta = (const uint4*)copy((const float4*)G.quad_meta, G.n_quads);
-    S.quad_nn = copy(G.quad_nn, G.n_quads);
-    S.materials = copy(G.materials, 2 * G.n_materials);
+    if (aux_f4(G.n_spheres, G.n_quads, G.n_materials) <= TRT_AUX_SMEM_F4) {   // else: left in global memory (generic loads)
+        S.sphere_meta = (const uint4*)copy((const float4*)G.sphere_meta, G.n_spheres);
+        S.quad_meta = (const uint4*)copy((const float4*)G.quad_meta, G.n_quads);
+        S.quad_nn = copy(G.quad_nn, G.n_quads);
+        S.materials = copy(G.materials, 2 * G.n_materials);
+    }
     S.flat = (const FlatPrim*)copy((const float4*)G.flat, 6 * G.n_flat);
     *tt_out = (float*)(smem_f4 + off) + threadIdx.x;     // column of this thread, stride blockDim.x
     __syncthreads();
@@ -387,8 +394,9 @@ __global__ void k_debug_philox(size_t n, const uint32_t* ctr, uint32_t k0, uint3
 namespace trtk {
 
 size_t scene_smem_bytes(const SceneView& v) {
-    size_t b = 16ull * (4ull * v.n_nodes + v.n_spheres + 4ull * v.n_quads + v.n_spheres + 2ull * v.n_quads + 2ull * v.n_materials + 6ull * v.n_flat);
-    return b;
+    size_t aux = aux_f4(v.n_spheres, v.n_quads, v.n_materials);
+    if (aux > TRT_AUX_SMEM_F4) aux = 0;
+    return 16ull * (4ull * v.n_nodes + v.n_spheres + 4ull * v.n_quads + 6ull * v.n_flat + aux);
 }
 
 template <int KIND, bool SMEM, bool COUNT>
