@@ -12,6 +12,7 @@ BVH_REFERENCE, BVH_SAH, BVH_FLAT, BVH_AUTO, BVH_LBVH_DEVICE = 0, 1, 2, 3, 4
 VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT = 0, 1
 FLAG_COUNT_EVENTS = 1
 FLAG_NO_TAIL_SPLIT = 2
+FLAG_BINARY_NODES = 4
 
 
 class TrtError(RuntimeError):

@@ -118,6 +118,7 @@ struct DevScene {
     const uint4* sphere_meta; const uint4* quad_meta; const float4* materials;
     const float4* quad_nn;                      // unit normal of every quad, precomputed on the host with HitRecord::new's operations
     const FlatPrim* flat; uint32_t n_flat;      // TRT_BVH_FLAT: primitives in reference leaf order (else null / 0)
+    const float4* nodes4; uint32_t n_nodes4;    // TRT_BVH_SAH: 4-wide nodes (8 float4 each, trt_scene.cpp collapse4) or null
     const float4* flat_cbox; float flat_bound;  // TRT_BVH_FLAT: conservative centre/half-width boxes (phase A), largest |coordinate|
     uint32_t root, n_nodes, n_spheres, n_quads, n_materials, ordered;
     float root_min[3], root_max[3];   // the root's own padded box (only consulted when counting events)
@@ -369,6 +370,79 @@ TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounter
     return T.best;
 }
 
+// ------------------------------------------------------------------ the ordered traversal on 4-wide nodes
+// Same rules as trav_step<ORDERED = true>: a child is entered when its box is crossed and its entry is not beyond the
+// closest hit, a primitive wins with a smaller t or an equal t and a smaller reference leaf rank, so the result does not
+// depend on the visiting order — only the number of dependent node fetches per ray does (about half of the binary walk).
+// The (up to) four crossed children are sorted by entry distance; the nearest is entered, the others are pushed farthest first.
+template <bool SMEM>
+TRT_DEV void trav4_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* stack_t) {
+    uint32_t cur = T.cur;
+    const V3 o = T.o, d = T.d, inv = T.inv; const float t_min = T.t_min;
+    if (!(cur & TRT_REF_LEAF)) {
+        const float4* np = S.nodes4 + 8 * (size_t)cur;
+        const float4 a0 = ld4<SMEM>(np), a1 = ld4<SMEM>(np + 1), a2 = ld4<SMEM>(np + 2);
+        const float4 b0 = ld4<SMEM>(np + 3), b1 = ld4<SMEM>(np + 4), b2 = ld4<SMEM>(np + 5), rf = ld4<SMEM>(np + 6);
+        float s0, e0, s1, e1, s2, e2, s3, e3;
+        if (T.tame) {
+            slab2_tame(a0, a1, a2, o, inv, t_min, &s0, &e0, &s1, &e1);
+            slab2_tame(b0, b1, b2, o, inv, t_min, &s2, &e2, &s3, &e3);
+        } else {
+            slab(a0.x, a0.z, a1.x, a1.z, a2.x, a2.z, o, inv, t_min, &s0, &e0);
+            slab(a0.y, a0.w, a1.y, a1.w, a2.y, a2.w, o, inv, t_min, &s1, &e1);
+            slab(b0.x, b0.z, b1.x, b1.z, b2.x, b2.z, o, inv, t_min, &s2, &e2);
+            slab(b0.y, b0.w, b1.y, b1.w, b2.y, b2.w, o, inv, t_min, &s3, &e3);
+        }
+        uint32_t r0 = __float_as_uint(rf.x), r1 = __float_as_uint(rf.y), r2 = __float_as_uint(rf.z), r3 = __float_as_uint(rf.w);
+        const float best = T.best.t;
+        // a child that is not entered sorts last (key +inf) and carries TRT_REF_INVALID
+        if (!(e0 > s0 && !(best < s0) && r0 != TRT_REF_INVALID)) { s0 = TRT_INF; r0 = TRT_REF_INVALID; }
+        if (!(e1 > s1 && !(best < s1) && r1 != TRT_REF_INVALID)) { s1 = TRT_INF; r1 = TRT_REF_INVALID; }
+        if (!(e2 > s2 && !(best < s2) && r2 != TRT_REF_INVALID)) { s2 = TRT_INF; r2 = TRT_REF_INVALID; }
+        if (!(e3 > s3 && !(best < s3) && r3 != TRT_REF_INVALID)) { s3 = TRT_INF; r3 = TRT_REF_INVALID; }
+#define TRT_CSWAP(sa, ra, sb, rb) { const bool w_ = sb < sa; const float ts_ = w_ ? sb : sa, tb_ = w_ ? sa : sb; \
+                                    const uint32_t tr_ = w_ ? rb : ra, tq_ = w_ ? ra : rb; sa = ts_; sb = tb_; ra = tr_; rb = tq_; }
+        TRT_CSWAP(s0, r0, s1, r1) TRT_CSWAP(s2, r2, s3, r3) TRT_CSWAP(s0, r0, s2, r2) TRT_CSWAP(s1, r1, s3, r3) TRT_CSWAP(s1, r1, s2, r2)
+#undef TRT_CSWAP
+        // an entered child with an infinite entry (s = +inf is possible only for a degenerate ray) must not be lost: the
+        // ref, not the key, says whether a slot is occupied
+        if (r3 != TRT_REF_INVALID) { stack_ref[T.sp] = r3; stack_t[T.sp] = s3; ++T.sp; }
+        if (r2 != TRT_REF_INVALID) { stack_ref[T.sp] = r2; stack_t[T.sp] = s2; ++T.sp; }
+        if (r1 != TRT_REF_INVALID) { stack_ref[T.sp] = r1; stack_t[T.sp] = s1; ++T.sp; }
+        cur = r0;
+    }
+    if (cur != TRT_REF_INVALID && (cur & TRT_REF_LEAF)) {
+        uint32_t idx = cur & TRT_REF_INDEX_MASK;
+        float t; bool h;
+        if (cur & TRT_REF_QUAD) h = quad_hit<SMEM>(S, idx, o, d, t_min, TRT_INF, T.best.t, &t);
+        else h = sphere_hit<SMEM>(S, idx, o, d, t_min, TRT_INF, &t);
+        if (h) {
+            if (t < T.best.t) { T.best.t = t; T.best.ref = cur; T.best_rank = 0xFFFFFFFFu; }
+            else if (t == T.best.t) {
+                if (T.best_rank == 0xFFFFFFFFu)
+                    T.best_rank = (T.best.ref & TRT_REF_QUAD) ? ld4ua(S.quad_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y
+                                                              : ld4ua(S.sphere_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y;
+                uint32_t rk = (cur & TRT_REF_QUAD) ? ld4ua(S.quad_meta + idx).y : ld4ua(S.sphere_meta + idx).y;
+                if (rk < T.best_rank) { T.best.ref = cur; T.best_rank = rk; }
+            }
+        }
+        cur = TRT_REF_INVALID;
+    }
+    while (cur == TRT_REF_INVALID && T.sp > 0) {
+        --T.sp;
+        if (!(T.best.t < stack_t[T.sp])) cur = stack_ref[T.sp];
+    }
+    T.cur = cur;
+}
+template <bool SMEM>
+TRT_DEV Hit closest_hit4(const DevScene& S, V3 o, V3 d, float t_min) {
+    Trav T; EventCounters ec;
+    trav_begin<false>(T, S, o, d, t_min, &ec);
+    uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
+    while (T.cur != TRT_REF_INVALID) trav4_step<SMEM>(T, S, stack_ref, stack_t);
+    return T.best;
+}
+
 // ------------------------------------------------------------------ camera: pointgen.rs:41-43 + camera.rs:58-66 + vec3extend.rs:45-53
 // `r` is Philox block 0 of the stream (pixel, sample, bounce 0): (xi1, xi2, a, b); further blocks feed the lens rejection loop.
 // Returns the UN-normalised direction; Ray::new's normalisation (ray.rs:12-14) is applied by the caller.
@@ -614,10 +688,11 @@ TRT_DEV Hit closest_hit_flat(const float4* __restrict__ CB, float bound, const F
 }
 
 // One whole path: CpuSampler::single_point_sampling, renderer/sampler/cpu.rs:39-65
-// KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH, 2 = TRT_BVH_FLAT
+// KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH (binary nodes), 2 = TRT_BVH_FLAT, 3 = TRT_BVH_SAH on its 4-wide nodes
 template <int KIND, bool SMEM, bool COUNT>
 TRT_DEV Hit closest_hit_any(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
     if (KIND == 2) return closest_hit_flat<false>(S.flat_cbox, S.flat_bound, S.flat, S.n_flat, o, d, t_min);
+    if (KIND == 3) return closest_hit4<SMEM>(S, o, d, t_min);
     return closest_hit<KIND == 1, SMEM, COUNT>(S, o, d, t_min, ec);
 }
 

@@ -35,7 +35,7 @@ using namespace trtd;
 #define TRT_AUX_SMEM_F4 512u       /* 8 KB */
 __host__ __device__ inline uint32_t aux_f4(uint32_t n_spheres, uint32_t n_quads, uint32_t n_materials) { return n_spheres + 2u * n_quads + 2u * n_materials; }
 // layout: [nodes | spheres | quads | sphere_meta | quad_meta | materials | flat list | per-thread phase-A columns]
-template <bool SMEM>
+template <bool SMEM, int KIND>
 __device__ __forceinline__ DevScene stage_scene(const DevScene& G, float** tt_out) {
     *tt_out = nullptr;
     if (!SMEM) return G;
@@ -48,7 +48,8 @@ __device__ __forceinline__ DevScene stage_scene(const DevScene& G, float** tt_ou
         off += n;
         return dst;
     };
-    S.nodes = copy(G.nodes, 4 * G.n_nodes);
+    if (KIND == 3) S.nodes4 = copy(G.nodes4, 8 * G.n_nodes4);          // the walk reads only one of the two node arrays
+    else S.nodes = copy(G.nodes, 4 * G.n_nodes);
     S.spheres = copy(G.spheres, G.n_spheres);
     S.quads = copy(G.quads, 4 * G.n_quads);
     if (aux_f4(G.n_spheres, G.n_quads, G.n_materials) <= TRT_AUX_SMEM_F4) {   // else: left in global memory (generic loads)
@@ -96,11 +97,12 @@ __device__ __forceinline__ bool decode_item(const MegaArgs& A, uint32_t item, ui
 // Loop body = T (one ray segment for every live lane) then S (shade-or-regenerate, fused so that the scattering lanes
 // and the lanes starting a new path share ONE Philox call, ONE normalisation and the work-fetch point; every lane that
 // still has work leaves S with a live ray, so T always runs with full lanes until the work counter runs dry).
-// KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH, 2 = TRT_BVH_FLAT (U = the phase-A boxes in the constant bank).
+// KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH, 2 = TRT_BVH_FLAT (U = the phase-A boxes in the constant bank),
+// 3 = TRT_BVH_SAH walked on its 4-wide nodes.
 template <int KIND, bool SMEM, bool COUNT>
 __device__ __forceinline__ void mega_body(const MegaArgs& A, const float4* U) {
     float* tt;
-    const DevScene S = stage_scene<SMEM>(A.scene, &tt);
+    const DevScene S = stage_scene<SMEM, KIND>(A.scene, &tt);
     const DevParams& P = A.p;
     const uint32_t lane = threadIdx.x & 31u;
     V3 o = mk(0, 0, 0), d = mk(0, 0, 1), atten = mk(1, 1, 1), color = mk(0, 0, 0);
@@ -115,6 +117,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& A, const float4* U) {
         Hit h; h.t = TRT_INF; h.ref = TRT_REF_INVALID;
         if (alive) {
             if (KIND == 2) h = closest_hit_flat<true>(U, S.flat_bound, S.flat, S.n_flat, o, d, P.t_min);
+            else if (KIND == 3) h = closest_hit4<SMEM>(S, o, d, P.t_min);
             else h = closest_hit<KIND == 1, SMEM, COUNT>(S, o, d, P.t_min, &ec);
             ++n_rays;
         }
@@ -200,7 +203,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& A, const float4* U) {
 template <int KIND, bool SMEM, bool COUNT>
 __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
     float* tt;
-    const DevScene S = stage_scene<SMEM>(A.scene, &tt);
+    const DevScene S = stage_scene<SMEM, KIND>(A.scene, &tt);
     const DevParams& P = A.p;
     const uint32_t lane = threadIdx.x & 31u;
     Trav T; T.cur = TRT_REF_INVALID; T.sp = 0; T.best.t = TRT_INF; T.best.ref = TRT_REF_INVALID;
@@ -216,7 +219,10 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
 
     for (;;) {
         // ---- T: one step of cpu.rs:48 for every lane whose ray is in flight
-        if (T.cur != TRT_REF_INVALID) trav_step<KIND == 1, SMEM, COUNT>(T, S, stack_ref, stack_t, &ec);
+        if (T.cur != TRT_REF_INVALID) {
+            if (KIND == 3) trav4_step<SMEM>(T, S, stack_ref, stack_t);
+            else trav_step<KIND == 1, SMEM, COUNT>(T, S, stack_ref, stack_t, &ec);
+        }
         const bool tracing = T.cur != TRT_REF_INVALID;
         const unsigned tm = __ballot_sync(0xFFFFFFFFu, tracing);
         const unsigned wm = __ballot_sync(0xFFFFFFFFu, !tracing && !done);
@@ -393,10 +399,13 @@ __global__ void k_debug_philox(size_t n, const uint32_t* ctr, uint32_t k0, uint3
 // ------------------------------------------------------------------ launchers
 namespace trtk {
 
-size_t scene_smem_bytes(const SceneView& v) {
+static uint32_t walk_kind(const SceneView& v, bool binary_only) { return (v.kind == 1 && v.nodes4 && v.n_nodes4 && !binary_only) ? 3u : v.kind; }
+// kind: as walked (3 = the 4-wide nodes of a TRT_BVH_SAH scene)
+size_t scene_smem_bytes(const SceneView& v, uint32_t kind) {
     size_t aux = aux_f4(v.n_spheres, v.n_quads, v.n_materials);
     if (aux > TRT_AUX_SMEM_F4) aux = 0;
-    return 16ull * (4ull * v.n_nodes + v.n_spheres + 4ull * v.n_quads + 6ull * v.n_flat + aux);
+    size_t nodes = kind == 3 ? 8ull * v.n_nodes4 : 4ull * v.n_nodes;
+    return 16ull * (nodes + v.n_spheres + 4ull * v.n_quads + 6ull * v.n_flat + aux);
 }
 
 template <int KIND, bool SMEM, bool COUNT>
@@ -421,16 +430,20 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     // measured (B200, regen sweep): Cornell 17 nodes, glass Cornell 33, final scene 486: 32 best; 1 M spheres: 16 best (+25 %)
     if (regen == 0) regen = v.n_nodes <= 4096 ? 32u : 16u;
     A.regen_min = regen > 32u ? 32u : regen;
-    size_t smem = scene_smem_bytes(v);
+    bool count = (p.flags & 1u) != 0;
+    // a TRT_BVH_SAH scene is walked on its 4-wide nodes unless events are counted (the counts are defined on binary nodes)
+    const uint32_t kind = walk_kind(v, count || (p.flags & TRT_FLAG_BINARY_NODES));
+    size_t smem = scene_smem_bytes(v, kind);
     bool use_smem = smem <= 64 * 1024;
     if (v.kind == 2 && (!use_smem || v.n_flat > TRT_FLAT_MAX || !v.flat_cbox_host)) return cudaErrorInvalidValue;
     if (!use_smem) smem = 0;
-    bool count = (p.flags & 1u) != 0;
     const void* fn = nullptr; int blocks_per_sm = 0; cudaError_t e;
     if (v.kind == 2) {
         if (smem > 48 * 1024) { e = cudaFuncSetAttribute(k_render_mega_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
         fn = (const void*)k_render_mega_flat;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_render_mega_flat, MEGA_THREADS, smem);
+    } else if (kind == 3) {
+        e = use_smem ? mega_fn<3, true, false>(&fn, &blocks_per_sm, smem) : mega_fn<3, false, false>(&fn, &blocks_per_sm, smem);
     } else if (v.kind == 1) {
         if (use_smem) e = count ? mega_fn<1, true, true>(&fn, &blocks_per_sm, smem) : mega_fn<1, true, false>(&fn, &blocks_per_sm, smem);
         else e = count ? mega_fn<1, false, true>(&fn, &blocks_per_sm, smem) : mega_fn<1, false, false>(&fn, &blocks_per_sm, smem);
@@ -478,7 +491,7 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
 
 #define TRT_KIND_LAUNCH(kern, kind, blocks, threads, st, A) \
     do { if ((kind) == 2) kern<2><<<(blocks), (threads), 0, (st)>>>(A); else if ((kind) == 1) kern<1><<<(blocks), (threads), 0, (st)>>>(A); \
-         else kern<0><<<(blocks), (threads), 0, (st)>>>(A); } while (0)
+         else if ((kind) == 3) kern<3><<<(blocks), (threads), 0, (st)>>>(A); else kern<0><<<(blocks), (threads), 0, (st)>>>(A); } while (0)
 
 cudaError_t launch_aov(const SceneView& v, const trt_camera& cam, const trt_params& p, uint32_t* d_prim, float* d_t,
                        float* d_rad, uint32_t* d_nrays, cudaStream_t st) {
@@ -488,7 +501,7 @@ cudaError_t launch_aov(const SceneView& v, const trt_camera& cam, const trt_para
     if (A.total == 0) return cudaSuccess;
     unsigned long long blocks = (A.total + 127) / 128;
     if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-    TRT_KIND_LAUNCH(k_aov, v.kind, (unsigned)blocks, 128, st, A);
+    TRT_KIND_LAUNCH(k_aov, walk_kind(v, false), (unsigned)blocks, 128, st, A);
     return cudaGetLastError();
 }
 
@@ -498,7 +511,7 @@ cudaError_t launch_sample_batch(const SceneView& v, const trt_params& p, const t
     if (n == 0) return cudaSuccess;
     unsigned long long blocks = (n + 127) / 128;
     if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-    TRT_KIND_LAUNCH(k_sample_batch, v.kind, (unsigned)blocks, 128, st, A);
+    TRT_KIND_LAUNCH(k_sample_batch, walk_kind(v, false), (unsigned)blocks, 128, st, A);
     return cudaGetLastError();
 }
 
@@ -508,7 +521,7 @@ cudaError_t launch_trace(const SceneView& v, const float* d_o, const float* d_d,
     if (n == 0) return cudaSuccess;
     unsigned long long blocks = (n + 127) / 128;
     if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-    TRT_KIND_LAUNCH(k_trace, v.kind, (unsigned)blocks, 128, st, A);
+    TRT_KIND_LAUNCH(k_trace, walk_kind(v, false), (unsigned)blocks, 128, st, A);
     return cudaGetLastError();
 }
 

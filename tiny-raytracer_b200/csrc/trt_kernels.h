@@ -17,12 +17,13 @@ struct SceneView {   // device copy of trt::FlatScene
     const void* flat_cbox_host;// the same boxes on the host: copied into the kernel parameters of k_render_mega_flat
     float flat_bound;          // largest |coordinate| of any flat-list box, or < 0: phase A disabled (literal scan only)
     uint32_t n_flat;
+    const void* nodes4; uint32_t n_nodes4;   // TRT_BVH_SAH: the tree collapsed to 4-wide nodes (8 float4 each) or null
     uint32_t root, n_nodes, n_spheres, n_quads, n_materials;
     uint32_t kind;             // trt_bvh_kind after AUTO resolution: 0 reference, 1 SAH, 2 flat
     float root_min[3], root_max[3];
 };
 
-size_t scene_smem_bytes(const SceneView& v);
+size_t scene_smem_bytes(const SceneView& v, uint32_t kind);
 
 cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const trt_params& p, double* d_sum64,
                                unsigned long long* d_counters, unsigned int* d_next_item, int sm_count, cudaStream_t st);

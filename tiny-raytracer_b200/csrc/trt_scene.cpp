@@ -277,6 +277,56 @@ static void flatten(const std::vector<TNode>& t, const std::vector<HostPrim>& pr
     out.root = 0; out.sah_cost = (float)cost;
 }
 
+// 4-wide nodes for the ordered (SAH) traversal: a wide node's children are the grandchildren of a binary node (a child
+// that is a leaf stays as it is), so every box is still one of the binary tree's boxes — in particular a leaf's box is
+// the primitive's own padded box — and the traversal does half as many dependent node fetches per ray. Record = eight
+// float4: [0..2] children 0,1 and [3..5] children 2,3 as (a, b) pairs per coordinate like the binary node (trt_layout.h),
+// [6] the four child refs, [7] unused. Absent children: TRT_REF_INVALID with an empty box. DFS preorder.
+static void collapse4(const std::vector<TNode>& t, const std::vector<HostPrim>& prims, FlatScene& out) {
+    out.nodes4.clear(); out.n_nodes4 = 0; out.max_depth4 = 0;
+    if (prims.size() < 2) return;
+    struct Item { uint32_t tnode, index, depth; };
+    std::vector<Item> st;
+    uint32_t next = 1;
+    st.push_back({0u, 0u, 1u});
+    const float inf = std::numeric_limits<float>::infinity();
+    while (!st.empty()) {
+        Item it = st.back(); st.pop_back();
+        if (it.depth > out.max_depth4) out.max_depth4 = it.depth;
+        const TNode& n = t[it.tnode];
+        uint32_t kids[4]; int nk = 0;
+        for (uint32_t c : {n.left, n.right}) {
+            if (t[c].prim != NOPRIM) kids[nk++] = c;
+            else { kids[nk++] = t[c].left; kids[nk++] = t[c].right; }
+        }
+        if (out.nodes4.size() < 8 * (size_t)(it.index + 1)) out.nodes4.resize(8 * (size_t)(it.index + 1));
+        float mn[4][3], mx[4][3]; uint32_t ref[4];
+        uint32_t child_index[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 4; ++k) {
+            if (k < nk) {
+                const TNode& c = t[kids[k]];
+                for (int a = 0; a < 3; ++a) { mn[k][a] = c.bmin[a]; mx[k][a] = c.bmax[a]; }
+                if (c.prim != NOPRIM) ref[k] = leaf_ref(prims[c.prim]);
+                else { child_index[k] = next++; ref[k] = child_index[k]; }
+            } else { for (int a = 0; a < 3; ++a) { mn[k][a] = inf; mx[k][a] = -inf; } ref[k] = TRT_REF_INVALID; }
+        }
+        // children are pushed in reverse so that the first child's subtree follows its parent in memory
+        for (int k = nk - 1; k >= 0; --k) if (t[kids[k]].prim == NOPRIM) st.push_back({kids[k], child_index[k], it.depth + 1});
+        if (out.nodes4.size() < 8 * (size_t)next) out.nodes4.resize(8 * (size_t)next);
+        trt_f4* rec = &out.nodes4[8 * (size_t)it.index];
+        for (int h = 0; h < 2; ++h) {
+            const int a = 2 * h, b = 2 * h + 1;
+            rec[3 * h + 0] = {mn[a][0], mn[b][0], mn[a][1], mn[b][1]};
+            rec[3 * h + 1] = {mn[a][2], mn[b][2], mx[a][0], mx[b][0]};
+            rec[3 * h + 2] = {mx[a][1], mx[b][1], mx[a][2], mx[b][2]};
+        }
+        rec[6] = {as_float(ref[0]), as_float(ref[1]), as_float(ref[2]), as_float(ref[3])};
+        rec[7] = {0.f, 0.f, 0.f, 0.f};
+    }
+    out.n_nodes4 = next;
+    out.nodes4.resize(8 * (size_t)next);
+}
+
 bool HostScene::commit(int bvh_kind, std::string* err) {
     if (bvh_kind < 0 || bvh_kind > 4) { *err = "trt_scene_commit: unknown bvh_kind"; return false; }
     size_t n = prims.size();
@@ -323,6 +373,10 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
         tree = &sah_tree;
     }
     if (!device_build) flatten(*tree, prims, flat);
+    if (bvh_kind == 1 && n) {
+        collapse4(*tree, prims, flat);
+        if (3 * flat.max_depth4 + 1 > TRT_MAX_STACK) { flat.nodes4.clear(); flat.n_nodes4 = 0; }   // walk the binary tree instead
+    }
     if (flat.max_depth > TRT_MAX_STACK) { *err = "trt_scene_commit: tree deeper than the traversal stack"; return false; }
 
     flat.spheres.resize(ns); flat.sphere_meta.resize(ns); flat.quads.resize(4 * (size_t)nq); flat.quad_nn.resize(nq); flat.quad_meta.resize(nq);

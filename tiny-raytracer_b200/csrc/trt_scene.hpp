@@ -21,6 +21,8 @@ struct HostPrim {
 
 struct FlatScene {
     std::vector<trt_f4> nodes;         // 4 per interior node
+    std::vector<trt_f4> nodes4;        // TRT_BVH_SAH: the same tree collapsed to 4-wide nodes, 8 per node (trt_scene.cpp collapse4); may be empty
+    uint32_t n_nodes4 = 0, max_depth4 = 0;
     std::vector<trt_f4> spheres;
     std::vector<trt_f4> quads;         // 4 per quad
     std::vector<trt_u4> sphere_meta, quad_meta;
