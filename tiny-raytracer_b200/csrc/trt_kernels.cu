@@ -428,11 +428,12 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     // for the whole warp; big trees cost ~50 steps per ray and waiting for the slowest of 32 rays wastes 3/4 of the lanes.
     uint32_t regen = (p.flags >> 8) & 0xFFu;
     // measured (B200, regen sweep): Cornell 17 nodes, glass Cornell 33, final scene 486: 32 best; 1 M spheres: 16 best (+25 %)
-    if (regen == 0) regen = v.n_nodes <= 4096 ? 32u : 16u;
+    if (regen == 0) regen = v.n_nodes <= 4096 ? 32u : 16u;       // (re-set below for 4-wide nodes, whose rays take half as many steps: 20)
     A.regen_min = regen > 32u ? 32u : regen;
     bool count = (p.flags & 1u) != 0;
     // a TRT_BVH_SAH scene is walked on its 4-wide nodes unless events are counted (the counts are defined on binary nodes)
     const uint32_t kind = walk_kind(v, count || (p.flags & TRT_FLAG_BINARY_NODES));
+    if (kind == 3 && ((p.flags >> 8) & 0xFFu) == 0 && v.n_nodes > 4096) A.regen_min = 20u;    // measured: 1 M spheres 2 315 (20) vs 2 282 (16) Mrays/s
     size_t smem = scene_smem_bytes(v, kind);
     bool use_smem = smem <= 64 * 1024;
     if (v.kind == 2 && (!use_smem || v.n_flat > TRT_FLAT_MAX || !v.flat_cbox_host)) return cudaErrorInvalidValue;

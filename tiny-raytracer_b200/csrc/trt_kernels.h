@@ -28,8 +28,8 @@ size_t scene_smem_bytes(const SceneView& v, uint32_t kind);
 cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const trt_params& p, double* d_sum64,
                                unsigned long long* d_counters, unsigned int* d_next_item, int sm_count, cudaStream_t st);
 size_t lbvh_tmp_bytes(uint32_t n);
-// Builds the 64-byte node array (n - 1 nodes) on the device from per-primitive padded boxes (2 float4 each, leaf-ref bits in bmin.w).
-cudaError_t build_lbvh(const void* d_boxes, uint32_t n, void* d_nodes, void* d_tmp, uint32_t* h_depth, float* h_ms, cudaStream_t st);
+// Builds the 64-byte node array (n - 1 nodes) and, if d_nodes4 is not null, its 4-wide form (128 bytes per node) on the device from per-primitive padded boxes (2 float4 each, leaf-ref bits in bmin.w).
+cudaError_t build_lbvh(const void* d_boxes, uint32_t n, void* d_nodes, void* d_nodes4, void* d_tmp, uint32_t* h_depth, float* h_ms, cudaStream_t st);
 size_t wavefront_scratch_bytes(uint32_t n_slots);
 // Runs the whole wavefront render (host loop inside; synchronises the stream). h_rays_paths[0] = rays, [1] = paths.
 cudaError_t launch_render_wavefront(const SceneView& v, const trt_camera& cam, const trt_params& p, double* d_sum64,

@@ -158,6 +158,39 @@ __global__ void k_lbvh_emit(const float4* __restrict__ boxes, const uint32_t* __
     rec[3] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), 0.f, 0.f);
 }
 
+// 4-wide record of binary node i (trt_scene.cpp collapse4 on the device): its children are node i's grandchildren, a leaf
+// child stays as it is. Every binary node gets one — only those an even number of levels below the root are ever reached —
+// so no compaction or depth is needed and a wide child ref is simply the binary index of that grandchild.
+__global__ void k_lbvh_collapse4(const float4* __restrict__ nodes, uint32_t n, float4* nodes4) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    float mn[4][3], mx[4][3]; uint32_t ref[4]; int nk = 0;
+    auto child = [&](const float4* r, int side) {
+        const float4 a = r[0], b = r[1], c = r[2];
+        mn[nk][0] = side ? a.y : a.x; mn[nk][1] = side ? a.w : a.z; mn[nk][2] = side ? b.y : b.x;
+        mx[nk][0] = side ? b.w : b.z; mx[nk][1] = side ? c.y : c.x; mx[nk][2] = side ? c.w : c.z;
+        ref[nk] = __float_as_uint(side ? r[3].y : r[3].x);
+        ++nk;
+    };
+    const float4* rec = nodes + 4 * (size_t)i;
+    for (int side = 0; side < 2; ++side) {
+        uint32_t c = __float_as_uint(side ? rec[3].y : rec[3].x);
+        if (c & 0x80000000u) child(rec, side);
+        else { const float4* cr = nodes + 4 * (size_t)c; child(cr, 0); child(cr, 1); }
+    }
+    const float inf = __int_as_float(0x7f800000);
+    for (; nk < 4; ++nk) { for (int a = 0; a < 3; ++a) { mn[nk][a] = inf; mx[nk][a] = -inf; } ref[nk] = 0x7FFFFFFFu; }
+    float4* out = nodes4 + 8 * (size_t)i;
+    for (int h = 0; h < 2; ++h) {
+        const int a = 2 * h, b = 2 * h + 1;
+        out[3 * h + 0] = make_float4(mn[a][0], mn[b][0], mn[a][1], mn[b][1]);
+        out[3 * h + 1] = make_float4(mn[a][2], mn[b][2], mx[a][0], mx[b][0]);
+        out[3 * h + 2] = make_float4(mx[a][1], mx[b][1], mx[a][2], mx[b][2]);
+    }
+    out[6] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), __uint_as_float(ref[2]), __uint_as_float(ref[3]));
+    out[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 } // namespace
 
 namespace trtk {
@@ -172,7 +205,8 @@ size_t lbvh_tmp_bytes(uint32_t n) {
 }
 
 // d_boxes: 2 float4 per primitive (bmin.xyz + leaf-ref bits, bmax.xyz). d_nodes: 4 float4 per interior node (n - 1 nodes).
-cudaError_t build_lbvh(const void* d_boxes, uint32_t n, void* d_nodes, void* d_tmp, uint32_t* h_depth, float* h_ms, cudaStream_t st) {
+// d_nodes4 (optional): 8 float4 per interior node, the 4-wide record of every binary node (k_lbvh_collapse4).
+cudaError_t build_lbvh(const void* d_boxes, uint32_t n, void* d_nodes, void* d_nodes4, void* d_tmp, uint32_t* h_depth, float* h_ms, cudaStream_t st) {
     if (n < 2) return cudaErrorInvalidValue;
     char* p = (char*)d_tmp;
     LbvhBounds* b = (LbvhBounds*)p; p += al(sizeof(LbvhBounds));
@@ -199,6 +233,7 @@ cudaError_t build_lbvh(const void* d_boxes, uint32_t n, void* d_nodes, void* d_t
         k_lbvh_karras<<<g, 256, 0, st>>>(keys_s, n, left, right, pn, pl, flags);
         k_lbvh_refit<<<g, 256, 0, st>>>(boxes, order, n, left, right, pn, pl, flags, node_min, node_max, b);
         k_lbvh_emit<<<g, 256, 0, st>>>(boxes, order, n, left, right, node_min, node_max, (float4*)d_nodes);
+        if (d_nodes4) k_lbvh_collapse4<<<g, 256, 0, st>>>((const float4*)d_nodes, n, (float4*)d_nodes4);
         cudaEventRecord(e1, st);
         LbvhBounds hb;
         e = cudaMemcpyAsync(&hb, b, sizeof hb, cudaMemcpyDeviceToHost, st);
