@@ -8,6 +8,8 @@
 //     [1] = ( lmin.z, rmin.z, lmax.x, rmax.x )      interleaved as (left, right) pairs per coordinate: each 64-bit half of a
 //     [2] = ( lmax.y, rmax.y, lmax.z, rmax.z )      load is one operand of a packed FADD2/FMUL2 (both slab tests at once)
 //     [3] = ( left_ref, right_ref, 0, 0 ) as bits
+//   wide node n (float4 nodes4[8n .. 8n+7], TRT_BVH_SAH and the device-built tree): [0..2] children 0,1 and [3..5] children 2,3
+//     in the same pair layout, [6] = the four child refs, [7] unused; absent child = TRT_REF_INVALID with an empty box.
 //   child ref: bit31 = leaf, bit30 = primitive type (0 sphere, 1 quad), bits0..29 = index into that type's array;
 //              otherwise the index of an interior node; TRT_REF_INVALID = absent child (single-primitive scene).
 //   With one primitive per leaf the child box stored in the parent IS the primitive's own padded box, i.e. the box the
