@@ -34,10 +34,9 @@ using namespace trtd;
 // staging its 31 KB of per-hit records would cap the kernel at 3 CTAs per SM instead of 4.
 #define TRT_AUX_SMEM_F4 512u       /* 8 KB */
 __host__ __device__ inline uint32_t aux_f4(uint32_t n_spheres, uint32_t n_quads, uint32_t n_materials) { return n_spheres + 2u * n_quads + 2u * n_materials; }
-// layout: [nodes | spheres | quads | sphere_meta | quad_meta | materials | flat list | per-thread phase-A columns]
+// layout: [nodes or wide nodes | spheres | quads | sphere_meta | quad_meta | quad_nn | materials (the four per-hit arrays only while small) | flat list]
 template <bool SMEM, int KIND>
-__device__ __forceinline__ DevScene stage_scene(const DevScene& G, float** tt_out) {
-    *tt_out = nullptr;
+__device__ __forceinline__ DevScene stage_scene(const DevScene& G) {
     if (!SMEM) return G;
     extern __shared__ float4 smem_f4[];
     DevScene S = G;
@@ -59,7 +58,6 @@ __device__ __forceinline__ DevScene stage_scene(const DevScene& G, float** tt_ou
         S.materials = copy(G.materials, 2 * G.n_materials);
     }
     S.flat = (const FlatPrim*)copy((const float4*)G.flat, 6 * G.n_flat);
-    *tt_out = (float*)(smem_f4 + off) + threadIdx.x;     // column of this thread, stride blockDim.x
     __syncthreads();
     return S;
 }
@@ -101,8 +99,7 @@ __device__ __forceinline__ bool decode_item(const MegaArgs& A, uint32_t item, ui
 // 3 = TRT_BVH_SAH walked on its 4-wide nodes.
 template <int KIND, bool SMEM, bool COUNT>
 __device__ __forceinline__ void mega_body(const MegaArgs& A, const float4* U) {
-    float* tt;
-    const DevScene S = stage_scene<SMEM, KIND>(A.scene, &tt);
+    const DevScene S = stage_scene<SMEM, KIND>(A.scene);
     const DevParams& P = A.p;
     const uint32_t lane = threadIdx.x & 31u;
     V3 o = mk(0, 0, 0), d = mk(0, 0, 1), atten = mk(1, 1, 1), color = mk(0, 0, 0);
@@ -202,8 +199,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& A, const float4* U) {
 // 7-step Cornell ray. The launcher picks regen_min from the tree size; trt_params.flags bits 8..15 override it.
 template <int KIND, bool SMEM, bool COUNT>
 __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
-    float* tt;
-    const DevScene S = stage_scene<SMEM, KIND>(A.scene, &tt);
+    const DevScene S = stage_scene<SMEM, KIND>(A.scene);
     const DevParams& P = A.p;
     const uint32_t lane = threadIdx.x & 31u;
     Trav T; T.cur = TRT_REF_INVALID; T.sp = 0; T.best.t = TRT_INF; T.best.ref = TRT_REF_INVALID;
