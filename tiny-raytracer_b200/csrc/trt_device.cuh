@@ -9,6 +9,15 @@
 #include <stdint.h>
 #include "trt_layout.h"
 
+// -DTRT_DEBUG_BOUNDS: device-side asserts on every traversal-stack push and node / primitive index (a debug build for the
+// GPU box; compute-sanitizer is not available on this pool). Off in the product build.
+#ifdef TRT_DEBUG_BOUNDS
+#include <assert.h>
+#define TRT_ASSERT(c) assert(c)
+#else
+#define TRT_ASSERT(c) ((void)0)
+#endif
+
 namespace trtd {
 
 #define TRT_DEV __device__ __forceinline__
@@ -308,6 +317,7 @@ TRT_DEV void trav_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* s
     const V3 o = T.o, d = T.d, inv = T.inv; const float t_min = T.t_min;
     if (!(cur & TRT_REF_LEAF)) {
         // ---- region A: one interior node = two child boxes (aabb.rs:36-61 twice)
+        TRT_ASSERT(cur < S.n_nodes);
         const float4* np = S.nodes + 4 * (size_t)cur;
         float4 n0 = ld4<SMEM>(np), n1 = ld4<SMEM>(np + 1), n2 = ld4<SMEM>(np + 2), n3 = ld4<SMEM>(np + 3);
         uint32_t lref = __float_as_uint(n3.x), rref = __float_as_uint(n3.y);
@@ -329,13 +339,14 @@ TRT_DEV void trav_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* s
         bool p0 = right_first ? pr : pl, p1 = right_first ? pl : pr;
         if (p0) {
             cur = c0;
-            if (p1) { stack_ref[T.sp] = c1; stack_t[T.sp] = s1; ++T.sp; }
+            if (p1) { TRT_ASSERT(T.sp < TRT_MAX_STACK); stack_ref[T.sp] = c1; stack_t[T.sp] = s1; ++T.sp; }
         } else if (p1 && (ORDERED || T.best.t > s1)) cur = c1;
         else cur = TRT_REF_INVALID;
     }
     if (cur != TRT_REF_INVALID && (cur & TRT_REF_LEAF)) {
         // ---- region B: one primitive (sphere.rs:29-45 / quad.rs:33-41)
         uint32_t idx = cur & TRT_REF_INDEX_MASK;
+        TRT_ASSERT(idx < ((cur & TRT_REF_QUAD) ? S.n_quads : S.n_spheres));
         float t; bool h;
         if (cur & TRT_REF_QUAD) { if (COUNT) ec->quad_tests++; h = quad_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : T.best.t, T.best.t, &t); }
         else { if (COUNT) ec->sphere_tests++; h = sphere_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : T.best.t, &t); }
@@ -380,6 +391,7 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* 
     uint32_t cur = T.cur;
     const V3 o = T.o, d = T.d, inv = T.inv; const float t_min = T.t_min;
     if (!(cur & TRT_REF_LEAF)) {
+        TRT_ASSERT(cur < S.n_nodes4);
         const float4* np = S.nodes4 + 8 * (size_t)cur;
         const float4 a0 = ld4<SMEM>(np), a1 = ld4<SMEM>(np + 1), a2 = ld4<SMEM>(np + 2);
         const float4 b0 = ld4<SMEM>(np + 3), b1 = ld4<SMEM>(np + 4), b2 = ld4<SMEM>(np + 5), rf = ld4<SMEM>(np + 6);
@@ -406,6 +418,7 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* 
 #undef TRT_CSWAP
         // an entered child with an infinite entry (s = +inf is possible only for a degenerate ray) must not be lost: the
         // ref, not the key, says whether a slot is occupied
+        TRT_ASSERT(T.sp + 3 <= TRT_MAX_STACK);
         if (r3 != TRT_REF_INVALID) { stack_ref[T.sp] = r3; stack_t[T.sp] = s3; ++T.sp; }
         if (r2 != TRT_REF_INVALID) { stack_ref[T.sp] = r2; stack_t[T.sp] = s2; ++T.sp; }
         if (r1 != TRT_REF_INVALID) { stack_ref[T.sp] = r1; stack_t[T.sp] = s1; ++T.sp; }
@@ -413,6 +426,7 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* 
     }
     if (cur != TRT_REF_INVALID && (cur & TRT_REF_LEAF)) {
         uint32_t idx = cur & TRT_REF_INDEX_MASK;
+        TRT_ASSERT(idx < ((cur & TRT_REF_QUAD) ? S.n_quads : S.n_spheres));
         float t; bool h;
         if (cur & TRT_REF_QUAD) h = quad_hit<SMEM>(S, idx, o, d, t_min, TRT_INF, T.best.t, &t);
         else h = sphere_hit<SMEM>(S, idx, o, d, t_min, TRT_INF, &t);
@@ -671,6 +685,7 @@ TRT_DEV Hit closest_hit_flat(const float4* __restrict__ CB, float bound, const F
         while (m) {
             const uint32_t i = (uint32_t)__ffs((int)m) - 1u + 32u * half;
             m &= m - 1u;
+            TRT_ASSERT(i < n);
             const float4* p = (const float4*)(Dv + i);
             const uint32_t ref = __float_as_uint(ldf<DSMEM>(p + 5).z);
             float t;
