@@ -70,7 +70,7 @@ typedef struct trt_params {
 #define TRT_FLAG_NO_TAIL_SPLIT 2u  /* megakernel: hand out whole pixels only (every pixel summed by one lane in sample order ->
                                     * run-to-run bit-identical f64 sums); default splits the last pixels into sample chunks
                                     * added with f64 atomics (tail balance; the f32 image can move by <= 1 ulp) */
-#define TRT_FLAG_BINARY_NODES 4u   /* TRT_BVH_SAH: walk the binary nodes instead of the 4-wide ones (same results; A/B and tests) */
+#define TRT_FLAG_BINARY_NODES 4u   /* tree kinds: walk the binary nodes instead of the 4-wide ones (same results; A/B and tests) */
 /* bits 8..15 of flags: megakernel tuning override, the number of lanes of a warp (1..32) that must have finished their ray
  * before the shade/regenerate block runs; 0 = chosen from the tree size (32 up to 4096 nodes, 16 above). Results do not
  * depend on it. */

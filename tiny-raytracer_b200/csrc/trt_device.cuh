@@ -381,12 +381,17 @@ TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounter
     return T.best;
 }
 
-// ------------------------------------------------------------------ the ordered traversal on 4-wide nodes
-// Same rules as trav_step<ORDERED = true>: a child is entered when its box is crossed and its entry is not beyond the
-// closest hit, a primitive wins with a smaller t or an equal t and a smaller reference leaf rank, so the result does not
-// depend on the visiting order — only the number of dependent node fetches per ray does (about half of the binary walk).
-// The (up to) four crossed children are sorted by entry distance; the nearest is entered, the others are pushed farthest first.
-template <bool SMEM>
+// ------------------------------------------------------------------ traversal on 4-wide nodes
+// A wide node's children are the grandchildren of a binary node in left-to-right order (trt_scene.cpp collapse4).
+// ORDERED (TRT_BVH_SAH, device-built tree): same rules as trav_step<true>: a child is entered when its box is crossed and
+//   its entry is not beyond the closest hit, a primitive wins with a smaller t or an equal t and a smaller reference leaf
+//   rank, so the result does not depend on the visiting order. The crossed children are sorted by entry distance; the
+//   nearest is entered, the others are pushed farthest first.
+// !ORDERED (TRT_BVH_REFERENCE): children are taken strictly left to right — the first now, the others pushed and
+//   re-checked against the narrowed closest hit when popped — so the leaves are met in the reference's order, each with
+//   its own box tested against the range the reference would use (lemma L: the skipped intermediate box cannot cull).
+// Either way only the number of dependent node fetches per ray changes (about half of the binary walk).
+template <bool ORDERED, bool SMEM>
 TRT_DEV void trav4_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* stack_t) {
     uint32_t cur = T.cur;
     const V3 o = T.o, d = T.d, inv = T.inv; const float t_min = T.t_min;
@@ -407,31 +412,39 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* 
         }
         uint32_t r0 = __float_as_uint(rf.x), r1 = __float_as_uint(rf.y), r2 = __float_as_uint(rf.z), r3 = __float_as_uint(rf.w);
         const float best = T.best.t;
-        // a child that is not entered sorts last (key +inf) and carries TRT_REF_INVALID
-        if (!(e0 > s0 && !(best < s0) && r0 != TRT_REF_INVALID)) { s0 = TRT_INF; r0 = TRT_REF_INVALID; }
-        if (!(e1 > s1 && !(best < s1) && r1 != TRT_REF_INVALID)) { s1 = TRT_INF; r1 = TRT_REF_INVALID; }
-        if (!(e2 > s2 && !(best < s2) && r2 != TRT_REF_INVALID)) { s2 = TRT_INF; r2 = TRT_REF_INVALID; }
-        if (!(e3 > s3 && !(best < s3) && r3 != TRT_REF_INVALID)) { s3 = TRT_INF; r3 = TRT_REF_INVALID; }
+        TRT_ASSERT(T.sp + 3 <= TRT_MAX_STACK);
+        if (ORDERED) {
+            // a child that is not entered sorts last (key +inf) and carries TRT_REF_INVALID
+            if (!(e0 > s0 && !(best < s0) && r0 != TRT_REF_INVALID)) { s0 = TRT_INF; r0 = TRT_REF_INVALID; }
+            if (!(e1 > s1 && !(best < s1) && r1 != TRT_REF_INVALID)) { s1 = TRT_INF; r1 = TRT_REF_INVALID; }
+            if (!(e2 > s2 && !(best < s2) && r2 != TRT_REF_INVALID)) { s2 = TRT_INF; r2 = TRT_REF_INVALID; }
+            if (!(e3 > s3 && !(best < s3) && r3 != TRT_REF_INVALID)) { s3 = TRT_INF; r3 = TRT_REF_INVALID; }
 #define TRT_CSWAP(sa, ra, sb, rb) { const bool w_ = sb < sa; const float ts_ = w_ ? sb : sa, tb_ = w_ ? sa : sb; \
                                     const uint32_t tr_ = w_ ? rb : ra, tq_ = w_ ? ra : rb; sa = ts_; sb = tb_; ra = tr_; rb = tq_; }
-        TRT_CSWAP(s0, r0, s1, r1) TRT_CSWAP(s2, r2, s3, r3) TRT_CSWAP(s0, r0, s2, r2) TRT_CSWAP(s1, r1, s3, r3) TRT_CSWAP(s1, r1, s2, r2)
+            TRT_CSWAP(s0, r0, s1, r1) TRT_CSWAP(s2, r2, s3, r3) TRT_CSWAP(s0, r0, s2, r2) TRT_CSWAP(s1, r1, s3, r3) TRT_CSWAP(s1, r1, s2, r2)
 #undef TRT_CSWAP
-        // an entered child with an infinite entry (s = +inf is possible only for a degenerate ray) must not be lost: the
-        // ref, not the key, says whether a slot is occupied
-        TRT_ASSERT(T.sp + 3 <= TRT_MAX_STACK);
-        if (r3 != TRT_REF_INVALID) { stack_ref[T.sp] = r3; stack_t[T.sp] = s3; ++T.sp; }
-        if (r2 != TRT_REF_INVALID) { stack_ref[T.sp] = r2; stack_t[T.sp] = s2; ++T.sp; }
-        if (r1 != TRT_REF_INVALID) { stack_ref[T.sp] = r1; stack_t[T.sp] = s1; ++T.sp; }
-        cur = r0;
+            // the ref, not the key, says whether a slot is occupied
+            if (r3 != TRT_REF_INVALID) { stack_ref[T.sp] = r3; stack_t[T.sp] = s3; ++T.sp; }
+            if (r2 != TRT_REF_INVALID) { stack_ref[T.sp] = r2; stack_t[T.sp] = s2; ++T.sp; }
+            if (r1 != TRT_REF_INVALID) { stack_ref[T.sp] = r1; stack_t[T.sp] = s1; ++T.sp; }
+            cur = r0;
+        } else {
+            // bvh.rs:97: a later sibling is searched with the range end narrowed by everything before it -> re-checked when popped
+            if (e3 > s3 && r3 != TRT_REF_INVALID) { stack_ref[T.sp] = r3; stack_t[T.sp] = s3; ++T.sp; }
+            if (e2 > s2 && r2 != TRT_REF_INVALID) { stack_ref[T.sp] = r2; stack_t[T.sp] = s2; ++T.sp; }
+            if (e1 > s1 && r1 != TRT_REF_INVALID) { stack_ref[T.sp] = r1; stack_t[T.sp] = s1; ++T.sp; }
+            cur = (e0 > s0 && best > s0) ? r0 : TRT_REF_INVALID;
+        }
     }
     if (cur != TRT_REF_INVALID && (cur & TRT_REF_LEAF)) {
         uint32_t idx = cur & TRT_REF_INDEX_MASK;
         TRT_ASSERT(idx < ((cur & TRT_REF_QUAD) ? S.n_quads : S.n_spheres));
         float t; bool h;
-        if (cur & TRT_REF_QUAD) h = quad_hit<SMEM>(S, idx, o, d, t_min, TRT_INF, T.best.t, &t);
-        else h = sphere_hit<SMEM>(S, idx, o, d, t_min, TRT_INF, &t);
+        if (cur & TRT_REF_QUAD) h = quad_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : T.best.t, T.best.t, &t);
+        else h = sphere_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : T.best.t, &t);
         if (h) {
-            if (t < T.best.t) { T.best.t = t; T.best.ref = cur; T.best_rank = 0xFFFFFFFFu; }
+            if (!ORDERED) { T.best.t = t; T.best.ref = cur; }
+            else if (t < T.best.t) { T.best.t = t; T.best.ref = cur; T.best_rank = 0xFFFFFFFFu; }
             else if (t == T.best.t) {
                 if (T.best_rank == 0xFFFFFFFFu)
                     T.best_rank = (T.best.ref & TRT_REF_QUAD) ? ld4ua(S.quad_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y
@@ -444,16 +457,17 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* 
     }
     while (cur == TRT_REF_INVALID && T.sp > 0) {
         --T.sp;
-        if (!(T.best.t < stack_t[T.sp])) cur = stack_ref[T.sp];
+        const float s = stack_t[T.sp];
+        if (ORDERED ? !(T.best.t < s) : (T.best.t > s)) cur = stack_ref[T.sp];
     }
     T.cur = cur;
 }
-template <bool SMEM>
+template <bool ORDERED, bool SMEM>
 TRT_DEV Hit closest_hit4(const DevScene& S, V3 o, V3 d, float t_min) {
     Trav T; EventCounters ec;
     trav_begin<false>(T, S, o, d, t_min, &ec);
     uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
-    while (T.cur != TRT_REF_INVALID) trav4_step<SMEM>(T, S, stack_ref, stack_t);
+    while (T.cur != TRT_REF_INVALID) trav4_step<ORDERED, SMEM>(T, S, stack_ref, stack_t);
     return T.best;
 }
 
@@ -703,11 +717,11 @@ TRT_DEV Hit closest_hit_flat(const float4* __restrict__ CB, float bound, const F
 }
 
 // One whole path: CpuSampler::single_point_sampling, renderer/sampler/cpu.rs:39-65
-// KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH (binary nodes), 2 = TRT_BVH_FLAT, 3 = TRT_BVH_SAH on its 4-wide nodes
+// KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH (binary nodes), 2 = TRT_BVH_FLAT, 3 / 4 = SAH / REFERENCE on their 4-wide nodes
 template <int KIND, bool SMEM, bool COUNT>
 TRT_DEV Hit closest_hit_any(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
     if (KIND == 2) return closest_hit_flat<false>(S.flat_cbox, S.flat_bound, S.flat, S.n_flat, o, d, t_min);
-    if (KIND == 3) return closest_hit4<SMEM>(S, o, d, t_min);
+    if (KIND == 3 || KIND == 4) return closest_hit4<KIND == 3, SMEM>(S, o, d, t_min);
     return closest_hit<KIND == 1, SMEM, COUNT>(S, o, d, t_min, ec);
 }
 

@@ -47,7 +47,7 @@ __device__ __forceinline__ DevScene stage_scene(const DevScene& G) {
         off += n;
         return dst;
     };
-    if (KIND == 3) S.nodes4 = copy(G.nodes4, 8 * G.n_nodes4);          // the walk reads only one of the two node arrays
+    if (KIND == 3 || KIND == 4) S.nodes4 = copy(G.nodes4, 8 * G.n_nodes4);          // the walk reads only one of the two node arrays
     else S.nodes = copy(G.nodes, 4 * G.n_nodes);
     S.spheres = copy(G.spheres, G.n_spheres);
     S.quads = copy(G.quads, 4 * G.n_quads);
@@ -96,7 +96,7 @@ __device__ __forceinline__ bool decode_item(const MegaArgs& A, uint32_t item, ui
 // and the lanes starting a new path share ONE Philox call, ONE normalisation and the work-fetch point; every lane that
 // still has work leaves S with a live ray, so T always runs with full lanes until the work counter runs dry).
 // KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH, 2 = TRT_BVH_FLAT (U = the phase-A boxes in the constant bank),
-// 3 = TRT_BVH_SAH walked on its 4-wide nodes.
+// 3 / 4 = TRT_BVH_SAH / TRT_BVH_REFERENCE walked on their 4-wide nodes.
 template <int KIND, bool SMEM, bool COUNT>
 __device__ __forceinline__ void mega_body(const MegaArgs& A, const float4* U) {
     const DevScene S = stage_scene<SMEM, KIND>(A.scene);
@@ -114,7 +114,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& A, const float4* U) {
         Hit h; h.t = TRT_INF; h.ref = TRT_REF_INVALID;
         if (alive) {
             if (KIND == 2) h = closest_hit_flat<true>(U, S.flat_bound, S.flat, S.n_flat, o, d, P.t_min);
-            else if (KIND == 3) h = closest_hit4<SMEM>(S, o, d, P.t_min);
+            else if (KIND == 3 || KIND == 4) h = closest_hit4<KIND == 3, SMEM>(S, o, d, P.t_min);
             else h = closest_hit<KIND == 1, SMEM, COUNT>(S, o, d, P.t_min, &ec);
             ++n_rays;
         }
@@ -216,7 +216,7 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
     for (;;) {
         // ---- T: one step of cpu.rs:48 for every lane whose ray is in flight
         if (T.cur != TRT_REF_INVALID) {
-            if (KIND == 3) trav4_step<SMEM>(T, S, stack_ref, stack_t);
+            if (KIND == 3 || KIND == 4) trav4_step<KIND == 3, SMEM>(T, S, stack_ref, stack_t);
             else trav_step<KIND == 1, SMEM, COUNT>(T, S, stack_ref, stack_t, &ec);
         }
         const bool tracing = T.cur != TRT_REF_INVALID;
@@ -395,12 +395,15 @@ __global__ void k_debug_philox(size_t n, const uint32_t* ctr, uint32_t k0, uint3
 // ------------------------------------------------------------------ launchers
 namespace trtk {
 
-static uint32_t walk_kind(const SceneView& v, bool binary_only) { return (v.kind == 1 && v.nodes4 && v.n_nodes4 && !binary_only) ? 3u : v.kind; }
+static uint32_t walk_kind(const SceneView& v, bool binary_only) {
+    if (binary_only || !v.nodes4 || !v.n_nodes4) return v.kind;
+    return v.kind == 1 ? 3u : (v.kind == 0 ? 4u : v.kind);
+}
 // kind: as walked (3 = the 4-wide nodes of a TRT_BVH_SAH scene)
 size_t scene_smem_bytes(const SceneView& v, uint32_t kind) {
     size_t aux = aux_f4(v.n_spheres, v.n_quads, v.n_materials);
     if (aux > TRT_AUX_SMEM_F4) aux = 0;
-    size_t nodes = kind == 3 ? 8ull * v.n_nodes4 : 4ull * v.n_nodes;
+    size_t nodes = (kind == 3 || kind == 4) ? 8ull * v.n_nodes4 : 4ull * v.n_nodes;
     return 16ull * (nodes + v.n_spheres + 4ull * v.n_quads + 6ull * v.n_flat + aux);
 }
 
@@ -429,7 +432,7 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     bool count = (p.flags & 1u) != 0;
     // a TRT_BVH_SAH scene is walked on its 4-wide nodes unless events are counted (the counts are defined on binary nodes)
     const uint32_t kind = walk_kind(v, count || (p.flags & TRT_FLAG_BINARY_NODES));
-    if (kind == 3 && ((p.flags >> 8) & 0xFFu) == 0 && v.n_nodes > 4096) A.regen_min = 20u;    // measured: 1 M spheres 2 315 (20) vs 2 282 (16) Mrays/s
+    if ((kind == 3 || kind == 4) && ((p.flags >> 8) & 0xFFu) == 0 && v.n_nodes > 4096) A.regen_min = 20u;    // measured: 1 M spheres 2 315 (20) vs 2 282 (16) Mrays/s
     size_t smem = scene_smem_bytes(v, kind);
     bool use_smem = smem <= 64 * 1024;
     if (v.kind == 2 && (!use_smem || v.n_flat > TRT_FLAT_MAX || !v.flat_cbox_host)) return cudaErrorInvalidValue;
@@ -441,6 +444,8 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_render_mega_flat, MEGA_THREADS, smem);
     } else if (kind == 3) {
         e = use_smem ? mega_fn<3, true, false>(&fn, &blocks_per_sm, smem) : mega_fn<3, false, false>(&fn, &blocks_per_sm, smem);
+    } else if (kind == 4) {
+        e = use_smem ? mega_fn<4, true, false>(&fn, &blocks_per_sm, smem) : mega_fn<4, false, false>(&fn, &blocks_per_sm, smem);
     } else if (v.kind == 1) {
         if (use_smem) e = count ? mega_fn<1, true, true>(&fn, &blocks_per_sm, smem) : mega_fn<1, true, false>(&fn, &blocks_per_sm, smem);
         else e = count ? mega_fn<1, false, true>(&fn, &blocks_per_sm, smem) : mega_fn<1, false, false>(&fn, &blocks_per_sm, smem);
@@ -488,7 +493,7 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
 
 #define TRT_KIND_LAUNCH(kern, kind, blocks, threads, st, A) \
     do { if ((kind) == 2) kern<2><<<(blocks), (threads), 0, (st)>>>(A); else if ((kind) == 1) kern<1><<<(blocks), (threads), 0, (st)>>>(A); \
-         else if ((kind) == 3) kern<3><<<(blocks), (threads), 0, (st)>>>(A); else kern<0><<<(blocks), (threads), 0, (st)>>>(A); } while (0)
+         else if ((kind) == 3) kern<3><<<(blocks), (threads), 0, (st)>>>(A); else if ((kind) == 4) kern<4><<<(blocks), (threads), 0, (st)>>>(A); else kern<0><<<(blocks), (threads), 0, (st)>>>(A); } while (0)
 
 cudaError_t launch_aov(const SceneView& v, const trt_camera& cam, const trt_params& p, uint32_t* d_prim, float* d_t,
                        float* d_rad, uint32_t* d_nrays, cudaStream_t st) {

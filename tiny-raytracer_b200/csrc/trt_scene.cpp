@@ -373,7 +373,7 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
         tree = &sah_tree;
     }
     if (!device_build) flatten(*tree, prims, flat);
-    if (bvh_kind == 1 && n) {
+    if ((bvh_kind == 0 || bvh_kind == 1) && n) {
         collapse4(*tree, prims, flat);
         if (3 * flat.max_depth4 + 1 > TRT_MAX_STACK) { flat.nodes4.clear(); flat.n_nodes4 = 0; }   // walk the binary tree instead
     }
