@@ -27,6 +27,9 @@ using namespace trtd;
 #define TRT_FLAT_MIN_BLOCKS 3   // 80 registers, no spills: measured equal to 4 blocks with spills, and ahead of 5
 #endif
 #define MEGA_THREADS TRT_MEGA_THREADS
+#ifndef TRT_FLAT_THREADS
+#define TRT_FLAT_THREADS 256
+#endif
 
 // ------------------------------------------------------------------ shared-memory staging of small scenes
 // The traversal data (nodes, primitives, flat list) are staged whenever they fit; the per-hit records (meta, materials,
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, TRT_MEGA_MIN_BLOCKS) k_render_me
     if (A.regen_min >= 32u) mega_body<KIND, SMEM, COUNT>(A, nullptr);
     else mega_body_async<KIND, SMEM, COUNT>(A);
 }
-__global__ void __launch_bounds__(MEGA_THREADS, TRT_FLAT_MIN_BLOCKS) k_render_mega_flat(const __grid_constant__ MegaArgs A, const __grid_constant__ FlatList L) {
+__global__ void __launch_bounds__(TRT_FLAT_THREADS, TRT_FLAT_MIN_BLOCKS) k_render_mega_flat(const __grid_constant__ MegaArgs A, const __grid_constant__ FlatList L) {
     mega_body<2, true, false>(A, L.cbox);
 }
 
@@ -441,7 +444,7 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     if (v.kind == 2) {
         if (smem > 48 * 1024) { e = cudaFuncSetAttribute(k_render_mega_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
         fn = (const void*)k_render_mega_flat;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_render_mega_flat, MEGA_THREADS, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_render_mega_flat, TRT_FLAT_THREADS, smem);
     } else if (kind == 3) {
         e = use_smem ? mega_fn<3, true, false>(&fn, &blocks_per_sm, smem) : mega_fn<3, false, false>(&fn, &blocks_per_sm, smem);
     } else if (kind == 4) {
@@ -457,7 +460,8 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     // persistent grid: every SM filled to the kernel's occupancy limit, one wave
     int grid = sm_count * blocks_per_sm;
-    uint64_t resident = (uint64_t)grid * MEGA_THREADS;
+    const unsigned threads = v.kind == 2 ? TRT_FLAT_THREADS : MEGA_THREADS;
+    uint64_t resident = (uint64_t)grid * threads;
     uint64_t pixels = (uint64_t)p.width * p.height;
     // work items: whole pixels (all samples, plain store) while there are plenty of them; the LAST tiles of the list are
     // split into chunks of samples so that no lane idles behind one long final pixel (at 1024 spp a pixel is 1/14 of a
@@ -485,7 +489,7 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
         FlatList L;
         memcpy(&L, v.flat_cbox_host, sizeof L);
         void* args[] = {(void*)&A, (void*)&L};
-        return cudaLaunchKernel(fn, dim3(grid), dim3(MEGA_THREADS), args, smem, st);
+        return cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, st);
     }
     void* args[] = {(void*)&A};
     return cudaLaunchKernel(fn, dim3(grid), dim3(MEGA_THREADS), args, smem, st);
