@@ -303,6 +303,23 @@ def test_event_counters_match_oracle(trt, orc, ctx, kind):
             assert st.node_visits > 0 and st.sphere_tests + st.quad_tests > 0
 
 
+@pytest.mark.parametrize("case", ["c3", "c5"])
+def test_flat_list_equals_reference_tree_at_full_resolution(trt, orc, ctx, case):
+    """The two kinds that reproduce the reference by construction — the flat list with its conservative FFMA2 box phase
+    and the reference-topology tree — on the BASELINE frames at full resolution (Cornell 1080p x 8 spp: 74 M ray segments;
+    glass Cornell 4K x 2 spp, depth 100): identical ray counts and bit-identical images (whole-pixel items, so the f64
+    sums are taken in the same order)."""
+    desc = trt.scenes.cornell(1920, 1080, 8, 50) if case == "c3" else trt.scenes.glass_cornell(3840, 2160, 2, 100)
+    cam = trt.make_camera(**desc.camera)
+    out = []
+    for kind in (trt.BVH_FLAT, trt.BVH_REFERENCE):
+        p, _ = params(trt, orc, desc, flags=2)      # TRT_FLAG_NO_TAIL_SPLIT
+        lin, u8, st = trt.Scene.from_desc(desc, kind).render(ctx, cam, p)
+        out.append((lin, u8, st))
+    assert out[0][2].rays == out[1][2].rays and out[0][2].paths == out[1][2].paths
+    assert np.array_equal(bits(out[0][0]), bits(out[1][0])) and np.array_equal(out[0][1], out[1][1])
+
+
 def test_render_is_deterministic_and_kind_independent(trt, orc, ctx):
     desc = trt.scenes.cornell_spheres(256, 256, 12, 20)
     cam = trt.make_camera(**desc.camera)
