@@ -153,8 +153,8 @@ def test_primary_hits_bvh_stress(trt, orc, ctx, kind):
     TRT_BVH_SAH visits nodes in another order. The reference's result is order-dependent in one corner:
     a grazing sphere hit whose computed t is smaller than its own box's computed entry (fp cancellation in
     hb*hb - a*c at distance ~150) is culled or not depending on which primitive the reference happened to visit first.
-    Such samples may differ; the test bounds their rate (<= 1e-5 of the samples), checks that each one is of exactly
-    that class (both answers within the fp error of the tangent), and requires all other samples to be bit-exact."""
+    The ordered walk detects exactly that situation on its winner and replays the ray in the reference's order, so it is
+    bit-exact as well (before the replay existed, 3-5 of these 0.5 M samples differed)."""
     desc = trt.scenes.random_spheres(200_000, 960, 540, 1, 3)
     flat_ok(kind, desc)
     osc, ocam, cam = both(trt, orc, desc)
@@ -163,15 +163,23 @@ def test_primary_hits_bvh_stress(trt, orc, ctx, kind):
     prim, t, rad, nr = sc.render_aov(ctx, cam, p, True, True)
     oprim, ot, orad, onr = osc.render_aov(ocam, op, True, True)
     same = (nr == onr) & (bits(rad) == bits(orad)).all(1) & (prim == oprim) & (bits(t) == bits(ot))
-    if kind == 0:
-        assert same.all(), "%d mismatches" % int((~same).sum())
-        return
-    bad = ~same
-    assert bad.sum() <= max(1, int(1e-5 * bad.size)), "%d of %d samples differ" % (int(bad.sum()), bad.size)
-    prim_bad = prim != oprim
-    assert prim_bad.sum() <= 2
-    for i in np.nonzero(prim_bad)[0]:
-        assert prim[i] != 0xFFFFFFFF and oprim[i] != 0xFFFFFFFF and abs(float(t[i]) - float(ot[i])) <= 2e-3 * max(1.0, float(ot[i]))
+    assert same.all(), "%d mismatches" % int((~same).sum())
+
+
+def test_sah_order_dependent_rays_are_replayed(trt, orc, ctx):
+    """Deep paths through 200 k spheres (depth 50, 1 M samples): the SAH walk with its replay equals the oracle on every
+    sample; the device-built tree, which has no reference tree to replay on, may differ on the §4.3 class only."""
+    desc = trt.scenes.random_spheres(200_000, 960, 540, 2, 50)
+    osc, ocam, cam = both(trt, orc, desc)
+    p, op = params(trt, orc, desc)
+    oprim, ot, orad, onr = osc.render_aov(ocam, op, True, True)
+    for kind in (trt.BVH_SAH, trt.BVH_LBVH_DEVICE):
+        prim, t, rad, nr = trt.Scene.from_desc(desc, kind).render_aov(ctx, cam, p, True, True)
+        same = (nr == onr) & (bits(rad) == bits(orad)).all(1) & (prim == oprim) & (bits(t) == bits(ot))
+        if kind == trt.BVH_SAH:
+            assert same.all(), "%d mismatches" % int((~same).sum())
+        else:
+            assert (~same).sum() <= 2e-5 * same.size
 
 
 # ------------------------------------------------------------------ whole renders (megakernel)
@@ -227,7 +235,7 @@ def test_async_regeneration_threshold_does_not_change_results(trt, orc, ctx, kin
 def test_binary_and_wide_nodes_agree(trt, orc, ctx, kind, regen_min):
     """Tree scenes are walked on 4-wide nodes (the binary tree collapsed by two levels) unless TRT_FLAG_BINARY_NODES asks
     for the binary walk: same boxes, same acceptance rules, so the images are identical bit for bit (whole-pixel items:
-    fixed summation order) and both match the oracle (the reference kind exactly, SAH up to DESIGN.md §4.3)."""
+    fixed summation order) and both match the oracle."""
     for desc in (trt.scenes.final_scene(120, 68, 6, 50), trt.scenes.random_mixed(300, 5, 96, 64, 4, 12), trt.scenes.random_spheres(6000, 96, 54, 3, 10)):
         osc, ocam, cam = both(trt, orc, desc)
         sc = trt.Scene.from_desc(desc, kind)
@@ -238,15 +246,12 @@ def test_binary_and_wide_nodes_agree(trt, orc, ctx, kind, regen_min):
             imgs.append((lin, st))
         assert np.array_equal(bits(imgs[0][0]), bits(imgs[1][0])) and imgs[0][1].rays == imgs[1][1].rays
         olin, ou8, ost, _ = osc.render(ocam, op)
-        if kind == 0:
-            assert imgs[0][1].rays == ost.rays and ulp_diff(imgs[0][0], olin).max() <= 1
-        else:
-            assert abs(int(imgs[0][1].rays) - int(ost.rays)) <= 16 and (ulp_diff(imgs[0][0], olin) > 1).any(axis=2).sum() <= 1
+        assert imgs[0][1].rays == ost.rays and ulp_diff(imgs[0][0], olin).max() <= 1
 
 
 def test_big_tree_render_matches_oracle(trt, orc, ctx):
     """20 k spheres (> 4096 nodes): the launcher picks the step-wise schedule by itself; SAH and reference kinds, both
-    against the oracle. Differences are allowed only for the grazing-hit class of DESIGN.md §4.3 (SAH), bounded here."""
+    equal to the oracle (the SAH walk replays the order-dependent rays of DESIGN.md §4.3 in the step-wise loop too)."""
     desc = trt.scenes.random_spheres(20_000, 160, 90, 4, 12)
     osc, ocam, cam = both(trt, orc, desc)
     p, op = params(trt, orc, desc)
@@ -256,10 +261,7 @@ def test_big_tree_render_matches_oracle(trt, orc, ctx):
         lin, u8, st = sc.render(ctx, cam, p)
         assert st.paths == ost.paths
         bad = (ulp_diff(lin, olin) > 1).any(axis=2)
-        if kind == 0:
-            assert st.rays == ost.rays and not bad.any()
-        else:
-            assert abs(int(st.rays) - int(ost.rays)) <= 64 and bad.sum() <= 2
+        assert st.rays == ost.rays and not bad.any()
         assert psnr8(u8, ou8) >= PSNR_MIN_DB
 
 

@@ -127,7 +127,9 @@ struct DevScene {
     const uint4* sphere_meta; const uint4* quad_meta; const float4* materials;
     const float4* quad_nn;                      // unit normal of every quad, precomputed on the host with HitRecord::new's operations
     const FlatPrim* flat; uint32_t n_flat;      // TRT_BVH_FLAT: primitives in reference leaf order (else null / 0)
-    const float4* nodes4; uint32_t n_nodes4;    // TRT_BVH_SAH: 4-wide nodes (8 float4 each, trt_scene.cpp collapse4) or null
+    const float4* nodes4; uint32_t n_nodes4;    // tree kinds: 4-wide nodes (8 float4 each, trt_scene.cpp collapse4) or null
+    const float4* nodes_ref4; uint32_t n_nodes_ref4;   // TRT_BVH_SAH: the REFERENCE-topology tree's wide nodes, for the rare replay (ordered_replay)
+    const float4* g_spheres; const float4* g_quads;    // global-memory copies of spheres / quads (the staged scene overrides those two)
     const float4* flat_cbox; float flat_bound;  // TRT_BVH_FLAT: conservative centre/half-width boxes (phase A), largest |coordinate|
     uint32_t root, n_nodes, n_spheres, n_quads, n_materials, ordered;
     float root_min[3], root_max[3];   // the root's own padded box (only consulted when counting events)
@@ -288,18 +290,32 @@ template <bool SMEM> TRT_DEV bool quad_hit(const DevScene& S, uint32_t idx, V3 o
 // A when its current ref is an interior node and in B when it is a leaf (possibly the leaf A just selected), so each
 // region's code is issued once per iteration for all lanes that need it instead of once per call site.
 struct Hit { float t; uint32_t ref; };
+// Ordered kinds cull a subtree whose box entry lies beyond the closest hit. The reference culls a LEAF the same way, but
+// against whatever hit its own left-to-right order has found by then — and a grazing sphere's computed t can be smaller
+// than the computed entry of its own box, so which of the two happens depends on that order. Culling
+// only beyond (1 + 2^-8) x the closest hit keeps every primitive whose t/entry disagreement is below 0.4 % in play (the
+// sphere's is bounded by ~sqrt(20 * 2^-24) = 0.1 %), which leaves the (t, rank)-smallest valid primitive as the answer —
+// the reference's — at the price of a few extra node visits.
+#ifndef TRT_SAH_CULL_MARGIN
+#define TRT_SAH_CULL_MARGIN 0.00390625f
+#endif
+TRT_DEV float cull_limit(float best) { return best + fabsf(best) * TRT_SAH_CULL_MARGIN; }
 
 // Resumable form: trav_begin() sets the state up, every trav_step() runs one iteration of the loop (region A, region B,
 // pop). closest_hit() is begin + step until done; the wavefront extend kernel interleaves steps of different rays.
 struct Trav {
     V3 o, d, inv; float t_min; bool tame;
-    uint32_t cur; int sp; Hit best; uint32_t best_rank;
+    uint32_t cur; int sp; Hit best;
+    float cur_s;        // ordered kinds: box entry of the child in `cur` (for a leaf: of the primitive's own box)
+    bool best_anom;     // ordered kinds: the closest hit's t is smaller than its own box's entry
+    bool replay;        // ordered kinds: this ray is being re-traced on the reference-topology tree (see needs_replay)
 };
 
 template <bool COUNT>
 TRT_DEV void trav_begin(Trav& T, const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
     T.o = o; T.d = d; T.t_min = t_min;
-    T.best.t = TRT_INF; T.best.ref = TRT_REF_INVALID; T.best_rank = 0xFFFFFFFFu; T.sp = 0;
+    T.best.t = TRT_INF; T.best.ref = TRT_REF_INVALID; T.sp = 0;
+    T.cur_s = 0.0f; T.best_anom = false; T.replay = false;
     T.cur = S.root;
     T.inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);           // aabb.rs:42, identical for every node of this ray
     T.tame = ray_is_tame(o, T.inv);
@@ -330,7 +346,7 @@ TRT_DEV void trav_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* s
         }
         if (COUNT) ec->node_visits += (rref == TRT_REF_INVALID) ? 0u : 2u;   // left.hit + right.hit
         bool pl, pr;
-        if (ORDERED) { pl = el > sl && !(T.best.t < sl); pr = er > sr && !(T.best.t < sr); }
+        if (ORDERED) { const float lim = cull_limit(T.best.t); pl = el > sl && !(lim < sl); pr = er > sr && !(lim < sr); }
         else { pl = el > sl && T.best.t > sl; pr = er > sr; }                // right: range end re-checked when it is entered
         pr = pr && rref != TRT_REF_INVALID;
         bool right_first = ORDERED && pl && pr && sr < sl;
@@ -338,9 +354,9 @@ TRT_DEV void trav_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* s
         float s1 = right_first ? sl : sr;
         bool p0 = right_first ? pr : pl, p1 = right_first ? pl : pr;
         if (p0) {
-            cur = c0;
+            cur = c0; if (ORDERED) T.cur_s = right_first ? sr : sl;
             if (p1) { TRT_ASSERT(T.sp < TRT_MAX_STACK); stack_ref[T.sp] = c1; stack_t[T.sp] = s1; ++T.sp; }
-        } else if (p1 && (ORDERED || T.best.t > s1)) cur = c1;
+        } else if (p1 && (ORDERED || T.best.t > s1)) { cur = c1; if (ORDERED) T.cur_s = s1; }
         else cur = TRT_REF_INVALID;
     }
     if (cur != TRT_REF_INVALID && (cur & TRT_REF_LEAF)) {
@@ -352,13 +368,12 @@ TRT_DEV void trav_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* s
         else { if (COUNT) ec->sphere_tests++; h = sphere_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : T.best.t, &t); }
         if (h) {
             if (!ORDERED) { T.best.t = t; T.best.ref = cur; }
-            else if (t < T.best.t) { T.best.t = t; T.best.ref = cur; T.best_rank = 0xFFFFFFFFu; }
-            else if (t == T.best.t) {
-                if (T.best_rank == 0xFFFFFFFFu)
-                    T.best_rank = (T.best.ref & TRT_REF_QUAD) ? ld4ua(S.quad_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y
-                                                              : ld4ua(S.sphere_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y;
-                uint32_t rk = (cur & TRT_REF_QUAD) ? ld4ua(S.quad_meta + idx).y : ld4ua(S.sphere_meta + idx).y;
-                if (rk < T.best_rank) { T.best.ref = cur; T.best_rank = rk; }
+            else if (t < T.best.t) { T.best.t = t; T.best.ref = cur; T.best_anom = T.cur_s > t; }
+            else if (t == T.best.t) {      // exact tie: the lower reference leaf rank wins (both ranks are fetched; ties are rare)
+                const uint32_t rb = (T.best.ref & TRT_REF_QUAD) ? ld4ua(S.quad_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y
+                                                                : ld4ua(S.sphere_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y;
+                const uint32_t rk = (cur & TRT_REF_QUAD) ? ld4ua(S.quad_meta + idx).y : ld4ua(S.sphere_meta + idx).y;
+                if (rk < rb) { T.best.ref = cur; T.best_anom = T.cur_s > t; }
             }
         }
         cur = TRT_REF_INVALID;
@@ -367,9 +382,23 @@ TRT_DEV void trav_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* s
     while (cur == TRT_REF_INVALID && T.sp > 0) {
         --T.sp;
         float s = stack_t[T.sp];
-        if (ORDERED ? !(T.best.t < s) : (T.best.t > s)) cur = stack_ref[T.sp];
+        if (ORDERED ? !(cull_limit(T.best.t) < s) : (T.best.t > s)) { cur = stack_ref[T.sp]; if (ORDERED) T.cur_s = s; }
     }
     T.cur = cur;
+}
+
+// The ordered walk returns the (t, rank)-smallest valid primitive W. That is the reference's answer whenever W's own box
+// entry does not exceed its t (nothing valid is closer, so the reference's scan cannot have narrowed its range below W's
+// box before reaching it). When it does exceed it — fp cancellation on a grazing hit, a few rays in 10^6 on the sphere
+// scenes — the reference's answer depends on its own visiting order, and the ray is replayed on the REFERENCE-topology
+// tree (wide nodes, global memory), which reproduces that order. Exact for every hit whose t/entry disagreement is below
+// the culling margin above (spheres: always); TRT_BVH_LBVH_DEVICE has no reference tree and keeps the W answer.
+template <bool ORDERED, bool SMEM> TRT_DEV Hit closest_hit4(const DevScene& S, V3 o, V3 d, float t_min);
+TRT_DEV bool needs_replay(const Trav& T, const DevScene& S) { return T.best_anom && !T.replay && T.best.ref != TRT_REF_INVALID && S.nodes_ref4 != nullptr; }
+TRT_DEV Hit ordered_replay(const DevScene& S, V3 o, V3 d, float t_min) {
+    DevScene R = S;
+    R.nodes4 = S.nodes_ref4; R.n_nodes4 = S.n_nodes_ref4; R.spheres = S.g_spheres; R.quads = S.g_quads;
+    return closest_hit4<false, false>(R, o, d, t_min);
 }
 
 template <bool ORDERED, bool SMEM, bool COUNT>
@@ -378,6 +407,7 @@ TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounter
     trav_begin<COUNT>(T, S, o, d, t_min, ec);
     uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
     while (T.cur != TRT_REF_INVALID) trav_step<ORDERED, SMEM, COUNT>(T, S, stack_ref, stack_t, ec);
+    if (ORDERED && !COUNT && needs_replay(T, S)) return ordered_replay(S, o, d, t_min);
     return T.best;
 }
 
@@ -392,9 +422,9 @@ TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounter
 //   its own box tested against the range the reference would use (lemma L: the skipped intermediate box cannot cull).
 // Either way only the number of dependent node fetches per ray changes (about half of the binary walk).
 template <bool ORDERED, bool SMEM>
-TRT_DEV void trav4_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* stack_t) {
+TRT_DEV void trav4_step(Trav& T, const DevScene& S, float t_min, uint32_t* stack_ref, float* stack_t) {   // t_min: the caller's (uniform) value, not a per-lane copy
     uint32_t cur = T.cur;
-    const V3 o = T.o, d = T.d, inv = T.inv; const float t_min = T.t_min;
+    const V3 o = T.o, d = T.d, inv = T.inv;
     if (!(cur & TRT_REF_LEAF)) {
         TRT_ASSERT(cur < S.n_nodes4);
         const float4* np = S.nodes4 + 8 * (size_t)cur;
@@ -411,7 +441,7 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* 
             slab(b0.y, b0.w, b1.y, b1.w, b2.y, b2.w, o, inv, t_min, &s3, &e3);
         }
         uint32_t r0 = __float_as_uint(rf.x), r1 = __float_as_uint(rf.y), r2 = __float_as_uint(rf.z), r3 = __float_as_uint(rf.w);
-        const float best = T.best.t;
+        const float best = ORDERED ? cull_limit(T.best.t) : T.best.t;
         TRT_ASSERT(T.sp + 3 <= TRT_MAX_STACK);
         if (ORDERED) {
             // a child that is not entered sorts last (key +inf) and carries TRT_REF_INVALID
@@ -427,7 +457,7 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* 
             if (r3 != TRT_REF_INVALID) { stack_ref[T.sp] = r3; stack_t[T.sp] = s3; ++T.sp; }
             if (r2 != TRT_REF_INVALID) { stack_ref[T.sp] = r2; stack_t[T.sp] = s2; ++T.sp; }
             if (r1 != TRT_REF_INVALID) { stack_ref[T.sp] = r1; stack_t[T.sp] = s1; ++T.sp; }
-            cur = r0;
+            cur = r0; T.cur_s = s0;
         } else {
             // bvh.rs:97: a later sibling is searched with the range end narrowed by everything before it -> re-checked when popped
             if (e3 > s3 && r3 != TRT_REF_INVALID) { stack_ref[T.sp] = r3; stack_t[T.sp] = s3; ++T.sp; }
@@ -444,13 +474,12 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* 
         else h = sphere_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : T.best.t, &t);
         if (h) {
             if (!ORDERED) { T.best.t = t; T.best.ref = cur; }
-            else if (t < T.best.t) { T.best.t = t; T.best.ref = cur; T.best_rank = 0xFFFFFFFFu; }
-            else if (t == T.best.t) {
-                if (T.best_rank == 0xFFFFFFFFu)
-                    T.best_rank = (T.best.ref & TRT_REF_QUAD) ? ld4ua(S.quad_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y
-                                                              : ld4ua(S.sphere_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y;
-                uint32_t rk = (cur & TRT_REF_QUAD) ? ld4ua(S.quad_meta + idx).y : ld4ua(S.sphere_meta + idx).y;
-                if (rk < T.best_rank) { T.best.ref = cur; T.best_rank = rk; }
+            else if (t < T.best.t) { T.best.t = t; T.best.ref = cur; T.best_anom = T.cur_s > t; }
+            else if (t == T.best.t) {      // exact tie: the lower reference leaf rank wins (both ranks are fetched; ties are rare)
+                const uint32_t rb = (T.best.ref & TRT_REF_QUAD) ? ld4ua(S.quad_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y
+                                                                : ld4ua(S.sphere_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y;
+                const uint32_t rk = (cur & TRT_REF_QUAD) ? ld4ua(S.quad_meta + idx).y : ld4ua(S.sphere_meta + idx).y;
+                if (rk < rb) { T.best.ref = cur; T.best_anom = T.cur_s > t; }
             }
         }
         cur = TRT_REF_INVALID;
@@ -458,16 +487,36 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* 
     while (cur == TRT_REF_INVALID && T.sp > 0) {
         --T.sp;
         const float s = stack_t[T.sp];
-        if (ORDERED ? !(T.best.t < s) : (T.best.t > s)) cur = stack_ref[T.sp];
+        if (ORDERED ? !(cull_limit(T.best.t) < s) : (T.best.t > s)) { cur = stack_ref[T.sp]; if (ORDERED) T.cur_s = s; }
     }
     T.cur = cur;
+}
+// One step of the wide walk, or — for a lane that is replaying its ray (needs_replay) — of the reference-order walk on the
+// reference tree's wide nodes in global memory. Sharing the loop and the stack keeps the rare replay out of the hot path's
+// register budget.
+template <bool ORDERED, bool SMEM>
+TRT_DEV void trav4_any_step(Trav& T, const DevScene& S, float t_min, uint32_t* stack_ref, float* stack_t) {
+    if (ORDERED && T.replay) {
+        DevScene R = S;
+        R.nodes4 = S.nodes_ref4; R.n_nodes4 = S.n_nodes_ref4; R.spheres = S.g_spheres; R.quads = S.g_quads;
+        trav4_step<false, false>(T, R, t_min, stack_ref, stack_t);
+    } else trav4_step<ORDERED, SMEM>(T, S, t_min, stack_ref, stack_t);
+}
+// restart the ray of a finished ordered walk in replay mode (root of the reference tree's wide nodes is 0 as well)
+TRT_DEV void begin_replay(Trav& T) {
+    T.replay = true; T.best_anom = false; T.cur = 0u; T.sp = 0;
+    T.best.t = TRT_INF; T.best.ref = TRT_REF_INVALID;
 }
 template <bool ORDERED, bool SMEM>
 TRT_DEV Hit closest_hit4(const DevScene& S, V3 o, V3 d, float t_min) {
     Trav T; EventCounters ec;
     trav_begin<false>(T, S, o, d, t_min, &ec);
     uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
-    while (T.cur != TRT_REF_INVALID) trav4_step<ORDERED, SMEM>(T, S, stack_ref, stack_t);
+    for (;;) {
+        while (T.cur != TRT_REF_INVALID) trav4_any_step<ORDERED, SMEM>(T, S, t_min, stack_ref, stack_t);
+        if (!(ORDERED && needs_replay(T, S))) break;
+        begin_replay(T);
+    }
     return T.best;
 }
 

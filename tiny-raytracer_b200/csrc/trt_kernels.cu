@@ -206,7 +206,7 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
     const DevParams& P = A.p;
     const uint32_t lane = threadIdx.x & 31u;
     Trav T; T.cur = TRT_REF_INVALID; T.sp = 0; T.best.t = TRT_INF; T.best.ref = TRT_REF_INVALID;
-    T.o = mk(0, 0, 0); T.d = mk(0, 0, 1); T.inv = mk(0, 0, 1); T.t_min = P.t_min; T.tame = false; T.best_rank = 0xFFFFFFFFu;
+    T.o = mk(0, 0, 0); T.d = mk(0, 0, 1); T.inv = mk(0, 0, 1); T.t_min = P.t_min; T.tame = false;
     uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
     V3 atten = mk(1, 1, 1), color = mk(0, 0, 0);
     uint32_t pixel = 0, px = 0, py = 0, s_cur = 0, s_end = 0, remain = 0, k = 0;
@@ -219,7 +219,10 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
     for (;;) {
         // ---- T: one step of cpu.rs:48 for every lane whose ray is in flight
         if (T.cur != TRT_REF_INVALID) {
-            if (KIND == 3 || KIND == 4) trav4_step<KIND == 3, SMEM>(T, S, stack_ref, stack_t);
+            if (KIND == 3 || KIND == 4) {
+                trav4_any_step<KIND == 3, SMEM>(T, S, P.t_min, stack_ref, stack_t);
+                if (KIND == 3 && T.cur == TRT_REF_INVALID && needs_replay(T, S)) begin_replay(T);     // rare: DESIGN.md §4.3
+            }
             else trav_step<KIND == 1, SMEM, COUNT>(T, S, stack_ref, stack_t, &ec);
         }
         const bool tracing = T.cur != TRT_REF_INVALID;
@@ -232,7 +235,8 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
         sf.point = sf.normal = sf.rgb = mk(0, 0, 0);
         bool scatter = false;
         if (in_s && alive) {
-            const Hit h = T.best;
+            Hit h = T.best;
+            if (KIND == 1 && !COUNT && needs_replay(T, S)) h = ordered_replay(S, T.o, T.d, P.t_min);   // rare: DESIGN.md §4.3 (binary walk)
             if (h.ref == TRT_REF_INVALID) color = color + atten * mk(P.bg[0], P.bg[1], P.bg[2]);
             else {
                 sf = hit_record<SMEM>(S, h, T.o, T.d);

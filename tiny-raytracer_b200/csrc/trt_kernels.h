@@ -17,7 +17,8 @@ struct SceneView {   // device copy of trt::FlatScene
     const void* flat_cbox_host;// the same boxes on the host: copied into the kernel parameters of k_render_mega_flat
     float flat_bound;          // largest |coordinate| of any flat-list box, or < 0: phase A disabled (literal scan only)
     uint32_t n_flat;
-    const void* nodes4; uint32_t n_nodes4;   // TRT_BVH_SAH: the tree collapsed to 4-wide nodes (8 float4 each) or null
+    const void* nodes4; uint32_t n_nodes4;   // tree kinds: the tree collapsed to 4-wide nodes (8 float4 each) or null
+    const void* nodes_ref4; uint32_t n_nodes_ref4;   // TRT_BVH_SAH: wide nodes of the reference-topology tree (replay of order-dependent rays) or null
     uint32_t root, n_nodes, n_spheres, n_quads, n_materials;
     uint32_t kind;             // trt_bvh_kind after AUTO resolution: 0 reference, 1 SAH, 2 flat
     float root_min[3], root_max[3];

@@ -377,6 +377,11 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
         collapse4(*tree, prims, flat);
         if (3 * flat.max_depth4 + 1 > TRT_MAX_STACK) { flat.nodes4.clear(); flat.n_nodes4 = 0; }   // walk the binary tree instead
     }
+    if (bvh_kind == 1 && n) {   // the reference-topology tree too: the ordered walk replays its rare order-dependent rays on it
+        FlatScene tmp;
+        collapse4(ref_tree, prims, tmp);
+        if (3 * tmp.max_depth4 + 1 <= TRT_MAX_STACK) { flat.nodes_ref4.swap(tmp.nodes4); flat.n_nodes_ref4 = tmp.n_nodes4; }
+    }
     if (flat.max_depth > TRT_MAX_STACK) { *err = "trt_scene_commit: tree deeper than the traversal stack"; return false; }
 
     flat.spheres.resize(ns); flat.sphere_meta.resize(ns); flat.quads.resize(4 * (size_t)nq); flat.quad_nn.resize(nq); flat.quad_meta.resize(nq);
