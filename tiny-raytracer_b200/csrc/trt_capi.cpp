@@ -23,7 +23,7 @@ static int fail_cuda(const char* what, cudaError_t e) {
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_cuda(#call, e_); } while (0)
 
 struct DeviceCopy {
-    uint64_t version = 0; void* buf = nullptr; size_t bytes = 0; trtk::SceneView view{};
+    uint64_t version = 0; void* buf = nullptr; size_t bytes = 0; trtk::SceneView view{}; uint32_t root_ref4 = 0;
 };
 struct trt_scene {
     trt::HostScene host;
@@ -192,13 +192,13 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
     const trt::FlatScene& f = s->host.flat;
     const bool device_build = f.bvh_kind == TRT_BVH_LBVH_DEVICE;
     const size_t n_prims = s->host.prims.size();
-    size_t sz[11] = {device_build ? 64 * (n_prims - 1) : f.nodes.size() * 16, f.spheres.size() * 16, f.quads.size() * 16, f.sphere_meta.size() * 16, f.quad_meta.size() * 16, f.materials.size() * 16, f.flat.size() * 16, f.quad_nn.size() * 16, f.flat_cbox.size() * 16, device_build ? 128 * (n_prims - 1) : f.nodes4.size() * 16, f.nodes_ref4.size() * 16};
+    size_t sz[11] = {device_build ? 64 * (n_prims - 1) : f.nodes.size() * 16, f.spheres.size() * 16, f.quads.size() * 16, f.sphere_meta.size() * 16, f.quad_meta.size() * 16, f.materials.size() * 16, f.flat.size() * 16, f.quad_nn.size() * 16, f.flat_cbox.size() * 16, device_build ? 128 * (n_prims - 1) : f.nodes4.size() * 16, device_build ? 128 * (n_prims - 1) : f.nodes_ref4.size() * 16};
     const void* src[11] = {f.nodes.data(), f.spheres.data(), f.quads.data(), f.sphere_meta.data(), f.quad_meta.data(), f.materials.data(), f.flat.data(), f.quad_nn.data(), f.flat_cbox.data(), f.nodes4.data(), f.nodes_ref4.data()};
     size_t off[11], total = 0;
     for (int i = 0; i < 11; ++i) { off[i] = total; total += align_up(sz[i] ? sz[i] : 16); }
     if (dc.buf && dc.bytes < total) { cudaFree(dc.buf); dc.buf = nullptr; }
     if (!dc.buf) { CU(cudaMalloc(&dc.buf, total)); dc.bytes = total; }
-    for (int i = 0; i < 11; ++i) if (sz[i] && !(device_build && (i == 0 || i == 9))) CU(cudaMemcpyAsync((char*)dc.buf + off[i], src[i], sz[i], cudaMemcpyHostToDevice, c->stream));
+    for (int i = 0; i < 11; ++i) if (sz[i] && !(device_build && (i == 0 || i == 9 || i == 10))) CU(cudaMemcpyAsync((char*)dc.buf + off[i], src[i], sz[i], cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (device_build) {
         // Node::new on the GPU: Morton codes + radix sort + Karras hierarchy + bottom-up boxes (trt_lbvh.cu)
@@ -208,9 +208,15 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_boxes, f.lbvh_boxes.data(), f.lbvh_boxes.size() * 16, cudaMemcpyHostToDevice, c->stream);
         uint32_t depth = 0; float ms = 0.f;
         if (e == cudaSuccess) e = trtk::build_lbvh(d_boxes, (uint32_t)n_prims, (char*)dc.buf + off[0], (char*)dc.buf + off[9], d_tmp, &depth, &ms, c->stream);
-        cudaFree(d_boxes); if (d_tmp) cudaFree(d_tmp);
+        if (d_tmp) cudaFree(d_tmp);
+        // Node::new itself on the device: the reference leaf order (tie rule) and the reference tree's wide nodes (replay)
+        uint32_t root_ref = 0; float ms_ref = 0.f; void* d_tmp2 = nullptr;
+        if (e == cudaSuccess) e = cudaMalloc(&d_tmp2, trtk::ref_order_tmp_bytes((uint32_t)n_prims));
+        if (e == cudaSuccess) e = trtk::build_reference_order(d_boxes, (uint32_t)n_prims, (char*)dc.buf + off[3], (char*)dc.buf + off[4], (char*)dc.buf + off[10], d_tmp2, &root_ref, &ms_ref, c->stream);
+        if (d_tmp2) cudaFree(d_tmp2);
+        cudaFree(d_boxes);
         if (e != cudaSuccess) return fail_cuda("trt_scene_upload: device BVH build", e);
-        s->host.flat.max_depth = depth; s->host.device_build_ms = ms;
+        s->host.flat.max_depth = depth; s->host.device_build_ms = ms + ms_ref; dc.root_ref4 = root_ref;
         if (depth > TRT_MAX_STACK) return fail(TRT_ERR_UNSUPPORTED, "trt_scene_upload: device-built tree deeper than the traversal stack; commit with TRT_BVH_SAH");
     }
     trtk::SceneView& v = dc.view;
@@ -220,7 +226,8 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
     v.n_materials = (uint32_t)(f.materials.size() / 2); v.kind = device_build ? 1u : (uint32_t)f.bvh_kind;   // the device-built tree is walked near-child-first like SAH
     v.flat = f.flat.empty() ? nullptr : b + off[6]; v.n_flat = (uint32_t)(f.flat.size() / 6);
     v.nodes4 = f.nodes4.empty() ? nullptr : b + off[9]; v.n_nodes4 = f.n_nodes4;
-    v.nodes_ref4 = f.nodes_ref4.empty() ? nullptr : b + off[10]; v.n_nodes_ref4 = f.n_nodes_ref4;
+    v.nodes_ref4 = f.nodes_ref4.empty() ? nullptr : b + off[10]; v.n_nodes_ref4 = f.n_nodes_ref4; v.root_ref4 = 0;
+    if (device_build) { v.nodes_ref4 = b + off[10]; v.n_nodes_ref4 = (uint32_t)(n_prims - 1); v.root_ref4 = dc.root_ref4; }
     if (device_build && 3 * ((s->host.flat.max_depth + 1) / 2) + 1 <= TRT_MAX_STACK) { v.nodes4 = b + off[9]; v.n_nodes4 = (uint32_t)(n_prims - 1); }
     v.flat_cbox = f.flat_cbox.empty() ? nullptr : b + off[8]; v.flat_cbox_host = f.flat_cbox.empty() ? nullptr : f.flat_cbox.data(); v.flat_bound = f.flat_bound;
     const float inf = std::numeric_limits<float>::infinity();

@@ -128,7 +128,7 @@ struct DevScene {
     const float4* quad_nn;                      // unit normal of every quad, precomputed on the host with HitRecord::new's operations
     const FlatPrim* flat; uint32_t n_flat;      // TRT_BVH_FLAT: primitives in reference leaf order (else null / 0)
     const float4* nodes4; uint32_t n_nodes4;    // tree kinds: 4-wide nodes (8 float4 each, trt_scene.cpp collapse4) or null
-    const float4* nodes_ref4; uint32_t n_nodes_ref4;   // TRT_BVH_SAH: the REFERENCE-topology tree's wide nodes, for the rare replay (ordered_replay)
+    const float4* nodes_ref4; uint32_t n_nodes_ref4, root_ref4;   // ordered kinds: the REFERENCE-topology tree's wide nodes, for the rare replay (ordered_replay)
     const float4* g_spheres; const float4* g_quads;    // global-memory copies of spheres / quads (the staged scene overrides those two)
     const float4* flat_cbox; float flat_bound;  // TRT_BVH_FLAT: conservative centre/half-width boxes (phase A), largest |coordinate|
     uint32_t root, n_nodes, n_spheres, n_quads, n_materials, ordered;
@@ -397,7 +397,7 @@ template <bool ORDERED, bool SMEM> TRT_DEV Hit closest_hit4(const DevScene& S, V
 TRT_DEV bool needs_replay(const Trav& T, const DevScene& S) { return T.best_anom && !T.replay && T.best.ref != TRT_REF_INVALID && S.nodes_ref4 != nullptr; }
 TRT_DEV Hit ordered_replay(const DevScene& S, V3 o, V3 d, float t_min) {
     DevScene R = S;
-    R.nodes4 = S.nodes_ref4; R.n_nodes4 = S.n_nodes_ref4; R.spheres = S.g_spheres; R.quads = S.g_quads;
+    R.nodes4 = S.nodes_ref4; R.n_nodes4 = S.n_nodes_ref4; R.root = S.root_ref4; R.spheres = S.g_spheres; R.quads = S.g_quads;
     return closest_hit4<false, false>(R, o, d, t_min);
 }
 
@@ -502,9 +502,9 @@ TRT_DEV void trav4_any_step(Trav& T, const DevScene& S, float t_min, uint32_t* s
         trav4_step<false, false>(T, R, t_min, stack_ref, stack_t);
     } else trav4_step<ORDERED, SMEM>(T, S, t_min, stack_ref, stack_t);
 }
-// restart the ray of a finished ordered walk in replay mode (root of the reference tree's wide nodes is 0 as well)
-TRT_DEV void begin_replay(Trav& T) {
-    T.replay = true; T.best_anom = false; T.cur = 0u; T.sp = 0;
+// restart the ray of a finished ordered walk in replay mode
+TRT_DEV void begin_replay(Trav& T, const DevScene& S) {
+    T.replay = true; T.best_anom = false; T.cur = S.root_ref4; T.sp = 0;
     T.best.t = TRT_INF; T.best.ref = TRT_REF_INVALID;
 }
 template <bool ORDERED, bool SMEM>
@@ -515,7 +515,7 @@ TRT_DEV Hit closest_hit4(const DevScene& S, V3 o, V3 d, float t_min) {
     for (;;) {
         while (T.cur != TRT_REF_INVALID) trav4_any_step<ORDERED, SMEM>(T, S, t_min, stack_ref, stack_t);
         if (!(ORDERED && needs_replay(T, S))) break;
-        begin_replay(T);
+        begin_replay(T, S);
     }
     return T.best;
 }

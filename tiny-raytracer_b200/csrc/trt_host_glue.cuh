@@ -14,7 +14,7 @@ inline DevScene dev_scene(const SceneView& v) {
     s.sphere_meta = (const uint4*)v.sphere_meta; s.quad_meta = (const uint4*)v.quad_meta; s.quad_nn = (const float4*)v.quad_nn; s.materials = (const float4*)v.materials;
     s.flat = (const FlatPrim*)v.flat; s.n_flat = v.n_flat; s.flat_cbox = (const float4*)v.flat_cbox; s.flat_bound = v.flat_bound;
     s.nodes4 = (const float4*)v.nodes4; s.n_nodes4 = v.n_nodes4;
-    s.nodes_ref4 = (const float4*)v.nodes_ref4; s.n_nodes_ref4 = v.n_nodes_ref4; s.g_spheres = s.spheres; s.g_quads = s.quads;
+    s.nodes_ref4 = (const float4*)v.nodes_ref4; s.n_nodes_ref4 = v.n_nodes_ref4; s.root_ref4 = v.root_ref4; s.g_spheres = s.spheres; s.g_quads = s.quads;
     s.root = v.root; s.n_nodes = v.n_nodes; s.n_spheres = v.n_spheres; s.n_quads = v.n_quads; s.n_materials = v.n_materials;
     s.ordered = v.kind == 1 ? 1u : 0u;
     for (int i = 0; i < 3; ++i) { s.root_min[i] = v.root_min[i]; s.root_max[i] = v.root_max[i]; }

@@ -221,7 +221,7 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
         if (T.cur != TRT_REF_INVALID) {
             if (KIND == 3 || KIND == 4) {
                 trav4_any_step<KIND == 3, SMEM>(T, S, P.t_min, stack_ref, stack_t);
-                if (KIND == 3 && T.cur == TRT_REF_INVALID && needs_replay(T, S)) begin_replay(T);     // rare: DESIGN.md §4.3
+                if (KIND == 3 && T.cur == TRT_REF_INVALID && needs_replay(T, S)) begin_replay(T, S);     // rare: DESIGN.md §4.3
             }
             else trav_step<KIND == 1, SMEM, COUNT>(T, S, stack_ref, stack_t, &ec);
         }

@@ -18,7 +18,7 @@ struct SceneView {   // device copy of trt::FlatScene
     float flat_bound;          // largest |coordinate| of any flat-list box, or < 0: phase A disabled (literal scan only)
     uint32_t n_flat;
     const void* nodes4; uint32_t n_nodes4;   // tree kinds: the tree collapsed to 4-wide nodes (8 float4 each) or null
-    const void* nodes_ref4; uint32_t n_nodes_ref4;   // TRT_BVH_SAH: wide nodes of the reference-topology tree (replay of order-dependent rays) or null
+    const void* nodes_ref4; uint32_t n_nodes_ref4, root_ref4;   // TRT_BVH_SAH: wide nodes of the reference-topology tree (replay of order-dependent rays) or null
     uint32_t root, n_nodes, n_spheres, n_quads, n_materials;
     uint32_t kind;             // trt_bvh_kind after AUTO resolution: 0 reference, 1 SAH, 2 flat
     float root_min[3], root_max[3];
@@ -31,6 +31,11 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
 size_t lbvh_tmp_bytes(uint32_t n);
 // Builds the 64-byte node array (n - 1 nodes) and, if d_nodes4 is not null, its 4-wide form (128 bytes per node) on the device from per-primitive padded boxes (2 float4 each, leaf-ref bits in bmin.w).
 cudaError_t build_lbvh(const void* d_boxes, uint32_t n, void* d_nodes, void* d_nodes4, void* d_tmp, uint32_t* h_depth, float* h_ms, cudaStream_t st);
+size_t ref_order_tmp_bytes(uint32_t n);
+// Node::new (hittable/bvh.rs:42-84) on the device: the reference leaf rank of every primitive into meta.y and the wide nodes
+// of the reference-topology tree (8 float4 per node, n - 1 nodes, root index in *h_root) into d_nodes_ref4.
+cudaError_t build_reference_order(const void* d_boxes, uint32_t n, void* d_sphere_meta, void* d_quad_meta, void* d_nodes_ref4,
+                                  void* d_tmp, uint32_t* h_root, float* h_ms, cudaStream_t st);
 size_t wavefront_scratch_bytes(uint32_t n_slots);
 // Runs the whole wavefront render (host loop inside; synchronises the stream). h_rays_paths[0] = rays, [1] = paths.
 cudaError_t launch_render_wavefront(const SceneView& v, const trt_camera& cam, const trt_params& p, double* d_sum64,

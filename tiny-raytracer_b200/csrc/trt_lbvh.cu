@@ -191,6 +191,110 @@ __global__ void k_lbvh_collapse4(const float4* __restrict__ nodes, uint32_t n, f
     out[7] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// ------------------------------------------------------------------ the REFERENCE tree on the device: Node::new, hittable/bvh.rs:42-84
+// The device-built scene still needs the reference's left-to-right leaf order (exact-t ties go to the lower rank, and the
+// rare order-dependent rays of DESIGN.md §4.3 are replayed in that order). Node::new is recursive, but every level of it is
+// data-parallel: all slices of one depth are disjoint ranges of one permutation. Per level:
+//   k_ref_bbox   union of the padded boxes of every slice of >= 2 primitives (ordered-int atomics, one per warp when a
+//                warp lies inside one slice); the box is also stored into the parent's node record (the child side)
+//   k_ref_keys   slices of >= 3: key = (slice start, f32::total_cmp key of bbox.min[longest axis]); slices of 1 or 2 keep
+//                their order (bvh.rs:58-60): key = (slice start, position)
+//   cub radix sort of (key, primitive): stable, and the slice start in the high word keeps every slice in place
+//   k_ref_split  mid = len/2 (bvh.rs:75); the node of slice [lo,hi) is number mid-1 (every boundary between two positions
+//                is the split of exactly one slice, so the n-1 nodes get distinct numbers); child refs and the boxes of
+//                single-primitive children are written now, boxes of bigger children by the next level's k_ref_bbox
+// ceil(log2 n) levels; 10^6 primitives: 20 sorts of 52-bit keys.
+struct RefSeg { uint32_t lo, hi, parent, side; };   // per position: its slice, the node that owns the slice as a child, which side
+
+__global__ void k_ref_init(uint32_t n, uint32_t* order, RefSeg* seg) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    order[i] = i;                                  // World insertion order (hittable/world.rs:23-26)
+    seg[i].lo = 0; seg[i].hi = n; seg[i].parent = 0xFFFFFFFFu; seg[i].side = 0;
+}
+__global__ void k_ref_bbox_init(uint32_t n, int* bb) {   // bb[6n]: min x,y,z then max x,y,z, indexed by slice start
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int a = 0; a < 3; ++a) { bb[(size_t)a * n + i] = 0x7FFFFFFF; bb[(size_t)(3 + a) * n + i] = (int)0x80000000; }
+}
+__global__ void k_ref_bbox(const float4* __restrict__ boxes, const uint32_t* __restrict__ order, const RefSeg* __restrict__ seg, uint32_t n, int* bb) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = i < n;
+    RefSeg s = ok ? seg[i] : RefSeg{0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0};
+    const bool act = ok && s.hi - s.lo >= 2;
+    int v[6];
+    if (act) {
+        const uint32_t p = order[i];
+        const float4 lo = boxes[2 * (size_t)p], hi = boxes[2 * (size_t)p + 1];
+        v[0] = f2ord(lo.x); v[1] = f2ord(lo.y); v[2] = f2ord(lo.z); v[3] = f2ord(hi.x); v[4] = f2ord(hi.y); v[5] = f2ord(hi.z);
+    } else { v[0] = v[1] = v[2] = 0x7FFFFFFF; v[3] = v[4] = v[5] = (int)0x80000000; }
+    const uint32_t lo0 = __shfl_sync(0xFFFFFFFFu, s.lo, 0);
+    if (__all_sync(0xFFFFFFFFu, act && s.lo == lo0)) {           // the whole warp inside one slice: one atomic per plane
+        for (int a = 0; a < 3; ++a) { v[a] = __reduce_min_sync(0xFFFFFFFFu, v[a]); v[3 + a] = __reduce_max_sync(0xFFFFFFFFu, v[3 + a]); }
+        if ((threadIdx.x & 31) == 0)
+            for (int a = 0; a < 3; ++a) { atomicMin(&bb[(size_t)a * n + lo0], v[a]); atomicMax(&bb[(size_t)(3 + a) * n + lo0], v[3 + a]); }
+    } else if (act) {
+        for (int a = 0; a < 3; ++a) { atomicMin(&bb[(size_t)a * n + s.lo], v[a]); atomicMax(&bb[(size_t)(3 + a) * n + s.lo], v[3 + a]); }
+    }
+}
+// node record (trt_layout.h) of node `id`, child `side`: plane k (min x,y,z, max x,y,z) is float 2k + side, the ref float 12 + side
+__device__ __forceinline__ void ref_put_child(float4* nodes, uint32_t id, uint32_t side, const float b[6], uint32_t ref) {
+    float* r = (float*)(nodes + 4 * (size_t)id);
+    for (int k = 0; k < 6; ++k) r[2 * k + side] = b[k];
+    r[12 + side] = __uint_as_float(ref);
+}
+__global__ void k_ref_keys(const float4* __restrict__ boxes, const uint32_t* __restrict__ order, const RefSeg* __restrict__ seg, uint32_t n,
+                           const int* __restrict__ bb, float4* nodes, unsigned long long* keys) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RefSeg s = seg[i];
+    const uint32_t len = s.hi - s.lo;
+    uint32_t low = i - s.lo;
+    if (len >= 2) {
+        float b[6];
+        for (int k = 0; k < 6; ++k) b[k] = ord2f(bb[(size_t)k * n + s.lo]);
+        if (i == s.lo && s.parent != 0xFFFFFFFFu) {              // this slice's box belongs into its parent's record
+            const uint32_t clen = len, cmid = s.lo + (clen == 2 ? 1 : clen / 2);
+            ref_put_child(nodes, s.parent, s.side, b, cmid - 1);
+        }
+        if (len >= 3) {
+            const float s0 = b[3] - b[0], s1 = b[4] - b[1], s2 = b[5] - b[2];
+            const int axis = (s0 > s1) ? ((s0 > s2) ? 0 : 2) : ((s1 > s2) ? 1 : 2);        // hittable/aabb.rs:63-78
+            const float4 lo = boxes[2 * (size_t)order[i]];
+            const float m = axis == 0 ? lo.x : (axis == 1 ? lo.y : lo.z);
+            low = (uint32_t)f2ord(m) ^ 0x80000000u;                                          // total_cmp order as unsigned
+        }
+    }
+    keys[i] = ((unsigned long long)s.lo << 32) | low;
+}
+__global__ void k_ref_split(const float4* __restrict__ boxes, const uint32_t* __restrict__ order, RefSeg* seg, uint32_t n, float4* nodes) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RefSeg s = seg[i];
+    const uint32_t len = s.hi - s.lo;
+    if (len < 2) return;
+    const uint32_t mid = s.lo + (len == 2 ? 1 : len / 2), id = mid - 1;
+    const uint32_t side = i >= mid ? 1u : 0u;
+    const uint32_t clo = side ? mid : s.lo, chi = side ? s.hi : mid;
+    if (chi - clo == 1) {                                        // single-primitive child: its own padded box and leaf ref
+        const uint32_t p = order[i];
+        const float4 lo = boxes[2 * (size_t)p], hi = boxes[2 * (size_t)p + 1];
+        const float b[6] = {lo.x, lo.y, lo.z, hi.x, hi.y, hi.z};
+        ref_put_child(nodes, id, side, b, __float_as_uint(lo.w));
+    }
+    s.lo = clo; s.hi = chi; s.parent = id; s.side = side;
+    seg[i] = s;
+}
+// rank of every primitive = its final position; stored where the traversal reads it (meta.y, trt_layout.h)
+__global__ void k_ref_ranks(const float4* __restrict__ boxes, const uint32_t* __restrict__ order, uint32_t n, uint4* sphere_meta, uint4* quad_meta) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t p = order[i];
+    const uint32_t ref = __float_as_uint(boxes[2 * (size_t)p].w);
+    uint4* m = (ref & TRT_REF_QUAD) ? quad_meta + (ref & TRT_REF_INDEX_MASK) : sphere_meta + (ref & TRT_REF_INDEX_MASK);
+    m->y = i;
+}
+
 } // namespace
 
 namespace trtk {
@@ -240,6 +344,60 @@ cudaError_t build_lbvh(const void* d_boxes, uint32_t n, void* d_nodes, void* d_n
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e == cudaSuccess) { *h_depth = hb.depth; float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); *h_ms = ms; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return e;
+}
+
+size_t ref_order_tmp_bytes(uint32_t n) {
+    size_t sort_tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 64);
+    return 2 * al(8ull * n) + 2 * al(4ull * n) + al(16ull * n) + al(24ull * n) + al(64ull * n) + al(sort_tmp);
+}
+
+// Node::new on the device (see the k_ref_* kernels): writes every primitive's reference leaf rank into meta.y and the
+// reference tree's wide nodes (128 bytes per node, n - 1 nodes, root = *h_root) into d_nodes_ref4.
+cudaError_t build_reference_order(const void* d_boxes, uint32_t n, void* d_sphere_meta, void* d_quad_meta, void* d_nodes_ref4,
+                                  void* d_tmp, uint32_t* h_root, float* h_ms, cudaStream_t st) {
+    if (n < 2) return cudaErrorInvalidValue;
+    char* p = (char*)d_tmp;
+    unsigned long long* keys = (unsigned long long*)p; p += al(8ull * n);
+    unsigned long long* keys_s = (unsigned long long*)p; p += al(8ull * n);
+    uint32_t* order = (uint32_t*)p; p += al(4ull * n);
+    uint32_t* order_s = (uint32_t*)p; p += al(4ull * n);
+    RefSeg* seg = (RefSeg*)p; p += al(16ull * n);
+    int* bb = (int*)p; p += al(24ull * n);
+    float4* nodes = (float4*)p; p += al(64ull * n);
+    void* sort_tmp = p;
+    size_t sort_bytes = 0;
+    int seg_bits = 1; while ((1ull << seg_bits) < n) ++seg_bits;
+    const int end_bit = 32 + seg_bits;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, end_bit);
+    const float4* boxes = (const float4*)d_boxes;
+    cudaEvent_t e0, e1; cudaError_t e;
+    if ((e = cudaEventCreate(&e0)) != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&e1)) != cudaSuccess) { cudaEventDestroy(e0); return e; }
+    const unsigned g = (n + 255) / 256;
+    cudaEventRecord(e0, st);
+    k_ref_init<<<g, 256, 0, st>>>(n, order, seg);
+    int levels = 0; while ((1ull << levels) < n) ++levels;            // ceil(log2 n): the longest slice halves (rounded up) per level
+    for (int l = 0; l <= levels; ++l) {                                // one extra pass stores the boxes of the last two-primitive slices
+        k_ref_bbox_init<<<g, 256, 0, st>>>(n, bb);
+        k_ref_bbox<<<g, 256, 0, st>>>(boxes, order, seg, n, bb);
+        k_ref_keys<<<g, 256, 0, st>>>(boxes, order, seg, n, bb, nodes, keys);
+        if (l == levels) break;
+        e = cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys, keys_s, order, order_s, (int)n, 0, end_bit, st);
+        if (e != cudaSuccess) break;
+        uint32_t* t = order; order = order_s; order_s = t;
+        k_ref_split<<<g, 256, 0, st>>>(boxes, order, seg, n, nodes);
+    }
+    if (e == cudaSuccess) {
+        k_ref_ranks<<<g, 256, 0, st>>>(boxes, order, n, (uint4*)d_sphere_meta, (uint4*)d_quad_meta);
+        k_lbvh_collapse4<<<g, 256, 0, st>>>(nodes, n, (float4*)d_nodes_ref4);
+        cudaEventRecord(e1, st);
+        e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e == cudaSuccess) { float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); *h_ms = ms; *h_root = (n == 2 ? 1u : n / 2) - 1u; }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return e;
