@@ -37,7 +37,8 @@ typedef enum trt_bvh_kind {
     TRT_BVH_FLAT = 2,        /* no tree: <= 64 primitives as a list in reference leaf order; reference results by construction */
     TRT_BVH_AUTO = 3,        /* FLAT when the scene has <= 64 primitives (fastest there, exact by construction), else SAH */
     TRT_BVH_LBVH_DEVICE = 4  /* built on the GPU during trt_scene_upload (Morton codes + radix sort + Karras), walked like SAH;
-                                no host tree: exact-t ties between different primitives go to the lower prim_id */
+                                the reference's own Node::new also runs there (level-parallel), so ties and the replay of
+                                order-dependent rays follow the reference leaf order exactly as with TRT_BVH_SAH */
 } trt_bvh_kind;
 
 /* Which kernel family renders. */

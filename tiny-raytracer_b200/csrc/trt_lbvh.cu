@@ -9,6 +9,9 @@
 //   5. k_lbvh_refit    bottom-up boxes: the second child to arrive at a node merges (atomic flag per node)
 //   6. k_lbvh_emit     the 64-byte node records of trt_layout.h (both children's boxes + child refs in the parent);
 //                      also the tree depth (needed: the traversal stack holds TRT_MAX_STACK entries)
+//   7. k_lbvh_collapse4  the 4-wide form of every node
+//   8. k_ref_*         the reference's own Node::new, level by level (reference leaf ranks + the reference tree for the replay
+//                      of order-dependent rays); see below
 // The leaf boxes are the primitives' own padded boxes computed on the host with the reference's arithmetic
 // (hittable/aabb.rs:13-20), interior boxes are exact min/max unions, so the culling argument of DESIGN.md §4.2 holds
 // unchanged; the tree is walked near-child-first like the SAH tree.

@@ -346,9 +346,8 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
     std::vector<uint32_t> order(n);
     for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
     if (device_build) {
-        // TRT_BVH_LBVH_DEVICE: no host tree at all. Ties are broken by prim_id instead of the reference's leaf order
-        // (which only a host build of the reference tree could give), and the node array is produced by trt_lbvh.cu
-        // during trt_scene_upload from these per-primitive boxes.
+        // TRT_BVH_LBVH_DEVICE: no host tree at all. The node arrays AND the reference leaf ranks (meta.y, placeholder here)
+        // are produced by trt_lbvh.cu during trt_scene_upload from these per-primitive boxes.
         for (size_t i = 0; i < n; ++i) leaf_rank[i] = (uint32_t)i;
         flat.lbvh_boxes.resize(2 * n);
         for (size_t i = 0; i < n; ++i) {
