@@ -118,7 +118,8 @@ int trt_scene_num_prims(trt_scene* scene, uint32_t* out);
 
 /* World::get_bvh (hittable/world.rs:43-45): builds the tree on the host. Does not touch the GPU. */
 int trt_scene_commit(trt_scene* scene, int bvh_kind);
-/* left-to-right leaf order of the reference-topology tree, indexed by prim_id (after commit) */
+/* left-to-right leaf order of the reference-topology tree, indexed by prim_id (after commit; for TRT_BVH_LBVH_DEVICE the
+ * order is computed on the GPU and is available after trt_scene_upload, prim_id order before) */
 int trt_scene_leaf_ranks(trt_scene* scene, uint32_t* rank_of_prim);
 int trt_scene_bvh_info(trt_scene* scene, uint32_t* n_nodes, uint32_t* max_depth, float* sah_cost);
 /* Seconds-scale costs of the last commit / upload: host build time of trt_scene_commit and, for TRT_BVH_LBVH_DEVICE, the

@@ -513,6 +513,27 @@ def test_device_built_bvh(trt, orc, ctx):
         assert ulp_diff(lin, olin).max() <= 1 and psnr8(u8, ou8) >= PSNR_MIN_DB
 
 
+@pytest.mark.parametrize("scene", ["mixed2", "mixed3", "mixed5", "mixed800", "cornell", "final", "spheres30k", "dups"])
+def test_device_node_new_gives_the_reference_leaf_order(trt, orc, ctx, scene):
+    """Node::new (bvh.rs:42-84) run level by level on the GPU must produce exactly the leaf order of the host builder and of
+    the oracle's independent builder: same longest-axis choice, stable sort with total_cmp, unsorted pairs, split at n/2.
+    `dups` is 600 primitives drawn from 40 distinct ones, so the sort is full of equal keys and only stability decides."""
+    S = trt.scenes
+    desc = {"mixed2": lambda: S.random_mixed(2, 3), "mixed3": lambda: S.random_mixed(3, 4), "mixed5": lambda: S.random_mixed(5, 8),
+            "mixed800": lambda: S.random_mixed(800, 4), "cornell": S.cornell, "final": S.final_scene,
+            "spheres30k": lambda: S.random_spheres(30_000, 64, 64, 1, 3), "dups": lambda: S.random_mixed(40, 12)}[scene]()
+    if scene == "dups":
+        idx = np.random.default_rng(5).integers(0, 40, 600)
+        desc = S.SceneDesc(desc.name, desc.materials, desc.prim_type[idx], desc.prim_data[idx], desc.prim_mat[idx], dict(desc.camera),
+                           desc.spp, desc.max_bounces, desc.background, desc.seed)
+    host = trt.Scene.from_desc(desc, trt.BVH_REFERENCE).leaf_ranks()
+    assert np.array_equal(host, orc.Scene.from_desc(desc).leaf_ranks())
+    sc = trt.Scene.from_desc(desc, trt.BVH_LBVH_DEVICE)
+    sc.upload(ctx)
+    dev = sc.leaf_ranks()
+    assert np.array_equal(np.sort(dev), np.arange(desc.n_prims)) and np.array_equal(dev, host), "%d ranks differ" % int((dev != host).sum())
+
+
 @pytest.mark.parametrize("n", [2, 31, 32, 33, 63, 64])
 def test_flat_list_mask_boundaries(trt, orc, ctx, n):
     """TRT_BVH_FLAT keeps its candidates in two 32-bit masks: primitive counts around 32 and at the limit of 64, on a

@@ -217,6 +217,12 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
         cudaFree(d_boxes);
         if (e != cudaSuccess) return fail_cuda("trt_scene_upload: device BVH build", e);
         s->host.flat.max_depth = depth; s->host.device_build_ms = ms + ms_ref; dc.root_ref4 = root_ref;
+        {   // bring the ranks back for trt_scene_leaf_ranks: meta = (material, rank, prim_id, 0)
+            std::vector<trt_u4> meta(f.sphere_meta.size() + f.quad_meta.size());
+            if (sz[3]) CU(cudaMemcpy(meta.data(), (char*)dc.buf + off[3], sz[3], cudaMemcpyDeviceToHost));
+            if (sz[4]) CU(cudaMemcpy(meta.data() + f.sphere_meta.size(), (char*)dc.buf + off[4], sz[4], cudaMemcpyDeviceToHost));
+            for (const trt_u4& m : meta) if (m.z < s->host.leaf_rank.size()) s->host.leaf_rank[m.z] = m.y;
+        }
         if (depth > TRT_MAX_STACK) return fail(TRT_ERR_UNSUPPORTED, "trt_scene_upload: device-built tree deeper than the traversal stack; commit with TRT_BVH_SAH");
     }
     trtk::SceneView& v = dc.view;
