@@ -188,7 +188,7 @@ def main():
     kind = {"auto": trt.BVH_AUTO, "sah": trt.BVH_SAH, "reference": trt.BVH_REFERENCE, "flat": trt.BVH_FLAT, "lbvh": trt.BVH_LBVH_DEVICE}[args.bvh]
     variant = trt.VARIANT_MEGAKERNEL if args.variant == "megakernel" else trt.VARIANT_WAVEFRONT
     flat = args.bvh == "flat" or (args.bvh == "auto" and 1 <= desc.n_prims <= 64)          # TRT_BVH_AUTO's rule (trt_scene.cpp)
-    bvh_resolved = "flat" if flat else ("sah" if args.bvh == "auto" else args.bvh)
+    bvh_resolved = "flat" if flat else (("lbvh" if desc.n_prims >= 65536 else "sah") if args.bvh == "auto" else args.bvh)
     kernel_name = "k_wf_shade + k_wf_extend" if variant != 0 else ("k_render_mega_flat" if flat else "k_render_mega")
     ctx = trt.Context(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)   # same stream as torch's events and the NCCL reduce

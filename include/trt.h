@@ -35,7 +35,8 @@ typedef enum trt_bvh_kind {
     TRT_BVH_REFERENCE = 0,   /* the reference's median-split topology, traversed left-first: reference results by construction */
     TRT_BVH_SAH = 1,         /* binned-SAH topology, near-child-first traversal, ties broken by reference leaf order */
     TRT_BVH_FLAT = 2,        /* no tree: <= 64 primitives as a list in reference leaf order; reference results by construction */
-    TRT_BVH_AUTO = 3,        /* FLAT when the scene has <= 64 primitives (fastest there, exact by construction), else SAH */
+    TRT_BVH_AUTO = 3,        /* FLAT when the scene has <= 64 primitives (fastest there, exact by construction), else SAH;
+                                from 65 536 primitives on LBVH_DEVICE (same results, the build moves to the GPU) */
     TRT_BVH_LBVH_DEVICE = 4  /* built on the GPU during trt_scene_upload (Morton codes + radix sort + Karras), walked like SAH;
                                 the reference's own Node::new also runs there (level-parallel), so ties and the replay of
                                 order-dependent rays follow the reference leaf order exactly as with TRT_BVH_SAH */

@@ -333,7 +333,7 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
     if (bvh_kind == 4 && n < 2) bvh_kind = 0;                    // nothing to build on the device
     // TRT_BVH_AUTO: up to TRT_FLAT_MAX primitives the flat list beats any tree on a SIMT machine (measured: Cornell 15.8 vs
     // 10.8 Grays/s, glass Cornell 9.8 vs 6.3) and reproduces the reference by construction; larger scenes need SAH.
-    if (bvh_kind == 3) bvh_kind = (n >= 1 && n <= TRT_FLAT_MAX) ? 2 : (n == 0 ? 0 : 1);
+    if (bvh_kind == 3) bvh_kind = (n >= 1 && n <= TRT_FLAT_MAX) ? 2 : (n == 0 ? 0 : (n >= TRT_AUTO_DEVICE_BUILD_MIN ? 4 : 1));
     if (bvh_kind == 2 && (n < 1 || n > TRT_FLAT_MAX)) { *err = "trt_scene_commit: TRT_BVH_FLAT takes 1..64 primitives"; return false; }
     // per-type arrays in insertion order (what World::get_geometries::<T>() returns, hittable/world.rs:47-55)
     uint32_t ns = 0, nq = 0;
