@@ -23,7 +23,7 @@ static int fail_cuda(const char* what, cudaError_t e) {
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_cuda(#call, e_); } while (0)
 
 struct DeviceCopy {
-    uint64_t version = 0; void* buf = nullptr; size_t bytes = 0; trtk::SceneView view{}; uint32_t root_ref4 = 0;
+    uint64_t version = 0; void* buf = nullptr; size_t bytes = 0; trtk::SceneView view{}; uint32_t root_ref4 = 0; bool wide_ok = false;
 };
 struct trt_scene {
     trt::HostScene host;
@@ -209,6 +209,11 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
         uint32_t depth = 0; float ms = 0.f;
         if (e == cudaSuccess) e = trtk::build_lbvh(d_boxes, (uint32_t)n_prims, (char*)dc.buf + off[0], (char*)dc.buf + off[9], d_tmp, &depth, &ms, c->stream);
         if (d_tmp) cudaFree(d_tmp);
+        // the wide records: plain two-level collapse (opening the largest children instead, as the host does for the SAH tree,
+        // measured no gain on the device-built tree: 10^6 spheres 2 100 vs 2 112 Mrays/s)
+        const bool greedy4 = false;
+        if (e == cudaSuccess) e = trtk::collapse_lbvh4((char*)dc.buf + off[0], (uint32_t)n_prims, (char*)dc.buf + off[9], greedy4, c->stream);
+        dc.wide_ok = greedy4 || 3 * ((depth + 1) / 2) + 1 <= TRT_MAX_STACK;
         // Node::new itself on the device: the reference leaf order (tie rule) and the reference tree's wide nodes (replay)
         uint32_t root_ref = 0; float ms_ref = 0.f; void* d_tmp2 = nullptr;
         if (e == cudaSuccess) e = cudaMalloc(&d_tmp2, trtk::ref_order_tmp_bytes((uint32_t)n_prims));
@@ -234,7 +239,7 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
     v.nodes4 = f.nodes4.empty() ? nullptr : b + off[9]; v.n_nodes4 = f.n_nodes4;
     v.nodes_ref4 = f.nodes_ref4.empty() ? nullptr : b + off[10]; v.n_nodes_ref4 = f.n_nodes_ref4; v.root_ref4 = 0;
     if (device_build) { v.nodes_ref4 = b + off[10]; v.n_nodes_ref4 = (uint32_t)(n_prims - 1); v.root_ref4 = dc.root_ref4; }
-    if (device_build && 3 * ((s->host.flat.max_depth + 1) / 2) + 1 <= TRT_MAX_STACK) { v.nodes4 = b + off[9]; v.n_nodes4 = (uint32_t)(n_prims - 1); }
+    if (device_build && dc.wide_ok) { v.nodes4 = b + off[9]; v.n_nodes4 = (uint32_t)(n_prims - 1); }
     v.flat_cbox = f.flat_cbox.empty() ? nullptr : b + off[8]; v.flat_cbox_host = f.flat_cbox.empty() ? nullptr : f.flat_cbox.data(); v.flat_bound = f.flat_bound;
     const float inf = std::numeric_limits<float>::infinity();
     for (int i = 0; i < 3; ++i) { v.root_min[i] = inf; v.root_max[i] = -inf; }

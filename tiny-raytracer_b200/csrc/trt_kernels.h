@@ -31,6 +31,7 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
 size_t lbvh_tmp_bytes(uint32_t n);
 // Builds the 64-byte node array (n - 1 nodes) and, if d_nodes4 is not null, its 4-wide form (128 bytes per node) on the device from per-primitive padded boxes (2 float4 each, leaf-ref bits in bmin.w).
 cudaError_t build_lbvh(const void* d_boxes, uint32_t n, void* d_nodes, void* d_nodes4, void* d_tmp, uint32_t* h_depth, float* h_ms, cudaStream_t st);
+cudaError_t collapse_lbvh4(const void* d_nodes, uint32_t n, void* d_nodes4, bool greedy, cudaStream_t st);
 size_t ref_order_tmp_bytes(uint32_t n);
 // Node::new (hittable/bvh.rs:42-84) on the device: the reference leaf rank of every primitive into meta.y and the wide nodes
 // of the reference-topology tree (8 float4 per node, n - 1 nodes, root index in *h_root) into d_nodes_ref4.

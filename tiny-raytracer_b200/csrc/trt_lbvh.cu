@@ -164,22 +164,38 @@ __global__ void k_lbvh_emit(const float4* __restrict__ boxes, const uint32_t* __
 // 4-wide record of binary node i (trt_scene.cpp collapse4 on the device): its children are node i's grandchildren, a leaf
 // child stays as it is. Every binary node gets one — only those an even number of levels below the root are ever reached —
 // so no compaction or depth is needed and a wide child ref is simply the binary index of that grandchild.
-__global__ void k_lbvh_collapse4(const float4* __restrict__ nodes, uint32_t n, float4* nodes4) {
+__global__ void k_lbvh_collapse4(const float4* __restrict__ nodes, uint32_t n, float4* nodes4, int greedy) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i + 1 >= n) return;
     float mn[4][3], mx[4][3]; uint32_t ref[4]; int nk = 0;
-    auto child = [&](const float4* r, int side) {
+    auto put = [&](int k, const float4* r, int side) {
         const float4 a = r[0], b = r[1], c = r[2];
-        mn[nk][0] = side ? a.y : a.x; mn[nk][1] = side ? a.w : a.z; mn[nk][2] = side ? b.y : b.x;
-        mx[nk][0] = side ? b.w : b.z; mx[nk][1] = side ? c.y : c.x; mx[nk][2] = side ? c.w : c.z;
-        ref[nk] = __float_as_uint(side ? r[3].y : r[3].x);
-        ++nk;
+        mn[k][0] = side ? a.y : a.x; mn[k][1] = side ? a.w : a.z; mn[k][2] = side ? b.y : b.x;
+        mx[k][0] = side ? b.w : b.z; mx[k][1] = side ? c.y : c.x; mx[k][2] = side ? c.w : c.z;
+        ref[k] = __float_as_uint(side ? r[3].y : r[3].x);
     };
     const float4* rec = nodes + 4 * (size_t)i;
-    for (int side = 0; side < 2; ++side) {
-        uint32_t c = __float_as_uint(side ? rec[3].y : rec[3].x);
-        if (c & 0x80000000u) child(rec, side);
-        else { const float4* cr = nodes + 4 * (size_t)c; child(cr, 0); child(cr, 1); }
+    if (!greedy) {
+        for (int side = 0; side < 2; ++side) {
+            uint32_t c = __float_as_uint(side ? rec[3].y : rec[3].x);
+            if (c & 0x80000000u) put(nk++, rec, side);
+            else { const float4* cr = nodes + 4 * (size_t)c; put(nk++, cr, 0); put(nk++, cr, 1); }
+        }
+    } else {
+        // twice: open the interior child with the largest surface area, in place (like trt_scene.cpp collapse4 for the SAH tree)
+        put(0, rec, 0); put(1, rec, 1); nk = 2;
+        for (int rep = 0; rep < 2; ++rep) {
+            int best = -1; float ba = -1.f;
+            for (int k = 0; k < nk; ++k) if (!(ref[k] & 0x80000000u)) {
+                const float dx = mx[k][0] - mn[k][0], dy = mx[k][1] - mn[k][1], dz = mx[k][2] - mn[k][2];
+                const float a = dx * dy + dy * dz + dz * dx;
+                if (a > ba) { ba = a; best = k; }
+            }
+            if (best < 0) break;
+            const float4* cr = nodes + 4 * (size_t)ref[best];
+            for (int k = nk; k > best + 1; --k) { for (int a = 0; a < 3; ++a) { mn[k][a] = mn[k - 1][a]; mx[k][a] = mx[k - 1][a]; } ref[k] = ref[k - 1]; }
+            put(best, cr, 0); put(best + 1, cr, 1); ++nk;
+        }
     }
     const float inf = __int_as_float(0x7f800000);
     for (; nk < 4; ++nk) { for (int a = 0; a < 3; ++a) { mn[nk][a] = inf; mx[nk][a] = -inf; } ref[nk] = 0x7FFFFFFFu; }
@@ -314,6 +330,7 @@ size_t lbvh_tmp_bytes(uint32_t n) {
 // d_boxes: 2 float4 per primitive (bmin.xyz + leaf-ref bits, bmax.xyz). d_nodes: 4 float4 per interior node (n - 1 nodes).
 // d_nodes4 (optional): 8 float4 per interior node, the 4-wide record of every binary node (k_lbvh_collapse4).
 cudaError_t build_lbvh(const void* d_boxes, uint32_t n, void* d_nodes, void* d_nodes4, void* d_tmp, uint32_t* h_depth, float* h_ms, cudaStream_t st) {
+    // (the wide records are written after the depth is known: collapse_lbvh4)
     if (n < 2) return cudaErrorInvalidValue;
     char* p = (char*)d_tmp;
     LbvhBounds* b = (LbvhBounds*)p; p += al(sizeof(LbvhBounds));
@@ -340,7 +357,6 @@ cudaError_t build_lbvh(const void* d_boxes, uint32_t n, void* d_nodes, void* d_n
         k_lbvh_karras<<<g, 256, 0, st>>>(keys_s, n, left, right, pn, pl, flags);
         k_lbvh_refit<<<g, 256, 0, st>>>(boxes, order, n, left, right, pn, pl, flags, node_min, node_max, b);
         k_lbvh_emit<<<g, 256, 0, st>>>(boxes, order, n, left, right, node_min, node_max, (float4*)d_nodes);
-        if (d_nodes4) k_lbvh_collapse4<<<g, 256, 0, st>>>((const float4*)d_nodes, n, (float4*)d_nodes4);
         cudaEventRecord(e1, st);
         LbvhBounds hb;
         e = cudaMemcpyAsync(&hb, b, sizeof hb, cudaMemcpyDeviceToHost, st);
@@ -350,6 +366,12 @@ cudaError_t build_lbvh(const void* d_boxes, uint32_t n, void* d_nodes, void* d_n
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return e;
+}
+
+// wide records of a binary node array; greedy = open the largest children (a wide level may then consume one binary level only)
+cudaError_t collapse_lbvh4(const void* d_nodes, uint32_t n, void* d_nodes4, bool greedy, cudaStream_t st) {
+    k_lbvh_collapse4<<<(n + 255) / 256, 256, 0, st>>>((const float4*)d_nodes, n, (float4*)d_nodes4, greedy ? 1 : 0);
+    return cudaGetLastError();
 }
 
 size_t ref_order_tmp_bytes(uint32_t n) {
@@ -396,7 +418,7 @@ cudaError_t build_reference_order(const void* d_boxes, uint32_t n, void* d_spher
     }
     if (e == cudaSuccess) {
         k_ref_ranks<<<g, 256, 0, st>>>(boxes, order, n, (uint4*)d_sphere_meta, (uint4*)d_quad_meta);
-        k_lbvh_collapse4<<<g, 256, 0, st>>>(nodes, n, (float4*)d_nodes_ref4);
+        k_lbvh_collapse4<<<g, 256, 0, st>>>(nodes, n, (float4*)d_nodes_ref4, 0);
         cudaEventRecord(e1, st);
         e = cudaStreamSynchronize(st);
         if (e == cudaSuccess) e = cudaGetLastError();
