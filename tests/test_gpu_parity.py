@@ -534,6 +534,23 @@ def test_device_node_new_gives_the_reference_leaf_order(trt, orc, ctx, scene):
     assert np.array_equal(np.sort(dev), np.arange(desc.n_prims)) and np.array_equal(dev, host), "%d ranks differ" % int((dev != host).sum())
 
 
+def test_big_sah_scene_takes_its_reference_order_from_the_device(trt, orc, ctx):
+    """From 65 536 primitives on, TRT_BVH_SAH builds only the SAH tree on the host; ranks and the replay tree come from the
+    device Node::new during upload. Same ranks as the host reference builder, and rays equal to the oracle."""
+    desc = trt.scenes.random_spheres(70_000, 64, 64, 1, 3)
+    host = trt.Scene.from_desc(desc, trt.BVH_REFERENCE).leaf_ranks()
+    sc = trt.Scene.from_desc(desc, trt.BVH_SAH)
+    assert np.array_equal(sc.leaf_ranks(), np.arange(desc.n_prims))       # placeholder before the upload
+    sc.upload(ctx)
+    assert np.array_equal(sc.leaf_ranks(), host) and sc.build_times()["device_build_ms"] > 0
+    rng = np.random.default_rng(11)
+    o = rng.uniform(-60, 60, (200_000, 3)).astype(np.float32)
+    d = rng.normal(size=(200_000, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    prim, t = sc.trace_rays(ctx, o, d, 0.001)
+    oprim, ot = orc.Scene.from_desc(desc).trace_rays(o, d, 0.001, use_bvh=True)
+    assert np.array_equal(prim, oprim) and np.array_equal(bits(t), bits(ot))
+
+
 @pytest.mark.parametrize("n", [2, 31, 32, 33, 63, 64])
 def test_flat_list_mask_boundaries(trt, orc, ctx, n):
     """TRT_BVH_FLAT keeps its candidates in two 32-bit masks: primitive counts around 32 and at the limit of 64, on a

@@ -192,16 +192,44 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
     const trt::FlatScene& f = s->host.flat;
     const bool device_build = f.bvh_kind == TRT_BVH_LBVH_DEVICE;
     const size_t n_prims = s->host.prims.size();
-    size_t sz[11] = {device_build ? 64 * (n_prims - 1) : f.nodes.size() * 16, f.spheres.size() * 16, f.quads.size() * 16, f.sphere_meta.size() * 16, f.quad_meta.size() * 16, f.materials.size() * 16, f.flat.size() * 16, f.quad_nn.size() * 16, f.flat_cbox.size() * 16, device_build ? 128 * (n_prims - 1) : f.nodes4.size() * 16, device_build ? 128 * (n_prims - 1) : f.nodes_ref4.size() * 16};
+    size_t sz[11] = {device_build ? 64 * (n_prims - 1) : f.nodes.size() * 16, f.spheres.size() * 16, f.quads.size() * 16, f.sphere_meta.size() * 16, f.quad_meta.size() * 16, f.materials.size() * 16, f.flat.size() * 16, f.quad_nn.size() * 16, f.flat_cbox.size() * 16, (device_build || f.wide_on_device) ? 128 * (n_prims - 1) : f.nodes4.size() * 16, (device_build || f.ref_on_device) ? 128 * (n_prims - 1) : f.nodes_ref4.size() * 16};
     const void* src[11] = {f.nodes.data(), f.spheres.data(), f.quads.data(), f.sphere_meta.data(), f.quad_meta.data(), f.materials.data(), f.flat.data(), f.quad_nn.data(), f.flat_cbox.data(), f.nodes4.data(), f.nodes_ref4.data()};
     size_t off[11], total = 0;
     for (int i = 0; i < 11; ++i) { off[i] = total; total += align_up(sz[i] ? sz[i] : 16); }
     if (dc.buf && dc.bytes < total) { cudaFree(dc.buf); dc.buf = nullptr; }
     if (!dc.buf) { CU(cudaMalloc(&dc.buf, total)); dc.bytes = total; }
-    for (int i = 0; i < 11; ++i) if (sz[i] && !(device_build && (i == 0 || i == 9 || i == 10))) CU(cudaMemcpyAsync((char*)dc.buf + off[i], src[i], sz[i], cudaMemcpyHostToDevice, c->stream));
+    for (int i = 0; i < 11; ++i) if (sz[i] && !(device_build && i == 0) && !((device_build || f.wide_on_device) && i == 9) && !((device_build || f.ref_on_device) && i == 10)) CU(cudaMemcpyAsync((char*)dc.buf + off[i], src[i], sz[i], cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    // Node::new (the reference's, level-parallel: trt_lbvh.cu k_ref_*) from the per-primitive boxes: ranks into meta.y (and back
+    // to the host for trt_scene_leaf_ranks), the reference tree's wide nodes into the buffer
+    auto ref_order = [&](const void* d_boxes, float* ms_out) -> cudaError_t {
+        void* d_tmp2 = nullptr; uint32_t root_ref = 0;
+        cudaError_t e = cudaMalloc(&d_tmp2, trtk::ref_order_tmp_bytes((uint32_t)n_prims));
+        if (e == cudaSuccess) e = trtk::build_reference_order(d_boxes, (uint32_t)n_prims, (char*)dc.buf + off[3], (char*)dc.buf + off[4], (char*)dc.buf + off[10], d_tmp2, &root_ref, ms_out, c->stream);
+        if (d_tmp2) cudaFree(d_tmp2);
+        if (e != cudaSuccess) return e;
+        dc.root_ref4 = root_ref;
+        std::vector<trt_u4> meta(f.sphere_meta.size() + f.quad_meta.size());     // meta = (material, rank, prim_id, 0)
+        if (sz[3]) e = cudaMemcpy(meta.data(), (char*)dc.buf + off[3], sz[3], cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && sz[4]) e = cudaMemcpy(meta.data() + f.sphere_meta.size(), (char*)dc.buf + off[4], sz[4], cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) for (const trt_u4& m : meta) if (m.z < s->host.leaf_rank.size()) s->host.leaf_rank[m.z] = m.y;
+        return e;
+    };
+    if (f.wide_on_device) {
+        cudaError_t e = trtk::collapse_lbvh4((char*)dc.buf + off[0], (uint32_t)n_prims, (char*)dc.buf + off[9], false, c->stream);
+        if (e != cudaSuccess) return fail_cuda("trt_scene_upload: wide nodes", e);
+    }
+    if (f.ref_on_device) {
+        void* d_boxes = nullptr; float ms_ref = 0.f;
+        CU(cudaMalloc(&d_boxes, f.lbvh_boxes.size() * 16));
+        cudaError_t e = cudaMemcpyAsync(d_boxes, f.lbvh_boxes.data(), f.lbvh_boxes.size() * 16, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = ref_order(d_boxes, &ms_ref);
+        cudaFree(d_boxes);
+        if (e != cudaSuccess) return fail_cuda("trt_scene_upload: device reference order", e);
+        s->host.device_build_ms = ms_ref;
+    }
     if (device_build) {
-        // Node::new on the GPU: Morton codes + radix sort + Karras hierarchy + bottom-up boxes (trt_lbvh.cu)
+        // the walked tree on the GPU: Morton codes + radix sort + Karras hierarchy + bottom-up boxes (trt_lbvh.cu)
         void *d_boxes = nullptr, *d_tmp = nullptr;
         CU(cudaMalloc(&d_boxes, f.lbvh_boxes.size() * 16));
         cudaError_t e = cudaMalloc(&d_tmp, trtk::lbvh_tmp_bytes((uint32_t)n_prims));
@@ -215,19 +243,11 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
         if (e == cudaSuccess) e = trtk::collapse_lbvh4((char*)dc.buf + off[0], (uint32_t)n_prims, (char*)dc.buf + off[9], greedy4, c->stream);
         dc.wide_ok = greedy4 || 3 * ((depth + 1) / 2) + 1 <= TRT_MAX_STACK;
         // Node::new itself on the device: the reference leaf order (tie rule) and the reference tree's wide nodes (replay)
-        uint32_t root_ref = 0; float ms_ref = 0.f; void* d_tmp2 = nullptr;
-        if (e == cudaSuccess) e = cudaMalloc(&d_tmp2, trtk::ref_order_tmp_bytes((uint32_t)n_prims));
-        if (e == cudaSuccess) e = trtk::build_reference_order(d_boxes, (uint32_t)n_prims, (char*)dc.buf + off[3], (char*)dc.buf + off[4], (char*)dc.buf + off[10], d_tmp2, &root_ref, &ms_ref, c->stream);
-        if (d_tmp2) cudaFree(d_tmp2);
+        float ms_ref = 0.f;
+        if (e == cudaSuccess) e = ref_order(d_boxes, &ms_ref);
         cudaFree(d_boxes);
         if (e != cudaSuccess) return fail_cuda("trt_scene_upload: device BVH build", e);
-        s->host.flat.max_depth = depth; s->host.device_build_ms = ms + ms_ref; dc.root_ref4 = root_ref;
-        {   // bring the ranks back for trt_scene_leaf_ranks: meta = (material, rank, prim_id, 0)
-            std::vector<trt_u4> meta(f.sphere_meta.size() + f.quad_meta.size());
-            if (sz[3]) CU(cudaMemcpy(meta.data(), (char*)dc.buf + off[3], sz[3], cudaMemcpyDeviceToHost));
-            if (sz[4]) CU(cudaMemcpy(meta.data() + f.sphere_meta.size(), (char*)dc.buf + off[4], sz[4], cudaMemcpyDeviceToHost));
-            for (const trt_u4& m : meta) if (m.z < s->host.leaf_rank.size()) s->host.leaf_rank[m.z] = m.y;
-        }
+        s->host.flat.max_depth = depth; s->host.device_build_ms = ms + ms_ref;
         if (depth > TRT_MAX_STACK) return fail(TRT_ERR_UNSUPPORTED, "trt_scene_upload: device-built tree deeper than the traversal stack; commit with TRT_BVH_SAH");
     }
     trtk::SceneView& v = dc.view;
@@ -238,8 +258,8 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
     v.flat = f.flat.empty() ? nullptr : b + off[6]; v.n_flat = (uint32_t)(f.flat.size() / 6);
     v.nodes4 = f.nodes4.empty() ? nullptr : b + off[9]; v.n_nodes4 = f.n_nodes4;
     v.nodes_ref4 = f.nodes_ref4.empty() ? nullptr : b + off[10]; v.n_nodes_ref4 = f.n_nodes_ref4; v.root_ref4 = 0;
-    if (device_build) { v.nodes_ref4 = b + off[10]; v.n_nodes_ref4 = (uint32_t)(n_prims - 1); v.root_ref4 = dc.root_ref4; }
-    if (device_build && dc.wide_ok) { v.nodes4 = b + off[9]; v.n_nodes4 = (uint32_t)(n_prims - 1); }
+    if (device_build || f.ref_on_device) { v.nodes_ref4 = b + off[10]; v.n_nodes_ref4 = (uint32_t)(n_prims - 1); v.root_ref4 = dc.root_ref4; }
+    if ((device_build && dc.wide_ok) || f.wide_on_device) { v.nodes4 = b + off[9]; v.n_nodes4 = (uint32_t)(n_prims - 1); }
     v.flat_cbox = f.flat_cbox.empty() ? nullptr : b + off[8]; v.flat_cbox_host = f.flat_cbox.empty() ? nullptr : f.flat_cbox.data(); v.flat_bound = f.flat_bound;
     const float inf = std::numeric_limits<float>::infinity();
     for (int i = 0; i < 3; ++i) { v.root_min[i] = inf; v.root_max[i] = -inf; }

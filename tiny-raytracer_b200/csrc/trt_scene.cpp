@@ -3,7 +3,9 @@
 // is compiled without FMA contraction, because the kernels cull with exactly these numbers.
 #include "trt_scene.hpp"
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <future>
@@ -126,6 +128,9 @@ struct RefBuilder {
 };
 
 // ---- binned SAH, one primitive per leaf. Same node numbering scheme.
+// min/max without libm calls (-fno-fast-math keeps fminf/fmaxf out of line; the builder's inputs are never NaN)
+static inline float fmin_(float a, float b) { return b < a ? b : a; }
+static inline float fmax_(float a, float b) { return b > a ? b : a; }
 struct SahBuilder {
     const std::vector<HostPrim>& prims;
     std::vector<TNode>& nodes;
@@ -136,14 +141,22 @@ struct SahBuilder {
         float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
         return dx * dy + dy * dz + dz * dx;
     }
-    float centroid(uint32_t p, int ax) const { return 0.5f * (prims[p].bmin[ax] + prims[p].bmax[ax]); }
+    // The builder partitions an array of (box, id) records in place, so that a slice is contiguous in memory at every depth
+    // (an index array into the primitives costs a cache miss per visit on big scenes: 10^6 spheres 900 -> 330 ms).
+    struct Item { float b[6]; uint32_t id; };
+    std::vector<Item> work;
+    void prepare() {
+        work.resize(prims.size());
+        for (size_t i = 0; i < prims.size(); ++i) { for (int a = 0; a < 3; ++a) { work[i].b[a] = prims[i].bmin[a]; work[i].b[3 + a] = prims[i].bmax[a]; } work[i].id = (uint32_t)i; }
+    }
+    static float centroid(const Item& it, int ax) { return 0.5f * (it.b[ax] + it.b[3 + ax]); }
 
     uint32_t build(size_t lo, size_t hi, uint32_t base, int depth, int par_depth) {
         size_t n = hi - lo;
         TNode& node = nodes[base];
         if (n == 1) {
-            const HostPrim& p = prims[order[lo]];
-            node.left = node.right = NOPRIM; node.prim = order[lo];
+            const HostPrim& p = prims[work[lo].id];
+            node.left = node.right = NOPRIM; node.prim = work[lo].id;
             for (int i = 0; i < 3; ++i) { node.bmin[i] = p.bmin[i]; node.bmax[i] = p.bmax[i]; }
             return base;
         }
@@ -153,30 +166,34 @@ struct SahBuilder {
             float cmn[3], cmx[3];
             for (int a = 0; a < 3; ++a) { cmn[a] = std::numeric_limits<float>::infinity(); cmx[a] = -cmn[a]; }
             for (size_t k = lo; k < hi; ++k)
-                for (int a = 0; a < 3; ++a) { float c = centroid(order[k], a); cmn[a] = fminf(cmn[a], c); cmx[a] = fmaxf(cmx[a], c); }
+                for (int a = 0; a < 3; ++a) { float c = centroid(work[k], a); cmn[a] = fmin_(cmn[a], c); cmx[a] = fmax_(cmx[a], c); }
             float best_cost = std::numeric_limits<float>::infinity(); int best_axis = -1, best_bin = -1;
-            for (int a = 0; a < 3; ++a) {
-                float ext = cmx[a] - cmn[a];
-                if (!(ext > 0.f)) continue;
-                float scale = (float)NB / ext;
-                uint32_t cnt[NB]; float bmn[NB][3], bmx[NB][3];
-                for (int b = 0; b < NB; ++b) { cnt[b] = 0; for (int i = 0; i < 3; ++i) { bmn[b][i] = std::numeric_limits<float>::infinity(); bmx[b][i] = -bmn[b][i]; } }
-                for (size_t k = lo; k < hi; ++k) {
-                    const HostPrim& p = prims[order[k]];
-                    int b = (int)((centroid(order[k], a) - cmn[a]) * scale); if (b >= NB) b = NB - 1; if (b < 0) b = 0;
-                    cnt[b]++;
-                    for (int i = 0; i < 3; ++i) { bmn[b][i] = fminf(bmn[b][i], p.bmin[i]); bmx[b][i] = fmaxf(bmx[b][i], p.bmax[i]); }
+            // one pass over the slice bins all three axes at once
+            float scale3[3]; bool use[3];
+            for (int a = 0; a < 3; ++a) { float ext = cmx[a] - cmn[a]; use[a] = ext > 0.f; scale3[a] = use[a] ? (float)NB / ext : 0.f; }
+            uint32_t cnt[3][NB]; float bmn[3][NB][3], bmx[3][NB][3];
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < NB; ++b) { cnt[a][b] = 0; for (int i = 0; i < 3; ++i) { bmn[a][b][i] = std::numeric_limits<float>::infinity(); bmx[a][b][i] = -bmn[a][b][i]; } }
+            for (size_t k = lo; k < hi; ++k) {
+                const float* bx = work[k].b;
+                for (int a = 0; a < 3; ++a) {
+                    if (!use[a]) continue;
+                    int b = (int)((0.5f * (bx[a] + bx[3 + a]) - cmn[a]) * scale3[a]); if (b >= NB) b = NB - 1; if (b < 0) b = 0;
+                    cnt[a][b]++;
+                    for (int i = 0; i < 3; ++i) { bmn[a][b][i] = fmin_(bmn[a][b][i], bx[i]); bmx[a][b][i] = fmax_(bmx[a][b][i], bx[3 + i]); }
                 }
+            }
+            for (int a = 0; a < 3; ++a) {
+                if (!use[a]) continue;
                 float la[NB - 1]; uint32_t lc[NB - 1];
                 float amn[3], amx[3]; uint32_t c = 0;
                 for (int i = 0; i < 3; ++i) { amn[i] = std::numeric_limits<float>::infinity(); amx[i] = -amn[i]; }
                 for (int b = 0; b < NB - 1; ++b) {
-                    c += cnt[b]; for (int i = 0; i < 3; ++i) { amn[i] = fminf(amn[i], bmn[b][i]); amx[i] = fmaxf(amx[i], bmx[b][i]); }
+                    c += cnt[a][b]; for (int i = 0; i < 3; ++i) { amn[i] = fmin_(amn[i], bmn[a][b][i]); amx[i] = fmax_(amx[i], bmx[a][b][i]); }
                     lc[b] = c; la[b] = c ? half_area(amn, amx) : 0.f;
                 }
                 c = 0; for (int i = 0; i < 3; ++i) { amn[i] = std::numeric_limits<float>::infinity(); amx[i] = -amn[i]; }
                 for (int b = NB - 1; b >= 1; --b) {
-                    c += cnt[b]; for (int i = 0; i < 3; ++i) { amn[i] = fminf(amn[i], bmn[b][i]); amx[i] = fmaxf(amx[i], bmx[b][i]); }
+                    c += cnt[a][b]; for (int i = 0; i < 3; ++i) { amn[i] = fmin_(amn[i], bmn[a][b][i]); amx[i] = fmax_(amx[i], bmx[a][b][i]); }
                     if (c == 0 || lc[b - 1] == 0) continue;
                     float cost = la[b - 1] * (float)lc[b - 1] + half_area(amn, amx) * (float)c;
                     if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b - 1; }
@@ -185,11 +202,11 @@ struct SahBuilder {
             if (best_axis >= 0) {
                 float ext = cmx[best_axis] - cmn[best_axis], scale = (float)NB / ext, c0 = cmn[best_axis];
                 int ax = best_axis, bb = best_bin;
-                auto it = std::stable_partition(order.begin() + lo, order.begin() + hi, [&](uint32_t p) {
+                auto it = std::partition(work.begin() + lo, work.begin() + hi, [&](const Item& p) {
                     int b = (int)((centroid(p, ax) - c0) * scale); if (b >= NB) b = NB - 1; if (b < 0) b = 0;
                     return b <= bb;
                 });
-                size_t m = (size_t)(it - order.begin());
+                size_t m = (size_t)(it - work.begin());
                 if (m > lo && m < hi) { mid = m; split_done = true; }
             }
         }
@@ -197,9 +214,9 @@ struct SahBuilder {
             // degenerate centroids or depth cap: median on the widest box axis
             float mn[3], mx[3];
             for (int i = 0; i < 3; ++i) { mn[i] = std::numeric_limits<float>::infinity(); mx[i] = -mn[i]; }
-            for (size_t k = lo; k < hi; ++k) for (int i = 0; i < 3; ++i) { mn[i] = fminf(mn[i], prims[order[k]].bmin[i]); mx[i] = fmaxf(mx[i], prims[order[k]].bmax[i]); }
+            for (size_t k = lo; k < hi; ++k) for (int i = 0; i < 3; ++i) { mn[i] = fmin_(mn[i], work[k].b[i]); mx[i] = fmax_(mx[i], work[k].b[3 + i]); }
             int ax = 0; if (mx[1] - mn[1] > mx[ax] - mn[ax]) ax = 1; if (mx[2] - mn[2] > mx[ax] - mn[ax]) ax = 2;
-            std::nth_element(order.begin() + lo, order.begin() + mid, order.begin() + hi, [&](uint32_t a, uint32_t b) { return centroid(a, ax) < centroid(b, ax); });
+            std::nth_element(work.begin() + lo, work.begin() + mid, work.begin() + hi, [&](const Item& a, const Item& b) { return centroid(a, ax) < centroid(b, ax); });
         }
         size_t nl = mid - lo;
         uint32_t lbase = base + 1, rbase = base + (uint32_t)(2 * nl);
@@ -357,11 +374,23 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
     leaf_rank.assign(n, 0);
     flat = FlatScene(); flat.bvh_kind = bvh_kind;
 
+    const bool timing = getenv("TRT_COMMIT_TIMING") != nullptr;      // stderr: where the commit time goes
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "trt_scene_commit: %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
     const bool device_build = bvh_kind == 4;
-    std::vector<TNode> ref_tree(n && !device_build ? 2 * n - 1 : 0), sah_tree;
+    // big SAH scenes: the reference tree (leaf ranks, replay tree) is left to the device as well (trt_lbvh.cu k_ref_*), which
+    // does in milliseconds what takes the host half of its commit time
+    const bool ref_on_device = bvh_kind == 1 && n >= TRT_AUTO_DEVICE_BUILD_MIN;
+    flat.ref_on_device = ref_on_device;
+    std::vector<TNode> ref_tree(n && !device_build && !ref_on_device ? 2 * n - 1 : 0), sah_tree;
     std::vector<uint32_t> order(n);
     for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
-    if (device_build) {
+    if (device_build || ref_on_device) {
         // TRT_BVH_LBVH_DEVICE: no host tree at all. The node arrays AND the reference leaf ranks (meta.y, placeholder here)
         // are produced by trt_lbvh.cu during trt_scene_upload from these per-primitive boxes.
         for (size_t i = 0; i < n; ++i) leaf_rank[i] = (uint32_t)i;
@@ -371,7 +400,7 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
             flat.lbvh_boxes[2 * i] = {p.bmin[0], p.bmin[1], p.bmin[2], as_float(leaf_ref(p))};
             flat.lbvh_boxes[2 * i + 1] = {p.bmax[0], p.bmax[1], p.bmax[2], 0.f};
         }
-        flat.root = 0; flat.n_nodes = (uint32_t)(n - 1); flat.max_depth = 0; flat.sah_cost = 0.f;
+        if (device_build) { flat.root = 0; flat.n_nodes = (uint32_t)(n - 1); flat.max_depth = 0; flat.sah_cost = 0.f; }
     } else if (n) {
         RefBuilder rb{prims, ref_tree, order, {}};
         for (int a = 0; a < 3; ++a) { rb.key[a].resize(n); for (size_t i = 0; i < n; ++i) rb.key[a][i] = total_order_key(prims[i].bmin[a]); }
@@ -379,24 +408,30 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
         // the in-place sorts leave `order` in left-to-right leaf order
         for (size_t i = 0; i < n; ++i) leaf_rank[order[i]] = (uint32_t)i;
     }
+    lap("reference tree / boxes");
     const std::vector<TNode>* tree = &ref_tree;
     if (bvh_kind == 1 && n) {
         sah_tree.resize(2 * n - 1);
         for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
-        SahBuilder sb{prims, sah_tree, order};
-        sb.build(0, n, 0, 1, 3);
+        SahBuilder sb{prims, sah_tree, order, {}};
+        sb.prepare();
+        sb.build(0, n, 0, 1, 4);
         tree = &sah_tree;
     }
+    lap("SAH tree");
     if (!device_build) flatten(*tree, prims, flat);
-    if ((bvh_kind == 0 || bvh_kind == 1) && n) {
+    lap("flatten");
+    flat.wide_on_device = ref_on_device && 3 * ((flat.max_depth + 1) / 2) + 1 <= TRT_MAX_STACK;   // big SAH scene: k_lbvh_collapse4 during upload
+    if ((bvh_kind == 0 || bvh_kind == 1) && n && !flat.wide_on_device) {
         collapse4(*tree, prims, flat, bvh_kind == 1);     // SAH: open the largest children (final scene +3 %)
         if (3 * flat.max_depth4 + 1 > TRT_MAX_STACK) { flat.nodes4.clear(); flat.n_nodes4 = 0; }   // walk the binary tree instead
     }
-    if (bvh_kind == 1 && n) {   // the reference-topology tree too: the ordered walk replays its rare order-dependent rays on it
+    if (bvh_kind == 1 && n && !ref_on_device) {   // the reference-topology tree too: the ordered walk replays its rare order-dependent rays on it
         FlatScene tmp;
         collapse4(ref_tree, prims, tmp);
         if (3 * tmp.max_depth4 + 1 <= TRT_MAX_STACK) { flat.nodes_ref4.swap(tmp.nodes4); flat.n_nodes_ref4 = tmp.n_nodes4; }
     }
+    lap("wide nodes");
     if (flat.max_depth > TRT_MAX_STACK) { *err = "trt_scene_commit: tree deeper than the traversal stack"; return false; }
 
     flat.spheres.resize(ns); flat.sphere_meta.resize(ns); flat.quads.resize(4 * (size_t)nq); flat.quad_nn.resize(nq); flat.quad_meta.resize(nq);

@@ -25,6 +25,8 @@ struct FlatScene {
     uint32_t n_nodes4 = 0, max_depth4 = 0;
     std::vector<trt_f4> nodes_ref4;    // TRT_BVH_SAH: wide nodes of the reference-topology tree, walked only to replay order-dependent rays
     uint32_t n_nodes_ref4 = 0;
+    bool wide_on_device = false;       // ... and so are its own wide nodes (plain two-level collapse of the uploaded binary nodes)
+    bool ref_on_device = false;        // TRT_BVH_SAH with many primitives: ranks and nodes_ref4 are produced during trt_scene_upload (lbvh_boxes is their input)
     std::vector<trt_f4> spheres;
     std::vector<trt_f4> quads;         // 4 per quad
     std::vector<trt_u4> sphere_meta, quad_meta;
