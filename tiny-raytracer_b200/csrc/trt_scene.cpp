@@ -280,18 +280,33 @@ static void flatten(const std::vector<TNode>& t, const std::vector<HostPrim>& pr
         out.n_nodes = next;
     }
     auto ha = [](const TNode& n) { float dx = n.bmax[0] - n.bmin[0], dy = n.bmax[1] - n.bmin[1], dz = n.bmax[2] - n.bmin[2]; return dx * dy + dy * dz + dz * dx; };
-    double root_area = ha(t[0]) > 0.f ? ha(t[0]) : 1.0, cost = 0.0;
-    for (size_t i = 0; i < t.size(); ++i) {
-        const TNode& n = t[i];
-        cost += (double)ha(n) / root_area;
-        if (n.prim != NOPRIM) continue;
-        const TNode& l = t[n.left]; const TNode& r = t[n.right];
-        trt_f4* rec = &out.nodes[4 * (size_t)flat_index[i]];
-        put_box(rec, &l, &r);
-        uint32_t lr = (l.prim != NOPRIM) ? leaf_ref(prims[l.prim]) : flat_index[n.left];
-        uint32_t rr = (r.prim != NOPRIM) ? leaf_ref(prims[r.prim]) : flat_index[n.right];
-        rec[3] = {as_float(lr), as_float(rr), 0.f, 0.f};
-    }
+    const double root_area = ha(t[0]) > 0.f ? ha(t[0]) : 1.0;
+    std::vector<uint32_t> refs(prims.size());                 // 4 bytes per primitive instead of a HostPrim per lookup
+    for (size_t i = 0; i < prims.size(); ++i) refs[i] = leaf_ref(prims[i]);
+    // pass 2: the records; independent per node, so big trees are written by a few threads
+    auto emit = [&](size_t i0, size_t i1) -> double {
+        double c = 0.0;
+        for (size_t i = i0; i < i1; ++i) {
+            const TNode& n = t[i];
+            c += (double)ha(n) / root_area;
+            if (n.prim != NOPRIM) continue;
+            const TNode& l = t[n.left]; const TNode& r = t[n.right];
+            trt_f4* rec = &out.nodes[4 * (size_t)flat_index[i]];
+            put_box(rec, &l, &r);
+            uint32_t lr = (l.prim != NOPRIM) ? refs[l.prim] : flat_index[n.left];
+            uint32_t rr = (r.prim != NOPRIM) ? refs[r.prim] : flat_index[n.right];
+            rec[3] = {as_float(lr), as_float(rr), 0.f, 0.f};
+        }
+        return c;
+    };
+    double cost = 0.0;
+    const size_t parts = t.size() > 200000 ? 8 : 1, step = (t.size() + parts - 1) / parts;
+    std::vector<std::future<double>> fut;
+    for (size_t k = 1; k < parts; ++k) fut.push_back(std::async(std::launch::async, emit, k * step, std::min(t.size(), (k + 1) * step)));
+    std::vector<double> part_cost(parts, 0.0);
+    part_cost[0] = emit(0, std::min(t.size(), step));
+    for (size_t k = 1; k < parts; ++k) part_cost[k] = fut[k - 1].get();
+    for (double c : part_cost) cost += c;                     // fixed summation order: the reported cost does not depend on scheduling
     out.root = 0; out.sah_cost = (float)cost;
 }
 
