@@ -290,12 +290,11 @@ template <bool SMEM> TRT_DEV bool quad_hit(const DevScene& S, uint32_t idx, V3 o
 // A when its current ref is an interior node and in B when it is a leaf (possibly the leaf A just selected), so each
 // region's code is issued once per iteration for all lanes that need it instead of once per call site.
 struct Hit { float t; uint32_t ref; };
-// Ordered kinds cull a subtree whose box entry lies beyond the closest hit. The reference culls a LEAF the same way, but
-// against whatever hit its own left-to-right order has found by then — and a grazing sphere's computed t can be smaller
-// than the computed entry of its own box, so which of the two happens depends on that order. Culling
-// only beyond (1 + 2^-8) x the closest hit keeps every primitive whose t/entry disagreement is below 0.4 % in play (the
-// sphere's is bounded by ~sqrt(20 * 2^-24) = 0.1 %), which leaves the (t, rank)-smallest valid primitive as the answer —
-// the reference's — at the price of a few extra node visits.
+// Ordered kinds cull a subtree whose box entry lies beyond the closest hit. A grazing sphere's computed t can be smaller
+// than the computed entry of its own box; for such a primitive the reference's answer depends on its own
+// visiting order, and the walk must at least FIND it to notice (needs_replay below). Culling only beyond (1 + 2^-8) x the
+// closest hit keeps every primitive whose t/entry disagreement is below 0.4 % in play (a sphere's is bounded by
+// ~sqrt(20 * 2^-24) = 0.1 %), at the price of a few extra node visits.
 #ifndef TRT_SAH_CULL_MARGIN
 #define TRT_SAH_CULL_MARGIN 0.00390625f
 #endif
