@@ -32,9 +32,23 @@ for k in range(n_scenes):
     n = desc.n_prims
     if n == 0:
         continue
+    # arbitrary rays too, a third of them degenerate (zero / tiny / axis-aligned components, origins on integer planes, far away)
+    nr_ = 3000
+    ro = rng.uniform(-14, 14, (nr_, 3)).astype(np.float32); rd = rng.normal(size=(nr_, 3)).astype(np.float32)
+    rd /= np.linalg.norm(rd, axis=1, keepdims=True).astype(np.float32)
+    rd[:150, int(rng.integers(3))] = 0.0; rd[150:300, int(rng.integers(3))] = np.float32(-0.0); rd[300:400, int(rng.integers(3))] = np.float32(1e-30)
+    rd[400:500] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 100)] * np.float32(rng.choice([-1.0, 1.0]))
+    ro[500:800] = np.round(ro[500:800]); ro[800:900] *= np.float32(1e6); ro[900:1000, 2] = np.float32(rng.integers(-3, 4))
+    oprim_r, ot_r = osc.trace_rays(ro, rd, 0.001, use_bvh=True)
     kinds = [trt.BVH_REFERENCE, trt.BVH_SAH, trt.BVH_AUTO] + ([trt.BVH_LBVH_DEVICE] if n >= 2 else []) + ([trt.BVH_FLAT] if n <= 64 else [])
     for kind in kinds:
         sc = trt.Scene.from_desc(desc, kind)
+        prim_r, t_r = sc.trace_rays(ctx, ro, rd, 0.001)
+        checked += 1
+        if not (np.array_equal(prim_r, oprim_r) and np.array_equal(t_r.view(np.uint32), ot_r.view(np.uint32))):
+            fails += 1
+            print("FAIL scene %d (n=%d seed=%d) kind=%d trace_rays: prim %d t %d" % (k, n, seed0 + k, kind, int((prim_r != oprim_r).sum()),
+                  int((t_r.view(np.uint32) != ot_r.view(np.uint32)).sum())), flush=True)
         for flags in (0, 4, 9 << 8):
             p = trt.make_params(w, h, spp, depth, desc.background, desc.seed, flags=flags | 2)
             prim, t, rad, nr = sc.render_aov(ctx, cam, p, True, True)
