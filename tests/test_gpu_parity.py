@@ -421,6 +421,30 @@ def test_reference_api_renderer(trt, orc, ctx):
     assert ulp_diff(image.linear, olin).max() <= 1 and np.abs(image.rgb8.astype(int) - ou8.astype(int)).max() <= 1
 
 
+def test_cpp_example_renders_main_rs_on_the_gpu(trt, orc, ctx, tmp_path):
+    """examples/cornell.cpp is /root/reference/src/main.rs against include/trt.hpp (300x300, 300 spp, depth 20). Compiled,
+    run on the GPU, its PNG decoded: the 8-bit image must equal the oracle's render of the same scene within +-1 LSB."""
+    import struct, subprocess, zlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "tiny-raytracer_b200")
+    exe, png = str(tmp_path / "cornell"), str(tmp_path / "out.png")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "cornell.cpp"),
+                           "-o", exe, "-L" + pkg, "-ltrt_b200", "-Wl,-rpath," + pkg])
+    r = subprocess.run([exe, png], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "27000000 paths" in r.stdout, r.stdout + r.stderr
+    b = open(png, "rb").read()
+    pos, idat = 8, b""
+    while pos < len(b):
+        n, = struct.unpack(">I", b[pos:pos + 4])
+        if b[pos + 4:pos + 8] == b"IDAT": idat += b[pos + 8:pos + 8 + n]
+        pos += 12 + n
+    img = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(300, 1 + 3 * 300)[:, 1:].reshape(300, 300, 3)
+    desc = trt.scenes.cornell(300, 300, 300, 20)
+    osc, ocam, _ = both(trt, orc, desc)
+    olin, ou8, _, _ = osc.render(ocam, orc.make_params(300, 300, 300, 20, desc.background, 1))
+    assert np.abs(img.astype(int) - ou8.astype(int)).max() <= 1 and (img != ou8).mean() < 0.02
+
+
 # ------------------------------------------------------------------ SURVEY §8f: progressive / resume, streaming Sampler adapter
 def test_progressive_render_and_checkpoint_resume(trt, orc, ctx):
     """Samples added in three instalments, with a checkpoint carried into a fresh renderer in between, give the image of
