@@ -158,3 +158,14 @@ def test_cpp_image_save_writes_a_valid_png(tmp_path):
     rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(219, 1 + 3 * 301)
     i = np.arange(301 * 219 * 3)
     assert (rows[:, 0] == 0).all() and np.array_equal(rows[:, 1:].reshape(-1), ((i * 7) ^ (i >> 8)).astype(np.uint8))
+
+
+def test_header_is_plain_c99_and_host_calls_work_from_c(tmp_path):
+    """include/trt.h compiles as strict C99 (`-pedantic -Werror`) and the host-only half of the ABI (scene, commit, camera,
+    error values) runs from a C program: examples/c_abi_host.c."""
+    exe, pkg = str(tmp_path / "c_abi_host"), os.path.join(ROOT, "tiny-raytracer_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_abi_host.c"), "-o", exe, "-L" + pkg, "-ltrt_b200", "-Wl,-rpath," + pkg])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "2 prims, 1 node(s), sample point 32 bytes" in r.stdout and "unknown material id" in r.stdout, r.stdout + r.stderr
+
