@@ -63,6 +63,15 @@ for k in range(n_scenes):
                     k, n, w, h, spp, depth, seed0 + k, kind, flags, int((prim != oprim).sum()), int((t.view(np.uint32) != ot.view(np.uint32)).sum()),
                     int((nr != onr).sum()), int((rad.view(np.uint32) != orad.view(np.uint32)).any(1).sum()), st.rays, ost.rays,
                     int((lin.view(np.uint32) != olin.view(np.uint32)).sum())), flush=True)
+        if kind in (trt.BVH_REFERENCE, trt.BVH_AUTO) and k % 4 == 0:
+            # the wavefront variant traces the same paths through queues in HBM; only the f64 summation order differs (<= 1 ulp)
+            p = trt.make_params(w, h, spp, depth, desc.background, desc.seed, variant=trt.VARIANT_WAVEFRONT)
+            lin, u8, st = sc.render(ctx, cam, p)
+            ulp = np.abs(lin.view(np.int32).astype(np.int64) - olin.view(np.int32).astype(np.int64)).max() if lin.size else 0
+            checked += 1
+            if not (st.rays == ost.rays and st.paths == ost.paths and ulp <= 1):
+                fails += 1
+                print("FAIL scene %d (n=%d seed=%d) kind=%d wavefront: rays %d/%d ulp %d" % (k, n, seed0 + k, kind, st.rays, ost.rays, int(ulp)), flush=True)
         sc.close()
 print("fuzz: %d scenes, %d (scene, kind, flags) renders checked, %d failures, %.0f s" % (n_scenes, checked, fails, time.time() - t_start))
 sys.exit(1 if fails else 0)
