@@ -306,6 +306,13 @@ def main():
         parity = {"psnr_db_8bit": None if mse == 0 else 10 * np.log10(255.0 ** 2 / mse), "psnr_is_infinite": mse == 0,
                   "linear_max_ulp": int(ulp.max(initial=0)), "linear_values_differing": int((ulp > 0).sum()),
                   "rays_equal": int(gst.rays) == counts["rays"], "sample": "%d spp, same Philox sample indices on both sides" % cpu_spp}
+        # primary hits (the (prim_id, t) mismatch count must be 0): one sample per pixel on both sides
+        from oracle import pyoracle as orc
+        op1 = orc.make_params(W, H, 1, desc.max_bounces, desc.background, desc.seed)
+        oprim, ot, _, _ = orc.Scene.from_desc(desc).render_aov(orc.make_camera(**c), op1)
+        gprim, gt, _, _ = scene.render_aov(ctx, cam, mk(1, 0, 1))
+        parity["primary_hit_mismatches"] = int(((gprim != oprim) | (gt.view(np.uint32) != ot.view(np.uint32))).sum())
+        parity["primary_hits_compared"] = int(oprim.size)
     if per_ray is None:
         g = golden_counters(args.workload)
         if g:
