@@ -15,6 +15,10 @@ pub const TRT_BVH_AUTO: c_int = 3;
 pub const TRT_BVH_LBVH_DEVICE: c_int = 4;
 pub const TRT_VARIANT_MEGAKERNEL: u32 = 0;
 pub const TRT_VARIANT_WAVEFRONT: u32 = 1;
+pub const TRT_FLAG_COUNT_EVENTS: u32 = 1;
+pub const TRT_FLAG_NO_TAIL_SPLIT: u32 = 2;
+pub const TRT_FLAG_BINARY_NODES: u32 = 4;
+pub const fn trt_flag_regen_min(n: u32) -> u32 { (n & 0xFF) << 8 }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct trt_camera {
