@@ -5,8 +5,9 @@
  * (file:line relative to /root/reference/raytracer/src). Plain pointers and sizes only: no C++ or torch types.
  * All functions return TRT_OK (0) or a negative trt_status; trt_last_error() gives the message of the last failure
  * on the calling thread. Nothing unwinds across this boundary (the reference panics instead: sampler/cpu.rs:35,85).
- * Thread-compatibility: one trt_ctx per host thread, or lock externally. One trt_ctx drives one GPU; multi-GPU is one
- * ctx (normally one process) per GPU with the accumulation buffers reduced by the caller (NCCL).
+ * Thread-compatibility: one trt_ctx per host thread, or lock externally. One trt_ctx drives one GPU. Multi-GPU: either
+ * trt_multi_* / trt_render_multi below (one call, one process, threads + NVLink peer reduce inside the library), or one ctx
+ * per process with the accumulation buffers reduced by the caller (NCCL; trt_render_accumulate + trt_finalize).
  * There is NO CPU fallback: every compute entry point fails with TRT_ERR_CUDA when no sm_100 device is usable.
  */
 #ifndef TRT_B200_H
@@ -72,6 +73,9 @@ typedef struct trt_params {
 #define TRT_FLAG_NO_TAIL_SPLIT 2u  /* megakernel: hand out whole pixels only (every pixel summed by one lane in sample order ->
                                     * run-to-run bit-identical f64 sums); default splits the last pixels into sample chunks
                                     * added with f64 atomics (tail balance; the f32 image can move by <= 1 ulp) */
+#define TRT_FLAG_COUNT_WALKED 8u   /* count on the walk the scene really gets (4-wide records where it has them): node_visits = records
+                                    * fetched (112 B each), sphere_tests / quad_tests = primitive records fetched. For the memory
+                                    * roofline of big scenes; ignored when TRT_FLAG_COUNT_EVENTS is set. Results do not change. */
 #define TRT_FLAG_BINARY_NODES 4u   /* tree kinds: walk the binary nodes instead of the 4-wide ones (same results; A/B and tests) */
 /* bits 8..15 of flags: megakernel tuning override, the number of lanes of a warp (1..32) that must have finished their ray
  * before the shade/regenerate block runs; 0 = chosen from the tree size (32 up to 4096 nodes, 16 above). Results do not
@@ -147,6 +151,25 @@ int trt_render_accumulate(trt_ctx* ctx, trt_scene* scene, const trt_camera* cam,
 /* Epilogue (imager.rs:35-60 + utils/image.rs:92-111) on DEVICE pointers: d_linear/d_rgb8 optional. */
 int trt_finalize(trt_ctx* ctx, const double* d_sum64, uint32_t width, uint32_t height, uint32_t spp_total,
                  float* d_linear, uint8_t* d_rgb8, trt_stats* stats);
+
+/* ---- the same render on several GPUs of one box (Renderer::render, renderer/renderer.rs:37-79, is still the one
+ * call the user makes). One host thread + one trt_ctx per listed device (a device may be listed more than once); the samples
+ * [p->sample_offset, +p->spp) are partitioned contiguously across them (Philox is keyed by the global sample index, so the set
+ * of paths is the 1-GPU set); every GPU accumulates f64 sums of its share; then ONE fused kernel per GPU reduce-scatters over
+ * NVLink peer memory — GPU k reads slice k of every peer's buffer, adds in rank order — and normalises + tone-maps its slice,
+ * which is copied straight into the caller's HOST buffers (out_linear / out_rgb8 [H*W*3], either may be NULL; both NULL = leave
+ * the result on the devices, for timing). Equals trt_render to <= 1 ulp (f64 partial sums in another order). No NCCL involved.
+ * stats: paths / rays / events summed over the devices; device_ms and finalize_ms are the MAX over the devices (they run side
+ * by side). Without peer access between two listed devices the slices are staged with cudaMemcpyPeer instead (same result). */
+typedef struct trt_multi trt_multi;
+int trt_multi_create(const int* devices, int n_devices, trt_multi** out);      /* 1..16 devices */
+int trt_multi_destroy(trt_multi* multi);
+int trt_multi_device_count(trt_multi* multi, int* n_devices, int* peer_direct /* optional: 1 = peer loads, 0 = staged copies */);
+int trt_multi_render(trt_multi* multi, trt_scene* scene, const trt_camera* cam, const trt_params* p,
+                     float* out_linear, uint8_t* out_rgb8, trt_stats* stats);
+/* create + render + destroy in one call */
+int trt_render_multi(const int* devices, int n_devices, trt_scene* scene, const trt_camera* cam, const trt_params* p,
+                     float* out_linear, uint8_t* out_rgb8, trt_stats* stats);
 
 /* Per-sample AOVs, HOST buffers indexed [pixel*spp + i]: primary-hit prim_id (0xFFFFFFFF = miss) and t, optional
  * whole-path radiance[3] and ray count. No reference counterpart (the reference has no primitive id); parity hook. */

@@ -160,9 +160,14 @@ public:
         : spp_(samples_per_pixel), max_bounces_(max_bounces), bg_(background_color.value_or(Vec3::zero())), seed_(seed),
           device_(device), bvh_kind_(bvh_kind), variant_(variant) {}
 
+    // Render on several GPUs of the box (trt_render_multi: samples-per-pixel partitioned, NVLink peer reduce + tone map on
+    // the GPUs). Empty or one entry = the single-GPU path on that device.
+    Renderer& set_devices(std::vector<int> devices) { devices_ = std::move(devices); return *this; }
+
     Image render(const Camera& camera, const World& world) {
         trt_ctx* ctx = nullptr; trt_scene* scene = nullptr;
-        check(trt_ctx_create(device_, &ctx));
+        const bool multi = devices_.size() > 1;
+        if (!multi) check(trt_ctx_create(devices_.empty() ? device_ : devices_[0], &ctx));
         try {
             check(trt_scene_create(&scene));
             std::map<const Material*, uint32_t> ids;
@@ -190,7 +195,8 @@ public:
             p.seed = seed_; p.t_min = 0.001f; p.spp_total = spp_; p.variant = variant_; p.flags = 0;
             Image img; img.width = p.width; img.height = p.height;
             img.linear.resize((size_t)p.width * p.height * 3); img.rgb8.resize(img.linear.size());
-            check(trt_render(ctx, scene, &camera.pod, &p, img.linear.data(), img.rgb8.data(), &last_stats));
+            if (multi) check(trt_render_multi(devices_.data(), (int)devices_.size(), scene, &camera.pod, &p, img.linear.data(), img.rgb8.data(), &last_stats));
+            else check(trt_render(ctx, scene, &camera.pod, &p, img.linear.data(), img.rgb8.data(), &last_stats));
             trt_scene_destroy(scene); trt_ctx_destroy(ctx);
             return img;
         } catch (...) { trt_scene_destroy(scene); trt_ctx_destroy(ctx); throw; }
@@ -198,6 +204,7 @@ public:
     trt_stats last_stats{};
 private:
     uint32_t spp_, max_bounces_; Vec3 bg_; uint64_t seed_; int device_; int bvh_kind_; uint32_t variant_;
+    std::vector<int> devices_;
 };
 
 } // namespace trt

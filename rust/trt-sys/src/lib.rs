@@ -6,6 +6,7 @@ use std::os::raw::{c_char, c_int, c_void};
 #[repr(C)] pub struct trt_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct trt_scene { _p: [u8; 0] }
 #[repr(C)] pub struct trt_sampler { _p: [u8; 0] }
+#[repr(C)] pub struct trt_multi { _p: [u8; 0] }
 
 pub const TRT_OK: c_int = 0;
 pub const TRT_BVH_REFERENCE: c_int = 0;
@@ -18,6 +19,7 @@ pub const TRT_VARIANT_WAVEFRONT: u32 = 1;
 pub const TRT_FLAG_COUNT_EVENTS: u32 = 1;
 pub const TRT_FLAG_NO_TAIL_SPLIT: u32 = 2;
 pub const TRT_FLAG_BINARY_NODES: u32 = 4;
+pub const TRT_FLAG_COUNT_WALKED: u32 = 8;
 pub const fn trt_flag_regen_min(n: u32) -> u32 { (n & 0xFF) << 8 }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]
@@ -72,6 +74,13 @@ extern "C" {
                                  d_sum64: *mut f64, stats: *mut trt_stats) -> c_int;
     pub fn trt_finalize(ctx: *mut trt_ctx, d_sum64: *const f64, width: u32, height: u32, spp_total: u32,
                         d_linear: *mut f32, d_rgb8: *mut u8, stats: *mut trt_stats) -> c_int;
+    pub fn trt_multi_create(devices: *const c_int, n_devices: c_int, out: *mut *mut trt_multi) -> c_int;
+    pub fn trt_multi_destroy(multi: *mut trt_multi) -> c_int;
+    pub fn trt_multi_device_count(multi: *mut trt_multi, n_devices: *mut c_int, peer_direct: *mut c_int) -> c_int;
+    pub fn trt_multi_render(multi: *mut trt_multi, scene: *mut trt_scene, cam: *const trt_camera, p: *const trt_params,
+                            out_linear: *mut f32, out_rgb8: *mut u8, stats: *mut trt_stats) -> c_int;
+    pub fn trt_render_multi(devices: *const c_int, n_devices: c_int, scene: *mut trt_scene, cam: *const trt_camera, p: *const trt_params,
+                            out_linear: *mut f32, out_rgb8: *mut u8, stats: *mut trt_stats) -> c_int;
     pub fn trt_render_aov(ctx: *mut trt_ctx, scene: *mut trt_scene, cam: *const trt_camera, p: *const trt_params,
                           prim_id: *mut u32, t: *mut f32, radiance: *mut f32, n_rays: *mut u32) -> c_int;
     pub fn trt_sample_batch(ctx: *mut trt_ctx, scene: *mut trt_scene, input: *const trt_sample_point, n: usize,

@@ -122,15 +122,52 @@ def test_rust_bindings_name_every_symbol():
     assert declared == bound, declared ^ bound
 
 
+def test_rust_build_lists_every_translation_unit():
+    """rust/trt-sys/build.rs had its own source list and missed trt_lbvh.cu. Both builds now read
+    csrc/sources.txt; that file must name every .cu / .cpp under csrc/ and neither build script may name one itself."""
+    csrc = os.path.join(ROOT, "tiny-raytracer_b200", "csrc")
+    listed = [ln.split()[0] for ln in open(os.path.join(csrc, "sources.txt")) if ln.strip() and not ln.startswith("#")]
+    on_disk = sorted(f for f in os.listdir(csrc) if f.endswith((".cu", ".cpp")))
+    assert sorted(listed) == on_disk, (listed, on_disk)
+    for script in (os.path.join(csrc, "build.sh"), os.path.join(ROOT, "rust", "trt-sys", "build.rs")):
+        src = open(script).read()
+        assert "sources.txt" in src, script
+        assert not re.search(r"trt_[a-z]+\.(cu|cpp)\b", src), "%s names a translation unit itself" % script
+    rs = open(os.path.join(ROOT, "rust", "raytracer-cuda", "src", "lib.rs")).read()
+    assert "geometries_in_order()" in rs and "get_geometries::<Quad>()" not in rs      # insertion order across types is kept
+
+
+def test_multi_gpu_entry_points_fail_as_values(trt):
+    """trt_multi_* / trt_render_multi argument errors are status codes; without a GPU creation fails loudly (no CPU path)."""
+    import torch
+    lib = trt._lib.load()
+    h = C.c_void_p()
+    assert lib.trt_multi_create(None, 1, C.byref(h)) == -1
+    arr = (C.c_int * 20)(*range(20))
+    assert lib.trt_multi_create(arr, 0, C.byref(h)) == -1 and lib.trt_multi_create(arr, 17, C.byref(h)) == -1
+    assert lib.trt_multi_destroy(None) == 0
+    if not torch.cuda.is_available():
+        assert lib.trt_multi_create(arr, 2, C.byref(h)) == -2 and b"no CPU path" in lib.trt_last_error()
+        sc = trt.Scene.from_desc(trt.scenes.cornell(8, 8, 1, 2), trt.BVH_AUTO)
+        with pytest.raises(trt.TrtError) as e:
+            sc.render_multi([0, 1], trt.make_camera(**trt.scenes.cornell(8, 8, 1, 2).camera), trt.make_params(8, 8, 1, 2))
+        assert e.value.code == -2
+
+
 def test_cpp_mirror_compiles_and_fails_loudly_without_gpu(trt, tmp_path):
     """include/trt.hpp + examples/cornell.cpp (main.rs translated) compile and link against the C ABI."""
     exe = str(tmp_path / "cornell")
     pkg = os.path.join(ROOT, "tiny-raytracer_b200")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"),
                            os.path.join(ROOT, "examples", "cornell.cpp"), "-o", exe, "-L" + pkg, "-ltrt_b200", "-Wl,-rpath," + pkg])
+    exe2 = str(tmp_path / "cornell_multi")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "cornell_multi.cpp"), "-o", exe2, "-L" + pkg, "-ltrt_b200", "-Wl,-rpath," + pkg])
     import torch
     if not torch.cuda.is_available():
         r = subprocess.run([exe, str(tmp_path / "o.png")], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU path" in r.stderr
+        r = subprocess.run([exe2, "2"], capture_output=True, text=True)
         assert r.returncode == 1 and "no CPU path" in r.stderr
 
 

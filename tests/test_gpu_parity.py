@@ -40,12 +40,12 @@ def params(trt, orc, desc, **kw):
             orc.make_params(w, h, spp, mb, desc.background, desc.seed, sample_offset=off, spp_total=tot))
 
 
-KINDS = [0, 1, 2]   # TRT_BVH_REFERENCE, TRT_BVH_SAH, TRT_BVH_FLAT (scenes of 1..48 primitives only)
+KINDS = [0, 1, 2]   # TRT_BVH_REFERENCE, TRT_BVH_SAH, TRT_BVH_FLAT (scenes of 1..64 primitives only: TRT_FLAT_MAX)
 
 
 def flat_ok(kind, desc):
-    if kind == 2 and not (1 <= desc.n_prims <= 48):
-        pytest.skip("TRT_BVH_FLAT takes 1..48 primitives")
+    if kind == 2 and not (1 <= desc.n_prims <= 64):
+        pytest.skip("TRT_BVH_FLAT takes 1..64 primitives")
 
 
 # ------------------------------------------------------------------ unit level: the numeric contract on the device
@@ -135,7 +135,7 @@ def test_primary_hits_full_resolution(trt, orc, ctx, kind):
     """BASELINE configs 2, 3 and 5 at their full resolution, 1 sample per pixel, primary hit only."""
     S = trt.scenes
     for desc in (S.final_scene(1200, 675, 1, 50), S.cornell(1920, 1080, 1, 50), S.glass_cornell(3840, 2160, 1, 100)):
-        if kind == 2 and desc.n_prims > 48:
+        if kind == 2 and desc.n_prims > 64:
             continue
         osc, ocam, cam = both(trt, orc, desc)
         sc = trt.Scene.from_desc(desc, kind)
@@ -660,3 +660,165 @@ def test_differential_fuzz_campaign(trt, ctx):
     r = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_parity.py"), "120", "777"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
+
+
+# ------------------------------------------------------------------ round 2: the gaps VERDICT r1 named
+def _one_prim_desc(trt, prim_kind, data):
+    d = np.zeros((1, 12), np.float32); d[0, :len(data)] = data
+    return trt.scenes.SceneDesc("one", [(0, (0.5, 0.5, 0.5), 0.0)], np.array([prim_kind], np.uint32), d, np.zeros(1, np.uint32))
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3, 4])
+def test_reference_kat_rays_through_the_cuda_path(trt, orc, ctx, kind):
+    """The reference's OWN known-answer rays — hittable/sphere.rs:68-100 (test_sphere_hit) and hittable/quad.rs:67-96
+    (test_quad_hit) — pushed through trt_trace_rays for every BVH kind (round 1 ran them through the oracle only):
+    same hit / miss, t equal to the reference's expected value under the reference's own tolerance, and equal to the
+    oracle bit for bit."""
+    import math
+    norm = lambda v: (np.float32(v) / np.sqrt(np.float32(np.dot(np.float32(v), np.float32(v))))).astype(np.float32)   # Ray::new, ray.rs:12-14
+    # sphere (0,0,-1) r 0.5: straight hit t = 0.5; oblique hit t ~ sqrt(3)/2 (1e-2, as the reference asserts); miss
+    sc = trt.Scene.from_desc(_one_prim_desc(trt, 0, [0, 0, -1, 0.5]), kind)
+    osc = orc.Scene.from_desc(_one_prim_desc(trt, 0, [0, 0, -1, 0.5]))
+    o = np.zeros((3, 3), np.float32)
+    d = np.stack([norm([0, 0, -1]), norm([0, math.sqrt(3.0), -3.0]), norm([0, -1, -1])])
+    prim, t = sc.trace_rays(ctx, o, d, 0.0)
+    oprim, ot = osc.trace_rays(o, d, 0.0, use_bvh=True)
+    assert list(prim) == [0, 0, 0xFFFFFFFF] and t[0] == 0.5 and abs(t[1] - math.sqrt(3) / 2) < 1e-2
+    assert np.array_equal(prim, oprim) and np.array_equal(bits(t), bits(ot))
+    p1 = o[1] + t[1] * d[1]
+    assert np.linalg.norm(p1 - np.float32([0, math.sqrt(3) / 4, -0.75])) < 1e-2
+    # quad corner 0, u = x, v = 3z: hit from above t = 1; diagonal hit t = sqrt 2 (1e-6); a ray that leaves the quad's extent
+    sc = trt.Scene.from_desc(_one_prim_desc(trt, 1, [0, 0, 0, 1, 0, 0, 0, 0, 3]), kind)
+    osc = orc.Scene.from_desc(_one_prim_desc(trt, 1, [0, 0, 0, 1, 0, 0, 0, 0, 3]))
+    o = np.float32([[0, 1, 0], [0, 1, 1], [0, 1, 1]])
+    d = np.stack([norm([0, -1, 0]), norm([0, -1, -1]), norm([0, -1, -1.1])])
+    prim, t = sc.trace_rays(ctx, o, d, 0.0)
+    oprim, ot = osc.trace_rays(o, d, 0.0, use_bvh=True)
+    assert list(prim) == [0, 0, 0xFFFFFFFF] and t[0] == 1.0 and abs(t[1] - math.sqrt(2)) < 1e-6
+    assert np.all(np.abs(o[1] + t[1] * d[1]) < 1e-6)
+    assert np.array_equal(prim, oprim) and np.array_equal(bits(t), bits(ot))
+
+
+@pytest.mark.parametrize("kind", [3, 1])     # TRT_BVH_AUTO (= trees built on the GPU at this size) and the host-built SAH tree
+def test_c4_million_spheres_matches_oracle(trt, orc, ctx, kind):
+    """BASELINE config 4 at its REAL scene size — 10^6 random spheres, depth 50 — at a quarter of the resolution and one
+    sample per pixel so that the oracle finishes in seconds: primary hits, path lengths and per-sample radiance bit-exact,
+    ray counts equal, image <= 1 ulp (whole-pixel items: in fact bit-exact)."""
+    desc = trt.scenes.random_spheres(1_000_000, 480, 270, 1, 50)
+    osc, ocam, cam = both(trt, orc, desc)
+    p, op = params(trt, orc, desc, flags=2)
+    oprim, ot, orad, onr = osc.render_aov(ocam, op, True, True)
+    olin, ou8, ost, _ = osc.render(ocam, op)
+    sc = trt.Scene.from_desc(desc, kind)
+    sc.upload(ctx)
+    if kind == 3:
+        assert sc.build_times()["device_build_ms"] > 0          # AUTO resolved to the device build
+    prim, t, rad, nr = sc.render_aov(ctx, cam, p, True, True)
+    same = (nr == onr) & (bits(rad) == bits(orad)).all(1) & (prim == oprim) & (bits(t) == bits(ot))
+    assert same.all(), "%d of %d samples differ" % (int((~same).sum()), same.size)
+    lin, u8, st = sc.render(ctx, cam, p)
+    assert (st.paths, st.rays) == (ost.paths, ost.rays)
+    assert ulp_diff(lin, olin).max() <= 1 and psnr8(u8, ou8) >= PSNR_MIN_DB
+    assert st.rays > 3 * st.paths                               # deep paths really happen in this scene
+
+
+def test_wavefront_and_event_counting_replay_order_dependent_rays(trt, orc, ctx):
+    """the wavefront extend kernel and the event-counting build of the walk skipped the replay of
+    order-dependent rays, so TRT_VARIANT_WAVEFRONT / TRT_FLAG_COUNT_EVENTS could return another hit than
+    the megakernel for a few rays per million. Same scene as test_sah_order_dependent_rays_are_replayed (200 k spheres,
+    depth 50, 1 M samples, where 3-5 such rays occur): every variant must give the oracle's ray count and image."""
+    desc = trt.scenes.random_spheres(200_000, 960, 540, 2, 50)
+    osc, ocam, cam = both(trt, orc, desc)
+    _, op = params(trt, orc, desc)
+    olin, ou8, ost, _ = osc.render(ocam, op)
+    w, h = desc.camera["width"], desc.camera["height"]
+    for kind in (trt.BVH_SAH, trt.BVH_LBVH_DEVICE):
+        sc = trt.Scene.from_desc(desc, kind)
+        for variant, flags in ((trt.VARIANT_MEGAKERNEL, 2), (trt.VARIANT_MEGAKERNEL, 2 | 1), (trt.VARIANT_WAVEFRONT, 0), (trt.VARIANT_WAVEFRONT, 4)):
+            p = trt.make_params(w, h, desc.spp, desc.max_bounces, desc.background, desc.seed, variant=variant, flags=flags)
+            lin, u8, st = sc.render(ctx, cam, p)
+            assert (st.paths, st.rays) == (ost.paths, ost.rays), (kind, variant, flags, st.rays, ost.rays)
+            d = ulp_diff(lin, olin)
+            assert d.max() <= 1, "kind %d variant %d flags %d: %d values differ by up to %d ulp" % (kind, variant, flags, int((d > 1).sum()), int(d.max()))
+
+
+def test_scene_recommit_while_streaming_sampler_is_alive(trt, orc, ctx):
+    """a scene re-committed (and re-uploaded) while a streaming sampler holds its device copy. The next submit
+    must pick up the new copy — never read freed or half-written memory — and results stay equal to the oracle."""
+    desc = trt.scenes.five_spheres(64, 48, 1, 10)
+    osc = orc.Scene.from_desc(desc)
+    sc = trt.Scene.from_desc(desc, trt.BVH_SAH)
+    rng = np.random.default_rng(3)
+    pts = np.zeros(6000, trt.SAMPLE_POINT_DTYPE)
+    pts["x"] = rng.integers(0, 64, 6000); pts["y"] = rng.integers(0, 48, 6000)
+    pts["origin"] = np.float32([-2.0, 2.0, 1.0])
+    d = rng.normal(size=(6000, 3)).astype(np.float32) * np.float32(0.08) + np.float32([2.0, -2.0, -2.0]) / np.float32(3.4641)
+    pts["direction"] = d / np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    p = trt.make_params(64, 48, 1, 10, desc.background, desc.seed)
+    want = osc.sample_batch(pts, orc.make_params(64, 48, 1, 10, desc.background, desc.seed))
+    st = trt.SamplerStream(ctx, sc, p, batch_capacity=2000)
+    st.submit(pts[:2000]); st.submit(pts[2000:4000])
+    sc.commit(trt.BVH_REFERENCE); sc.upload(ctx)                # re-commit with another kind while two batches are in flight
+    a = st.collect(); b = st.collect()
+    st.submit(pts[4000:6000])                                   # served from the new device copy
+    c = st.collect()
+    st.close()
+    got = np.concatenate([a, b, c])
+    assert np.array_equal(bits(got["color"]), bits(want["color"]))
+
+
+def test_two_gpus_equal_one_gpu_equal_oracle(trt, orc, ctx):
+    """N-GPU parity on hardware (skipped on a one-GPU box): two trt_ctx on two devices, each renders its share of the
+    samples (multigpu.partition_samples), the f64 sums are added, and the image must equal the 1-GPU image and the
+    oracle (<= 1 ulp, ray counts exactly) — through the Python plumbing AND through trt_render_multi (C ABI)."""
+    import torch
+    from tiny_raytracer_b200.multigpu import partition_samples
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    for desc in (trt.scenes.cornell(320, 200, 24, 20), trt.scenes.final_scene(160, 90, 7, 50)):
+        osc, ocam, cam = both(trt, orc, desc)
+        w, h = desc.camera["width"], desc.camera["height"]
+        p, op = params(trt, orc, desc)
+        olin, ou8, ost, _ = osc.render(ocam, op)
+        sc = trt.Scene.from_desc(desc, trt.BVH_AUTO)
+        one, one8, st1 = sc.render(ctx, cam, p)
+        ctxs = [ctx, trt.Context(1)]
+        accs, rays = [], 0
+        for r, c in enumerate(ctxs):
+            off, cnt = partition_samples(desc.spp, 2, r)
+            acc = torch.zeros(h * w * 3, dtype=torch.float64, device="cuda:%d" % r)
+            torch.cuda.synchronize(r)
+            pr, _ = params(trt, orc, desc, spp=cnt, sample_offset=off, spp_total=desc.spp)
+            s = sc.render_accumulate(c, cam, pr, acc.data_ptr())
+            c.synchronize()
+            rays += int(s.rays); accs.append(acc)
+        total = accs[0] + accs[1].to("cuda:0")
+        lin = (total * (1.0 / desc.spp)).to(torch.float32).cpu().numpy().reshape(h, w, 3)
+        assert rays == st1.rays == ost.rays
+        assert ulp_diff(lin, one).max() <= 1 and ulp_diff(lin, olin).max() <= 1
+        # the same through the C ABI: one call, both devices, P2P reduce-scatter + tone map on the GPUs
+        mlin, mu8, mst = sc.render_multi([0, 1], cam, p)
+        assert (mst.paths, mst.rays) == (ost.paths, ost.rays)
+        assert ulp_diff(mlin, one).max() <= 1 and ulp_diff(mlin, olin).max() <= 1
+        assert np.abs(mu8.astype(int) - ou8.astype(int)).max() <= 1 and psnr8(mu8, ou8) >= PSNR_MIN_DB
+        ctxs[1].close()
+
+
+def test_render_multi_on_one_device_equals_render(trt, orc, ctx):
+    """trt_render_multi with a device list of length 1 (and with the same device twice: two ctx, two shares, one GPU) goes
+    through the same partition + reduce-scatter + tone-map path as the 8-GPU run and must equal trt_render and the oracle."""
+    desc = trt.scenes.cornell_spheres(200, 120, 10, 20)
+    osc, ocam, cam = both(trt, orc, desc)
+    p, op = params(trt, orc, desc)
+    olin, ou8, ost, _ = osc.render(ocam, op)
+    sc = trt.Scene.from_desc(desc, trt.BVH_AUTO)
+    one, one8, st1 = sc.render(ctx, cam, p)
+    for devs in ([0], [0, 0], [0, 0, 0]):
+        lin, u8, st = sc.render_multi(devs, cam, p)
+        assert (st.paths, st.rays) == (ost.paths, ost.rays) == (st1.paths, st1.rays)
+        assert ulp_diff(lin, olin).max() <= 1 and ulp_diff(lin, one).max() <= 1
+        assert np.abs(u8.astype(int) - ou8.astype(int)).max() <= 1
+    with pytest.raises(trt.TrtError):
+        sc.render_multi([], cam, p)
+    with pytest.raises(trt.TrtError):
+        sc.render_multi([99], cam, p)

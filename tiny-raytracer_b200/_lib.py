@@ -13,6 +13,7 @@ VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT = 0, 1
 FLAG_COUNT_EVENTS = 1
 FLAG_NO_TAIL_SPLIT = 2
 FLAG_BINARY_NODES = 4
+FLAG_COUNT_WALKED = 8
 
 
 class TrtError(RuntimeError):
@@ -79,6 +80,11 @@ SYMBOLS = {
     "trt_render": (C.c_int, [_P, _P, C.POINTER(Camera), C.POINTER(Params), _P, _P, C.POINTER(Stats)]),
     "trt_render_accumulate": (C.c_int, [_P, _P, C.POINTER(Camera), C.POINTER(Params), _P, C.POINTER(Stats)]),
     "trt_finalize": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, C.POINTER(Stats)]),
+    "trt_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "trt_multi_destroy": (C.c_int, [_P]),
+    "trt_multi_device_count": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "trt_multi_render": (C.c_int, [_P, _P, C.POINTER(Camera), C.POINTER(Params), _P, _P, C.POINTER(Stats)]),
+    "trt_render_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, _P, C.POINTER(Camera), C.POINTER(Params), _P, _P, C.POINTER(Stats)]),
     "trt_render_aov": (C.c_int, [_P, _P, C.POINTER(Camera), C.POINTER(Params), _P, _P, _P, _P]),
     "trt_sample_batch": (C.c_int, [_P, _P, _P, C.c_size_t, C.POINTER(Params), _P]),
     "trt_sampler_create": (C.c_int, [_P, _P, C.POINTER(Params), C.c_size_t, C.POINTER(_P)]),

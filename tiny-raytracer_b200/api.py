@@ -38,6 +38,7 @@ class Context:
         L.check(self._lib.trt_ctx_create(int(device), C.byref(h)))
         self._h = h
         self.device = int(device)
+        self.stream_handle = None      # None = the ctx's own non-blocking stream; else the cudaStream_t given to set_stream
 
     def close(self):
         if getattr(self, "_h", None):
@@ -68,6 +69,47 @@ class Context:
     def set_stream(self, cuda_stream: int):
         """Run on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = legacy default stream."""
         L.check(self._lib.trt_ctx_set_stream(self._h, C.c_void_p(int(cuda_stream)) if cuda_stream else None))
+        self.stream_handle = int(cuda_stream or 0)
+
+
+class MultiContext:
+    """Several GPUs of one box behind one handle (trt_multi): contexts, peer mappings and buffers are created once and
+    reused across renders. `devices` may list a device more than once (two shares on one GPU: tests)."""
+
+    def __init__(self, devices):
+        self._lib = L.load()
+        devs = [int(d) for d in devices]
+        arr = (C.c_int * max(len(devs), 1))(*devs)
+        h = C.c_void_p()
+        L.check(self._lib.trt_multi_create(arr, len(devs), C.byref(h)))
+        self._h, self.devices = h, devs
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.trt_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def peer_direct(self) -> bool:
+        n, d = C.c_int(), C.c_int()
+        L.check(self._lib.trt_multi_device_count(self._h, C.byref(n), C.byref(d)))
+        return bool(d.value)
+
+    def render(self, scene: "Scene", cam: L.Camera, params: L.Params, want_linear=True, want_rgb8=True):
+        """trt_multi_render: HOST buffers out; with both outputs off the result stays on the devices (timing)."""
+        n = params.width * params.height * 3
+        lin = np.empty(n, np.float32) if want_linear else None
+        u8 = np.empty(n, np.uint8) if want_rgb8 else None
+        st = L.Stats()
+        L.check(self._lib.trt_multi_render(self._h, scene._h, C.byref(cam), C.byref(params), _ptr(lin), _ptr(u8), C.byref(st)))
+        shape = (params.height, params.width, 3)
+        return (None if lin is None else lin.reshape(shape)), (None if u8 is None else u8.reshape(shape)), st
 
 
 def make_camera(focus_distance, defocus_angle, position, look_at, up, vertical_fov, width, height) -> L.Camera:
@@ -184,6 +226,17 @@ class Scene:
         L.check(self._lib.trt_render(ctx._h, self._h, C.byref(cam), C.byref(params), _ptr(lin), _ptr(u8), C.byref(st)))
         shape = (params.height, params.width, 3)
         return (None if lin is None else lin.reshape(shape)), (None if u8 is None else u8.reshape(shape)), st
+
+    def render_multi(self, devices, cam: L.Camera, params: L.Params):
+        """trt_render_multi: one call, several GPUs (create + render + destroy); HOST buffers out."""
+        devs = [int(d) for d in devices]
+        arr = (C.c_int * max(len(devs), 1))(*devs)
+        n = params.width * params.height * 3
+        lin = np.empty(n, np.float32); u8 = np.empty(n, np.uint8)
+        st = L.Stats()
+        L.check(self._lib.trt_render_multi(arr, len(devs), self._h, C.byref(cam), C.byref(params), _ptr(lin), _ptr(u8), C.byref(st)))
+        shape = (params.height, params.width, 3)
+        return lin.reshape(shape), u8.reshape(shape), st
 
     def render_accumulate(self, ctx: Context, cam: L.Camera, params: L.Params, d_sum64_ptr: int, want_stats=True):
         st = L.Stats() if want_stats else None
@@ -456,20 +509,31 @@ class Image:
 class Renderer:
     """renderer::Renderer::new(samples_per_pixel, num_sampler_threads, max_bounces, progressbar, background_color)
     and `render(camera, world) -> Image` (renderer/renderer.rs:21-79). `num_sampler_threads` and `progressbar` are
-    accepted for signature compatibility and ignored: generator, sampler and imager all run on the GPU."""
+    accepted for signature compatibility and ignored: generator, sampler and imager all run on the GPU.
+    `devices=[0, 1, ...]` renders on several GPUs of the box through trt_render_multi (samples-per-pixel partitioned,
+    NVLink peer reduce + tone map on the GPUs); the default is one GPU (`device`)."""
 
     def __init__(self, samples_per_pixel, num_sampler_threads=0, max_bounces=20, progressbar=False, background_color=None,
-                 *, seed=1, device=0, bvh_kind=BVH_SAH, variant=VARIANT_MEGAKERNEL):
+                 *, seed=1, device=0, bvh_kind=BVH_AUTO, variant=VARIANT_MEGAKERNEL, devices=None):
         self.samples_per_pixel, self.max_bounces = int(samples_per_pixel), int(max_bounces)
         self.background_color = _v(background_color) if background_color is not None else (0.0, 0.0, 0.0)   # renderer.rs:33
         self.seed, self.device, self.bvh_kind, self.variant = int(seed), int(device), int(bvh_kind), int(variant)
+        self.devices = [int(d) for d in devices] if devices else None
         self.last_stats = None
 
     @classmethod
     def new(cls, *a, **k): return cls(*a, **k)
 
     def render(self, camera: Camera, world: World) -> Image:
-        ctx = Context(self.device)
+        if self.devices and len(self.devices) > 1:
+            scene = Scene.from_desc(world.to_desc(), self.bvh_kind)
+            w, h = camera.get_image_size()
+            p = make_params(w, h, self.samples_per_pixel, self.max_bounces, self.background_color, self.seed, variant=self.variant)
+            lin, u8, st = scene.render_multi(self.devices, camera.pod, p)
+            self.last_stats = st
+            scene.close()
+            return Image(lin, u8)
+        ctx = Context(self.devices[0] if self.devices else self.device)
         try:
             scene = Scene.from_desc(world.to_desc(), self.bvh_kind)
             w, h = camera.get_image_size()

@@ -3,8 +3,12 @@
 #include "../../include/trt.h"
 #include "trt_kernels.h"
 #include "trt_scene.hpp"
+#include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -70,10 +74,11 @@ int trt_ctx_create(int device_ordinal, trt_ctx** out) {
     if (!c) return fail(TRT_ERR_OOM, "trt_ctx_create: host allocation failed");
     c->device = device_ordinal; c->sm_count = prop.multiProcessorCount;
     std::snprintf(c->name, sizeof c->name, "%s", prop.name);
-    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    cudaError_t ce = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     c->stream = c->own_stream;
-    for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&c->ev[i]));
-    CU(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long) + 64));
+    for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&c->ev[i]);
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long) + 64);
+    if (ce != cudaSuccess) { trt_ctx_destroy(c); return fail_cuda("trt_ctx_create", ce); }    // frees whatever was created
     c->d_next_item = (unsigned int*)(c->d_counters + 8);
     *out = c;
     return TRT_OK;
@@ -81,7 +86,7 @@ int trt_ctx_create(int device_ordinal, trt_ctx** out) {
 int trt_ctx_destroy(trt_ctx* c) {
     if (!c) return TRT_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 4; ++i) if (c->scratch[i]) cudaFree(c->scratch[i]);
     if (c->d_counters) cudaFree(c->d_counters);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -196,6 +201,9 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
     const void* src[11] = {f.nodes.data(), f.spheres.data(), f.quads.data(), f.sphere_meta.data(), f.quad_meta.data(), f.materials.data(), f.flat.data(), f.quad_nn.data(), f.flat_cbox.data(), f.nodes4.data(), f.nodes_ref4.data()};
     size_t off[11], total = 0;
     for (int i = 0; i < 11; ++i) { off[i] = total; total += align_up(sz[i] ? sz[i] : 16); }
+    // a re-upload frees or overwrites memory that kernels of ANY stream of this device may still be reading (the streaming
+    // sampler's two streams, a caller-owned stream): wait for all of them first. Rare (only after a re-commit).
+    if (dc.buf) CU(cudaDeviceSynchronize());
     if (dc.buf && dc.bytes < total) { cudaFree(dc.buf); dc.buf = nullptr; }
     if (!dc.buf) { CU(cudaMalloc(&dc.buf, total)); dc.bytes = total; }
     for (int i = 0; i < 11; ++i) if (sz[i] && !(device_build && i == 0) && !((device_build || f.wide_on_device) && i == 9) && !((device_build || f.ref_on_device) && i == 10)) CU(cudaMemcpyAsync((char*)dc.buf + off[i], src[i], sz[i], cudaMemcpyHostToDevice, c->stream));
@@ -221,18 +229,18 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
     }
     if (f.ref_on_device) {
         void* d_boxes = nullptr; float ms_ref = 0.f;
-        CU(cudaMalloc(&d_boxes, f.lbvh_boxes.size() * 16));
-        cudaError_t e = cudaMemcpyAsync(d_boxes, f.lbvh_boxes.data(), f.lbvh_boxes.size() * 16, cudaMemcpyHostToDevice, c->stream);
+        cudaError_t e = cudaMalloc(&d_boxes, f.lbvh_boxes.size() * 16);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_boxes, f.lbvh_boxes.data(), f.lbvh_boxes.size() * 16, cudaMemcpyHostToDevice, c->stream);
         if (e == cudaSuccess) e = ref_order(d_boxes, &ms_ref);
-        cudaFree(d_boxes);
+        if (d_boxes) cudaFree(d_boxes);
         if (e != cudaSuccess) return fail_cuda("trt_scene_upload: device reference order", e);
         s->host.device_build_ms = ms_ref;
     }
     if (device_build) {
         // the walked tree on the GPU: Morton codes + radix sort + Karras hierarchy + bottom-up boxes (trt_lbvh.cu)
         void *d_boxes = nullptr, *d_tmp = nullptr;
-        CU(cudaMalloc(&d_boxes, f.lbvh_boxes.size() * 16));
-        cudaError_t e = cudaMalloc(&d_tmp, trtk::lbvh_tmp_bytes((uint32_t)n_prims));
+        cudaError_t e = cudaMalloc(&d_boxes, f.lbvh_boxes.size() * 16);        // no early return below: both temporaries are freed on every path
+        if (e == cudaSuccess) e = cudaMalloc(&d_tmp, trtk::lbvh_tmp_bytes((uint32_t)n_prims));
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_boxes, f.lbvh_boxes.data(), f.lbvh_boxes.size() * 16, cudaMemcpyHostToDevice, c->stream);
         uint32_t depth = 0; float ms = 0.f;
         if (e == cudaSuccess) e = trtk::build_lbvh(d_boxes, (uint32_t)n_prims, (char*)dc.buf + off[0], (char*)dc.buf + off[9], d_tmp, &depth, &ms, c->stream);
@@ -245,7 +253,7 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
         // Node::new itself on the device: the reference leaf order (tie rule) and the reference tree's wide nodes (replay)
         float ms_ref = 0.f;
         if (e == cudaSuccess) e = ref_order(d_boxes, &ms_ref);
-        cudaFree(d_boxes);
+        if (d_boxes) cudaFree(d_boxes);
         if (e != cudaSuccess) return fail_cuda("trt_scene_upload: device BVH build", e);
         s->host.flat.max_depth = depth; s->host.device_build_ms = ms + ms_ref;
         if (depth > TRT_MAX_STACK) return fail(TRT_ERR_UNSUPPORTED, "trt_scene_upload: device-built tree deeper than the traversal stack; commit with TRT_BVH_SAH");
@@ -308,6 +316,7 @@ static int check_render_args(trt_ctx* c, trt_scene* s, const trt_camera* cam, co
     return TRT_OK;
 }
 
+static int render_into(trt_ctx* c, trt_scene* s, const trt_camera* cam, const trt_params* p, double* d_sum64, trt_stats* stats);
 static int render_into(trt_ctx* c, trt_scene* s, const trt_camera* cam, const trt_params* p, double* d_sum64, trt_stats* stats) {
     int rc = trt_scene_upload(c, s); if (rc) return rc;
     const trtk::SceneView& v = s->on_device[c->device].view;
@@ -387,6 +396,196 @@ int trt_render(trt_ctx* c, trt_scene* s, const trt_camera* cam, const trt_params
     return TRT_OK;
 }
 
+// ------------------------------------------------------------------ multi-GPU behind the boundary
+// Renderer::render (renderer/renderer.rs:37-79) on the GPUs of one box, from ONE call of a C / C++ / Rust host: one host
+// thread and one trt_ctx per device, samples-per-pixel partitioned contiguously (rank k renders global sample indices
+// [offset + k*spp/N, ...), Philox keyed by the global index, so the union of paths is the 1-GPU set), every GPU keeps the f64
+// sums of its samples, then the fused reduce-scatter + tone-map kernel of trt_multi.cu: GPU k pulls slice k of every peer's
+// buffer over NVLink (peer-mapped loads), adds in rank order, normalises and tone-maps, and copies its slice of the result
+// straight into the caller's host buffers — N PCIe links in parallel. No NCCL, no Python.
+namespace {
+struct Barrier {            // C++17 has no std::barrier
+    std::mutex m; std::condition_variable cv; int n, waiting = 0; unsigned gen = 0;
+    explicit Barrier(int n_) : n(n_) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        const unsigned g = gen;
+        if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+struct MultiSlot {
+    int device = 0; trt_ctx* ctx = nullptr;
+    double* d_sum = nullptr; size_t cap_values = 0;              // whole-image f64 sums of this rank's samples
+    float* d_lin = nullptr; uint8_t* d_u8 = nullptr; double* d_stage = nullptr; size_t cap_slice = 0, cap_stage = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int rc = TRT_OK; std::string err; trt_stats st{};
+};
+}
+struct trt_multi {
+    std::vector<MultiSlot> slot;
+    bool direct = true;          // every pair of distinct devices can peer-load: the reduce reads the peers' buffers in place
+};
+
+int trt_multi_destroy(trt_multi* m) {
+    if (!m) return TRT_OK;
+    for (MultiSlot& k : m->slot) {
+        if (!k.ctx) continue;
+        cudaSetDevice(k.device);
+        cudaStreamSynchronize(k.ctx->stream);
+        if (k.d_sum) cudaFree(k.d_sum);
+        if (k.d_lin) cudaFree(k.d_lin);
+        if (k.d_u8) cudaFree(k.d_u8);
+        if (k.d_stage) cudaFree(k.d_stage);
+        if (k.ev0) cudaEventDestroy(k.ev0);
+        if (k.ev1) cudaEventDestroy(k.ev1);
+        trt_ctx_destroy(k.ctx);
+    }
+    delete m;
+    return TRT_OK;
+}
+
+int trt_multi_create(const int* devices, int n_devices, trt_multi** out) {
+    if (!out) return fail(TRT_ERR_INVALID, "trt_multi_create: out is null");
+    *out = nullptr;
+    if (!devices || n_devices < 1 || n_devices > TRT_MULTI_MAX_DEVICES) return fail(TRT_ERR_INVALID, "trt_multi_create: 1..16 devices");
+    trt_multi* m = new (std::nothrow) trt_multi();
+    if (!m) return fail(TRT_ERR_OOM, "trt_multi_create: host allocation failed");
+    m->slot.resize((size_t)n_devices);
+    for (int i = 0; i < n_devices; ++i) {
+        MultiSlot& k = m->slot[(size_t)i];
+        k.device = devices[i];
+        int rc = trt_ctx_create(devices[i], &k.ctx);
+        if (rc) { std::string e = g_last_error; trt_multi_destroy(m); return fail(rc, e); }
+        cudaError_t ce = cudaEventCreate(&k.ev0);
+        if (ce == cudaSuccess) ce = cudaEventCreate(&k.ev1);
+        if (ce != cudaSuccess) { trt_multi_destroy(m); return fail_cuda("trt_multi_create", ce); }
+    }
+    // peer mapping in both directions for every pair of distinct devices (NVLink / NVSwitch on a B200 box)
+    for (int i = 0; i < n_devices && m->direct; ++i)
+        for (int j = 0; j < n_devices; ++j) {
+            const int a = devices[i], b = devices[j];
+            if (a == b) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, a, b) != cudaSuccess || !can) { m->direct = false; break; }
+            cudaSetDevice(a);
+            cudaError_t ce = cudaDeviceEnablePeerAccess(b, 0);
+            if (ce == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();      // fine: clear the sticky-less error
+            else if (ce != cudaSuccess) { cudaGetLastError(); m->direct = false; break; }
+        }
+    if (const char* e = std::getenv("TRT_MULTI_STAGED")) if (e[0] == '1') m->direct = false;    // test hook: force the copy path
+    *out = m;
+    return TRT_OK;
+}
+int trt_multi_device_count(trt_multi* m, int* n_devices, int* peer_direct) {
+    if (!m || !n_devices) return fail(TRT_ERR_INVALID, "trt_multi_device_count: null argument");
+    *n_devices = (int)m->slot.size();
+    if (peer_direct) *peer_direct = m->direct ? 1 : 0;
+    return TRT_OK;
+}
+
+static int render_into(trt_ctx* c, trt_scene* s, const trt_camera* cam, const trt_params* p, double* d_sum64, trt_stats* stats);
+
+int trt_multi_render(trt_multi* m, trt_scene* s, const trt_camera* cam, const trt_params* p, float* out_linear, uint8_t* out_rgb8, trt_stats* stats) {
+    if (!m || m->slot.empty()) return fail(TRT_ERR_INVALID, "trt_multi_render: null handle");
+    int rc = check_render_args(m->slot[0].ctx, s, cam, p, "trt_multi_render"); if (rc) return rc;
+    const int N = (int)m->slot.size();
+    const size_t n_values = (size_t)p->width * p->height * 3, pairs = (n_values + 1) / 2;
+    uint32_t spp_total = p->spp_total ? p->spp_total : p->spp;
+    if (spp_total == 0) spp_total = 1;
+    std::vector<size_t> cut((size_t)N + 1);                         // slice k = [cut[k], cut[k+1]), even boundaries (double2 loads)
+    for (int k = 0; k <= N; ++k) cut[(size_t)k] = std::min(n_values, 2 * (pairs * (size_t)k / (size_t)N));
+    cut[(size_t)N] = n_values;
+    size_t max_slice = 0;
+    for (int k = 0; k < N; ++k) max_slice = std::max(max_slice, cut[(size_t)k + 1] - cut[(size_t)k]);
+    max_slice = (max_slice + 1) & ~(size_t)1;
+    // buffers and the scene's device copies: serially, on the calling thread (trt_scene_upload also writes host-side state)
+    for (MultiSlot& k : m->slot) {
+        CU(cudaSetDevice(k.device));
+        if (k.cap_values < n_values) {
+            if (k.d_sum) { cudaFree(k.d_sum); k.d_sum = nullptr; k.cap_values = 0; }
+            CU(cudaMalloc((void**)&k.d_sum, (n_values + 2) * sizeof(double))); k.cap_values = n_values;
+        }
+        if (k.cap_slice < max_slice) {
+            if (k.d_lin) { cudaFree(k.d_lin); k.d_lin = nullptr; } if (k.d_u8) { cudaFree(k.d_u8); k.d_u8 = nullptr; } k.cap_slice = 0;
+            CU(cudaMalloc((void**)&k.d_lin, max_slice * sizeof(float))); CU(cudaMalloc((void**)&k.d_u8, max_slice)); k.cap_slice = max_slice;
+        }
+        if (!m->direct && k.cap_stage < max_slice * (size_t)N) {
+            if (k.d_stage) { cudaFree(k.d_stage); k.d_stage = nullptr; k.cap_stage = 0; }
+            CU(cudaMalloc((void**)&k.d_stage, max_slice * (size_t)N * sizeof(double))); k.cap_stage = max_slice * (size_t)N;
+        }
+        if ((rc = trt_scene_upload(k.ctx, s))) return rc;
+    }
+    Barrier bar(N);
+    std::vector<int> failed_flag(1, 0);
+    std::mutex fail_m;
+    auto worker = [&](int r) {
+        MultiSlot& k = m->slot[(size_t)r];
+        std::memset(&k.st, 0, sizeof k.st); k.rc = TRT_OK; k.err.clear();
+        auto bad = [&](int code) { k.rc = code; k.err = g_last_error; std::lock_guard<std::mutex> lk(fail_m); failed_flag[0] = 1; };
+        auto cu = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && k.rc == TRT_OK) bad(fail_cuda(what, e)); return e == cudaSuccess; };
+        cudaStream_t st = k.ctx->stream;
+        // ---- this rank's share of the samples: contiguous, balanced (first spp % N ranks get one more)
+        const uint32_t base = p->spp / (uint32_t)N, extra = p->spp % (uint32_t)N;
+        const uint32_t cnt = base + ((uint32_t)r < extra ? 1u : 0u), off = (uint32_t)r * base + std::min((uint32_t)r, extra);
+        if (cu(cudaSetDevice(k.device), "cudaSetDevice") && cu(cudaMemsetAsync(k.d_sum, 0, n_values * sizeof(double), st), "cudaMemsetAsync")) {
+            if (cnt) {
+                trt_params q = *p; q.spp = cnt; q.sample_offset = p->sample_offset + off; q.spp_total = spp_total;
+                int rc2 = render_into(k.ctx, s, cam, &q, k.d_sum, &k.st);       // synchronises the stream (stats)
+                if (rc2) bad(rc2);
+            } else cu(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+        }
+        bar.wait();                                                  // every rank's sums are complete and visible
+        if (failed_flag[0]) return;
+        // ---- reduce-scatter + epilogue of slice r, then the slice goes home over this GPU's own PCIe link
+        const size_t b = cut[(size_t)r], e = cut[(size_t)r + 1], len = e - b;
+        const double* src[TRT_MULTI_MAX_DEVICES];
+        for (int q = 0; q < N; ++q) {
+            const MultiSlot& o = m->slot[(size_t)q];
+            if (m->direct || o.device == k.device) src[q] = o.d_sum;
+            else {      // no peer mapping: copy the peer's slice into a local staging area first
+                double* dst = k.d_stage + (size_t)q * max_slice;
+                if (len) cu(cudaMemcpyPeerAsync(dst, k.device, o.d_sum + b, o.device, len * sizeof(double), st), "cudaMemcpyPeerAsync");
+                src[q] = dst - b;                                    // indexed with whole-image indices by the kernel
+            }
+        }
+        cu(cudaEventRecord(k.ev0, st), "cudaEventRecord");
+        cu(trtk::launch_reduce_scatter_finalize(src, N, b, e, spp_total, k.d_lin, k.d_u8, k.ctx->sm_count, st), "launch_reduce_scatter_finalize");
+        cu(cudaEventRecord(k.ev1, st), "cudaEventRecord");
+        if (out_linear && len) cu(cudaMemcpyAsync(out_linear + b, k.d_lin, len * sizeof(float), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync");
+        if (out_rgb8 && len) cu(cudaMemcpyAsync(out_rgb8 + b, k.d_u8, len, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync");
+        cu(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+        float ms = 0.f;
+        if (k.rc == TRT_OK && cu(cudaEventElapsedTime(&ms, k.ev0, k.ev1), "cudaEventElapsedTime")) { k.st.finalize_ms = ms; k.st.launches += len ? 1 : 0; }
+    };
+    std::vector<std::thread> th;
+    for (int r = 1; r < N; ++r) th.emplace_back(worker, r);
+    worker(0);
+    for (std::thread& t : th) t.join();
+    trt_stats tot; std::memset(&tot, 0, sizeof tot);
+    for (const MultiSlot& k : m->slot) {
+        if (k.rc) return fail(k.rc, "trt_multi_render (device " + std::to_string(k.device) + "): " + k.err);
+        tot.paths += k.st.paths; tot.rays += k.st.rays; tot.node_visits += k.st.node_visits; tot.sphere_tests += k.st.sphere_tests; tot.quad_tests += k.st.quad_tests;
+        tot.launches += k.st.launches;
+        tot.device_ms = std::max(tot.device_ms, k.st.device_ms);            // the ranks run side by side: the slowest one counts
+        tot.finalize_ms = std::max(tot.finalize_ms, k.st.finalize_ms);
+    }
+    if (stats) *stats = tot;
+    CU(cudaSetDevice(m->slot[0].device));
+    return TRT_OK;
+}
+
+int trt_render_multi(const int* devices, int n_devices, trt_scene* s, const trt_camera* cam, const trt_params* p,
+                     float* out_linear, uint8_t* out_rgb8, trt_stats* stats) {
+    trt_multi* m = nullptr;
+    int rc = trt_multi_create(devices, n_devices, &m); if (rc) return rc;
+    rc = trt_multi_render(m, s, cam, p, out_linear, out_rgb8, stats);
+    std::string e = g_last_error;
+    trt_multi_destroy(m);
+    if (rc) g_last_error = e;
+    return rc;
+}
+
 int trt_render_aov(trt_ctx* c, trt_scene* s, const trt_camera* cam, const trt_params* p, uint32_t* prim_id, float* t, float* radiance, uint32_t* n_rays) {
     int rc = check_render_args(c, s, cam, p, "trt_render_aov"); if (rc) return rc;
     CU(cudaSetDevice(c->device));
@@ -434,6 +633,7 @@ struct SamplerSlot {
 };
 struct trt_sampler {
     trt_ctx* ctx; trt_scene* scene; trt_params params; size_t capacity; uint32_t next_sample;
+    uint64_t scene_version;          // host scene version the device copy had when it was last (re-)uploaded for this adapter
     SamplerSlot slot[2]; int head = 0, tail = 0, in_flight = 0;   // FIFO over the two slots
 };
 
@@ -445,6 +645,7 @@ int trt_sampler_create(trt_ctx* c, trt_scene* s, const trt_params* p, size_t bat
     trt_sampler* a = new (std::nothrow) trt_sampler();
     if (!a) return fail(TRT_ERR_OOM, "trt_sampler_create: host allocation failed");
     a->ctx = c; a->scene = s; a->params = *p; a->capacity = batch_capacity; a->next_sample = p->sample_offset;
+    a->scene_version = s->host.version;
     for (SamplerSlot& k : a->slot) {
         cudaError_t e = cudaStreamCreateWithFlags(&k.stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&k.done, cudaEventDisableTiming);
@@ -478,6 +679,13 @@ int trt_sampler_submit(trt_sampler* a, const trt_sample_point* in, size_t n) {
     if (n > a->capacity) return fail(TRT_ERR_INVALID, "trt_sampler_submit: batch larger than the adapter's capacity");
     if (a->in_flight == 2) return fail(TRT_ERR_INVALID, "trt_sampler_submit: two batches in flight, call trt_sampler_collect first");
     CU(cudaSetDevice(a->ctx->device));
+    if (!a->scene->host.committed) return fail(TRT_ERR_INVALID, "trt_sampler_submit: the scene was modified and not re-committed");
+    if (a->scene_version != a->scene->host.version || a->scene->on_device[a->ctx->device].version != a->scene->host.version) {
+        // the scene was re-committed since the last batch: bring the device copy up to date (trt_scene_upload waits for every
+        // stream of the device, so batches still in flight finish on the old copy first) and carry on with the new one
+        int rc = trt_scene_upload(a->ctx, a->scene); if (rc) return rc;
+        a->scene_version = a->scene->host.version;
+    }
     SamplerSlot& k = a->slot[a->head];
     const trtk::SceneView& v = a->scene->on_device[a->ctx->device].view;
     if (n) std::memcpy(k.h_in, in, n * sizeof(trt_sample_point));

@@ -391,13 +391,14 @@ TRT_DEV void trav_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* s
 // box before reaching it). When it does exceed it — fp cancellation on a grazing hit, a few rays in 10^6 on the sphere
 // scenes — the reference's answer depends on its own visiting order, and the ray is replayed on the REFERENCE-topology
 // tree (wide nodes, global memory), which reproduces that order. Exact for every hit whose t/entry disagreement is below
-// the culling margin above (spheres: always); TRT_BVH_LBVH_DEVICE has no reference tree and keeps the W answer.
-template <bool ORDERED, bool SMEM> TRT_DEV Hit closest_hit4(const DevScene& S, V3 o, V3 d, float t_min);
+// the culling margin above (spheres: always). Every ordered kind carries a reference tree: the host builds it for TRT_BVH_SAH,
+// the device's own Node::new (trt_lbvh.cu k_ref_*) for TRT_BVH_LBVH_DEVICE and for big SAH scenes.
+template <bool ORDERED, bool SMEM, bool COUNT> TRT_DEV Hit closest_hit4(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec);
 TRT_DEV bool needs_replay(const Trav& T, const DevScene& S) { return T.best_anom && !T.replay && T.best.ref != TRT_REF_INVALID && S.nodes_ref4 != nullptr; }
 TRT_DEV Hit ordered_replay(const DevScene& S, V3 o, V3 d, float t_min) {
     DevScene R = S;
     R.nodes4 = S.nodes_ref4; R.n_nodes4 = S.n_nodes_ref4; R.root = S.root_ref4; R.spheres = S.g_spheres; R.quads = S.g_quads;
-    return closest_hit4<false, false>(R, o, d, t_min);
+    return closest_hit4<false, false, false>(R, o, d, t_min, nullptr);
 }
 
 template <bool ORDERED, bool SMEM, bool COUNT>
@@ -406,7 +407,7 @@ TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounter
     trav_begin<COUNT>(T, S, o, d, t_min, ec);
     uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
     while (T.cur != TRT_REF_INVALID) trav_step<ORDERED, SMEM, COUNT>(T, S, stack_ref, stack_t, ec);
-    if (ORDERED && !COUNT && needs_replay(T, S)) return ordered_replay(S, o, d, t_min);
+    if (ORDERED && needs_replay(T, S)) return ordered_replay(S, o, d, t_min);   // also when counting: the replay's own events are not counted, the RESULT must not depend on the flag
     return T.best;
 }
 
@@ -420,12 +421,15 @@ TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounter
 //   re-checked against the narrowed closest hit when popped — so the leaves are met in the reference's order, each with
 //   its own box tested against the range the reference would use (lemma L: the skipped intermediate box cannot cull).
 // Either way only the number of dependent node fetches per ray changes (about half of the binary walk).
-template <bool ORDERED, bool SMEM>
-TRT_DEV void trav4_step(Trav& T, const DevScene& S, float t_min, uint32_t* stack_ref, float* stack_t) {   // t_min: the caller's (uniform) value, not a per-lane copy
+// COUNT (TRT_FLAG_COUNT_WALKED): ec->node_visits counts the wide records fetched (7 x 16 B each), sphere_tests / quad_tests the
+// primitive tests — the traffic of THIS walk, for the memory roofline of big scenes (bench.py); results are unaffected.
+template <bool ORDERED, bool SMEM, bool COUNT = false>
+TRT_DEV void trav4_step(Trav& T, const DevScene& S, float t_min, uint32_t* stack_ref, float* stack_t, EventCounters* ec = nullptr) {   // t_min: the caller's (uniform) value, not a per-lane copy
     uint32_t cur = T.cur;
     const V3 o = T.o, d = T.d, inv = T.inv;
     if (!(cur & TRT_REF_LEAF)) {
         TRT_ASSERT(cur < S.n_nodes4);
+        if (COUNT) ec->node_visits += 1;
         const float4* np = S.nodes4 + 8 * (size_t)cur;
         const float4 a0 = ld4<SMEM>(np), a1 = ld4<SMEM>(np + 1), a2 = ld4<SMEM>(np + 2);
         const float4 b0 = ld4<SMEM>(np + 3), b1 = ld4<SMEM>(np + 4), b2 = ld4<SMEM>(np + 5), rf = ld4<SMEM>(np + 6);
@@ -469,6 +473,7 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, float t_min, uint32_t* stack
         uint32_t idx = cur & TRT_REF_INDEX_MASK;
         TRT_ASSERT(idx < ((cur & TRT_REF_QUAD) ? S.n_quads : S.n_spheres));
         float t; bool h;
+        if (COUNT) { if (cur & TRT_REF_QUAD) ec->quad_tests += 1; else ec->sphere_tests += 1; }
         if (cur & TRT_REF_QUAD) h = quad_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : T.best.t, T.best.t, &t);
         else h = sphere_hit<SMEM>(S, idx, o, d, t_min, ORDERED ? TRT_INF : T.best.t, &t);
         if (h) {
@@ -493,26 +498,26 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, float t_min, uint32_t* stack
 // One step of the wide walk, or — for a lane that is replaying its ray (needs_replay) — of the reference-order walk on the
 // reference tree's wide nodes in global memory. Sharing the loop and the stack keeps the rare replay out of the hot path's
 // register budget.
-template <bool ORDERED, bool SMEM>
-TRT_DEV void trav4_any_step(Trav& T, const DevScene& S, float t_min, uint32_t* stack_ref, float* stack_t) {
+template <bool ORDERED, bool SMEM, bool COUNT = false>
+TRT_DEV void trav4_any_step(Trav& T, const DevScene& S, float t_min, uint32_t* stack_ref, float* stack_t, EventCounters* ec = nullptr) {
     if (ORDERED && T.replay) {
         DevScene R = S;
         R.nodes4 = S.nodes_ref4; R.n_nodes4 = S.n_nodes_ref4; R.spheres = S.g_spheres; R.quads = S.g_quads;
-        trav4_step<false, false>(T, R, t_min, stack_ref, stack_t);
-    } else trav4_step<ORDERED, SMEM>(T, S, t_min, stack_ref, stack_t);
+        trav4_step<false, false, COUNT>(T, R, t_min, stack_ref, stack_t, ec);
+    } else trav4_step<ORDERED, SMEM, COUNT>(T, S, t_min, stack_ref, stack_t, ec);
 }
 // restart the ray of a finished ordered walk in replay mode
 TRT_DEV void begin_replay(Trav& T, const DevScene& S) {
     T.replay = true; T.best_anom = false; T.cur = S.root_ref4; T.sp = 0;
     T.best.t = TRT_INF; T.best.ref = TRT_REF_INVALID;
 }
-template <bool ORDERED, bool SMEM>
-TRT_DEV Hit closest_hit4(const DevScene& S, V3 o, V3 d, float t_min) {
-    Trav T; EventCounters ec;
-    trav_begin<false>(T, S, o, d, t_min, &ec);
+template <bool ORDERED, bool SMEM, bool COUNT>
+TRT_DEV Hit closest_hit4(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
+    Trav T;
+    trav_begin<false>(T, S, o, d, t_min, ec);
     uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
     for (;;) {
-        while (T.cur != TRT_REF_INVALID) trav4_any_step<ORDERED, SMEM>(T, S, t_min, stack_ref, stack_t);
+        while (T.cur != TRT_REF_INVALID) trav4_any_step<ORDERED, SMEM, COUNT>(T, S, t_min, stack_ref, stack_t, ec);
         if (!(ORDERED && needs_replay(T, S))) break;
         begin_replay(T, S);
     }
@@ -769,7 +774,7 @@ TRT_DEV Hit closest_hit_flat(const float4* __restrict__ CB, float bound, const F
 template <int KIND, bool SMEM, bool COUNT>
 TRT_DEV Hit closest_hit_any(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
     if (KIND == 2) return closest_hit_flat<false>(S.flat_cbox, S.flat_bound, S.flat, S.n_flat, o, d, t_min);
-    if (KIND == 3 || KIND == 4) return closest_hit4<KIND == 3, SMEM>(S, o, d, t_min);
+    if (KIND == 3 || KIND == 4) return closest_hit4<KIND == 3, SMEM, COUNT>(S, o, d, t_min, ec);
     return closest_hit<KIND == 1, SMEM, COUNT>(S, o, d, t_min, ec);
 }
 
@@ -789,6 +794,49 @@ TRT_DEV V3 trace_path(const DevScene& S, const DevParams& P, V3 o, V3 d, uint32_
     }
     if (n_rays_out) *n_rays_out = rays;
     return color;
+}
+
+// ------------------------------------------------------------------ epilogue arithmetic (shared by k_finalize and the multi-GPU reduce)
+// Color::gamma_correction (utils/image.rs:92-98), clamp(0, 0.999) and `* 255 as u8` (utils/image.rs:100-111)
+TRT_DEV uint8_t tonemap_u8(float lin) {
+    float g = powf(lin, 1.0f / 2.2f);
+    float cl = g < 0.0f ? 0.0f : (g > 0.999f ? 0.999f : g);     // NaN stays NaN
+    float s = cl * 255.0f;
+    return (s == s) ? (uint8_t)s : (uint8_t)0;                   // `as u8`: truncation, NaN -> 0
+}
+
+// ------------------------------------------------------------------ shared-memory staging of small scenes
+// The traversal data (nodes, primitives, flat list) are staged whenever they fit; the per-hit records (meta, materials,
+// quad normals: one access per ray segment) only while they are small — the final scene has one material per sphere, and
+// staging its 31 KB of per-hit records would cap the kernel at 3 CTAs per SM instead of 4.
+#define TRT_AUX_SMEM_F4 512u       /* 8 KB */
+__host__ __device__ inline uint32_t aux_f4(uint32_t n_spheres, uint32_t n_quads, uint32_t n_materials) { return n_spheres + 2u * n_quads + 2u * n_materials; }
+// layout: [nodes or wide nodes | spheres | quads | sphere_meta | quad_meta | quad_nn | materials (the four per-hit arrays only while small) | flat list]
+template <bool SMEM, int KIND>
+__device__ __forceinline__ DevScene stage_scene(const DevScene& G) {
+    if (!SMEM) return G;
+    extern __shared__ float4 smem_f4[];
+    DevScene S = G;
+    uint32_t off = 0;
+    auto copy = [&](const float4* src, uint32_t n) -> const float4* {
+        float4* dst = smem_f4 + off;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        off += n;
+        return dst;
+    };
+    if (KIND == 3 || KIND == 4) S.nodes4 = copy(G.nodes4, 8 * G.n_nodes4);          // the walk reads only one of the two node arrays
+    else S.nodes = copy(G.nodes, 4 * G.n_nodes);
+    S.spheres = copy(G.spheres, G.n_spheres);
+    S.quads = copy(G.quads, 4 * G.n_quads);
+    if (aux_f4(G.n_spheres, G.n_quads, G.n_materials) <= TRT_AUX_SMEM_F4) {   // else: left in global memory (generic loads)
+        S.sphere_meta = (const uint4*)copy((const float4*)G.sphere_meta, G.n_spheres);
+        S.quad_meta = (const uint4*)copy((const float4*)G.quad_meta, G.n_quads);
+        S.quad_nn = copy(G.quad_nn, G.n_quads);
+        S.materials = copy(G.materials, 2 * G.n_materials);
+    }
+    S.flat = (const FlatPrim*)copy((const float4*)G.flat, 6 * G.n_flat);
+    __syncthreads();
+    return S;
 }
 
 } // namespace trtd

@@ -31,40 +31,6 @@ using namespace trtd;
 #define TRT_FLAT_THREADS 256
 #endif
 
-// ------------------------------------------------------------------ shared-memory staging of small scenes
-// The traversal data (nodes, primitives, flat list) are staged whenever they fit; the per-hit records (meta, materials,
-// quad normals: one access per ray segment) only while they are small — the final scene has one material per sphere, and
-// staging its 31 KB of per-hit records would cap the kernel at 3 CTAs per SM instead of 4.
-#define TRT_AUX_SMEM_F4 512u       /* 8 KB */
-__host__ __device__ inline uint32_t aux_f4(uint32_t n_spheres, uint32_t n_quads, uint32_t n_materials) { return n_spheres + 2u * n_quads + 2u * n_materials; }
-// layout: [nodes or wide nodes | spheres | quads | sphere_meta | quad_meta | quad_nn | materials (the four per-hit arrays only while small) | flat list]
-template <bool SMEM, int KIND>
-__device__ __forceinline__ DevScene stage_scene(const DevScene& G) {
-    if (!SMEM) return G;
-    extern __shared__ float4 smem_f4[];
-    DevScene S = G;
-    uint32_t off = 0;
-    auto copy = [&](const float4* src, uint32_t n) -> const float4* {
-        float4* dst = smem_f4 + off;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-        off += n;
-        return dst;
-    };
-    if (KIND == 3 || KIND == 4) S.nodes4 = copy(G.nodes4, 8 * G.n_nodes4);          // the walk reads only one of the two node arrays
-    else S.nodes = copy(G.nodes, 4 * G.n_nodes);
-    S.spheres = copy(G.spheres, G.n_spheres);
-    S.quads = copy(G.quads, 4 * G.n_quads);
-    if (aux_f4(G.n_spheres, G.n_quads, G.n_materials) <= TRT_AUX_SMEM_F4) {   // else: left in global memory (generic loads)
-        S.sphere_meta = (const uint4*)copy((const float4*)G.sphere_meta, G.n_spheres);
-        S.quad_meta = (const uint4*)copy((const float4*)G.quad_meta, G.n_quads);
-        S.quad_nn = copy(G.quad_nn, G.n_quads);
-        S.materials = copy(G.materials, 2 * G.n_materials);
-    }
-    S.flat = (const FlatPrim*)copy((const float4*)G.flat, 6 * G.n_flat);
-    __syncthreads();
-    return S;
-}
-
 // ------------------------------------------------------------------ megakernel
 struct MegaArgs {
     DevScene scene; DevCamera cam; DevParams p;
@@ -117,7 +83,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& A, const float4* U) {
         Hit h; h.t = TRT_INF; h.ref = TRT_REF_INVALID;
         if (alive) {
             if (KIND == 2) h = closest_hit_flat<true>(U, S.flat_bound, S.flat, S.n_flat, o, d, P.t_min);
-            else if (KIND == 3 || KIND == 4) h = closest_hit4<KIND == 3, SMEM>(S, o, d, P.t_min);
+            else if (KIND == 3 || KIND == 4) h = closest_hit4<KIND == 3, SMEM, COUNT>(S, o, d, P.t_min, &ec);
             else h = closest_hit<KIND == 1, SMEM, COUNT>(S, o, d, P.t_min, &ec);
             ++n_rays;
         }
@@ -220,7 +186,7 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
         // ---- T: one step of cpu.rs:48 for every lane whose ray is in flight
         if (T.cur != TRT_REF_INVALID) {
             if (KIND == 3 || KIND == 4) {
-                trav4_any_step<KIND == 3, SMEM>(T, S, P.t_min, stack_ref, stack_t);
+                trav4_any_step<KIND == 3, SMEM, COUNT>(T, S, P.t_min, stack_ref, stack_t, &ec);
                 if (KIND == 3 && T.cur == TRT_REF_INVALID && needs_replay(T, S)) begin_replay(T, S);     // rare: DESIGN.md §4.3
             }
             else trav_step<KIND == 1, SMEM, COUNT>(T, S, stack_ref, stack_t, &ec);
@@ -236,7 +202,7 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
         bool scatter = false;
         if (in_s && alive) {
             Hit h = T.best;
-            if (KIND == 1 && !COUNT && needs_replay(T, S)) h = ordered_replay(S, T.o, T.d, P.t_min);   // rare: DESIGN.md §4.3 (binary walk)
+            if (KIND == 1 && needs_replay(T, S)) h = ordered_replay(S, T.o, T.d, P.t_min);   // rare: DESIGN.md §4.3 (binary walk)
             if (h.ref == TRT_REF_INVALID) color = color + atten * mk(P.bg[0], P.bg[1], P.bg[2]);
             else {
                 sf = hit_record<SMEM>(S, h, T.o, T.d);
@@ -289,7 +255,7 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
                 camera_ray(A.cam, P, px, py, pixel, sample, r, &o, &dir);
                 atten = mk(1, 1, 1); color = mk(0, 0, 0); remain = P.max_bounces; alive = true;
             }
-            trav_begin<COUNT>(T, S, o, normalized(dir), P.t_min, &ec);      // Ray::new normalises, ray.rs:12-14
+            trav_begin<COUNT && (KIND < 3)>(T, S, o, normalized(dir), P.t_min, &ec);      // Ray::new normalises, ray.rs:12-14 (root-box event only for the binary counts)
             ++n_rays;
             // an empty scene (or, when counting, a ray that misses the root box) is finished at once: T.cur stays INVALID
             // and the lane re-enters S on the next pass with T.best = miss.
@@ -378,12 +344,7 @@ __global__ void __launch_bounds__(256) k_finalize(const double* __restrict__ sum
     if (i >= n) return;
     float lin = (float)(sum64[i] * inv_spp);
     if (linear) linear[i] = lin;
-    if (rgb8) {
-        float g = powf(lin, 1.0f / 2.2f);                       // Color::gamma_correction, utils/image.rs:92-98
-        float cl = g < 0.0f ? 0.0f : (g > 0.999f ? 0.999f : g);  // clamp(0, 0.999), NaN stays NaN
-        float s = cl * 255.0f;
-        rgb8[i] = (s == s) ? (uint8_t)s : (uint8_t)0;            // `as u8`: truncation, NaN -> 0
-    }
+    if (rgb8) rgb8[i] = tonemap_u8(lin);
 }
 
 __global__ void k_debug_math(size_t n, const float* u, float* s, float* c, float* cb) {
@@ -402,7 +363,7 @@ __global__ void k_debug_philox(size_t n, const uint32_t* ctr, uint32_t k0, uint3
 // ------------------------------------------------------------------ launchers
 namespace trtk {
 
-static uint32_t walk_kind(const SceneView& v, bool binary_only) {
+uint32_t walk_kind(const SceneView& v, bool binary_only) {
     if (binary_only || !v.nodes4 || !v.n_nodes4) return v.kind;
     return v.kind == 1 ? 3u : (v.kind == 0 ? 4u : v.kind);
 }
@@ -436,9 +397,12 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     // measured (B200, regen sweep): Cornell 17 nodes, glass Cornell 33, final scene 486: 32 best; 1 M spheres: 16 best (+25 %)
     if (regen == 0) regen = v.n_nodes <= 4096 ? 32u : 16u;       // (re-set below for 4-wide nodes, whose rays take half as many steps: 20)
     A.regen_min = regen > 32u ? 32u : regen;
+    const bool count_walked = (p.flags & TRT_FLAG_COUNT_WALKED) != 0 && !(p.flags & 1u);
     bool count = (p.flags & 1u) != 0;
-    // a TRT_BVH_SAH scene is walked on its 4-wide nodes unless events are counted (the counts are defined on binary nodes)
+    // a TRT_BVH_SAH scene is walked on its 4-wide nodes unless events are counted (TRT_FLAG_COUNT_EVENTS' counts are defined on
+    // binary nodes; TRT_FLAG_COUNT_WALKED counts the records of whatever walk the scene would get anyway)
     const uint32_t kind = walk_kind(v, count || (p.flags & TRT_FLAG_BINARY_NODES));
+    if (count_walked) count = true;
     if ((kind == 3 || kind == 4) && ((p.flags >> 8) & 0xFFu) == 0 && v.n_nodes > 4096) A.regen_min = 20u;    // measured: 1 M spheres 2 315 (20) vs 2 282 (16) Mrays/s
     size_t smem = scene_smem_bytes(v, kind);
     bool use_smem = smem <= 64 * 1024;
@@ -450,9 +414,11 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
         fn = (const void*)k_render_mega_flat;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_render_mega_flat, TRT_FLAT_THREADS, smem);
     } else if (kind == 3) {
-        e = use_smem ? mega_fn<3, true, false>(&fn, &blocks_per_sm, smem) : mega_fn<3, false, false>(&fn, &blocks_per_sm, smem);
+        if (count) e = use_smem ? mega_fn<3, true, true>(&fn, &blocks_per_sm, smem) : mega_fn<3, false, true>(&fn, &blocks_per_sm, smem);
+        else e = use_smem ? mega_fn<3, true, false>(&fn, &blocks_per_sm, smem) : mega_fn<3, false, false>(&fn, &blocks_per_sm, smem);
     } else if (kind == 4) {
-        e = use_smem ? mega_fn<4, true, false>(&fn, &blocks_per_sm, smem) : mega_fn<4, false, false>(&fn, &blocks_per_sm, smem);
+        if (count) e = use_smem ? mega_fn<4, true, true>(&fn, &blocks_per_sm, smem) : mega_fn<4, false, true>(&fn, &blocks_per_sm, smem);
+        else e = use_smem ? mega_fn<4, true, false>(&fn, &blocks_per_sm, smem) : mega_fn<4, false, false>(&fn, &blocks_per_sm, smem);
     } else if (v.kind == 1) {
         if (use_smem) e = count ? mega_fn<1, true, true>(&fn, &blocks_per_sm, smem) : mega_fn<1, true, false>(&fn, &blocks_per_sm, smem);
         else e = count ? mega_fn<1, false, true>(&fn, &blocks_per_sm, smem) : mega_fn<1, false, false>(&fn, &blocks_per_sm, smem);

@@ -24,6 +24,8 @@ struct SceneView {   // device copy of trt::FlatScene
     float root_min[3], root_max[3];
 };
 
+// kind as walked: 3 / 4 = the 4-wide nodes of a TRT_BVH_SAH / TRT_BVH_REFERENCE scene (when it has them and binary_only is false)
+uint32_t walk_kind(const SceneView& v, bool binary_only);
 size_t scene_smem_bytes(const SceneView& v, uint32_t kind);
 
 cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const trt_params& p, double* d_sum64,
@@ -49,6 +51,11 @@ cudaError_t launch_sample_batch(const SceneView& v, const trt_params& p, const t
 cudaError_t launch_trace(const SceneView& v, const float* d_o, const float* d_d, size_t n, float t_min, uint32_t* d_prim,
                          float* d_t, cudaStream_t st);
 cudaError_t launch_finalize(const double* d_sum64, size_t n_values, uint32_t spp_total, float* d_linear, uint8_t* d_rgb8, cudaStream_t st);
+// Multi-GPU exchange + epilogue (trt_multi.cu): slice [begin, end) of the image = sum over d_src[0..n_src) in rank order, normalised
+// and tone-mapped. d_src are device pointers valid on the launching device (own memory or peer-mapped memory of the other GPUs).
+#define TRT_MULTI_MAX_DEVICES 16
+cudaError_t launch_reduce_scatter_finalize(const double* const* d_src, int n_src, size_t begin, size_t end, uint32_t spp_total,
+                                           float* d_lin, uint8_t* d_rgb8, int sm_count, cudaStream_t st);
 cudaError_t launch_debug_math(size_t n, const float* u, float* s, float* c, float* cb, cudaStream_t st);
 cudaError_t launch_debug_philox(size_t n, const uint32_t* ctr, uint32_t k0, uint32_t k1, uint32_t* out, cudaStream_t st);
 

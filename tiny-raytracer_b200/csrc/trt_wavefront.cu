@@ -49,6 +49,8 @@ struct WfArgs {
 
 #define WF_NO_PATH 0xFFFFFFFFu
 
+// per-hit data only (hit_record reads spheres / quads / meta / normals / materials); the extend kernel stages the
+// traversal arrays with the megakernel's stage_scene<SMEM, KIND>
 template <bool SMEM>
 __device__ __forceinline__ DevScene wf_stage_scene(const DevScene& G) {
     if (!SMEM) return G;
@@ -61,8 +63,7 @@ __device__ __forceinline__ DevScene wf_stage_scene(const DevScene& G) {
         off += n;
         return dst;
     };
-    S.nodes = copy(G.nodes, 4 * G.n_nodes);
-    S.spheres = copy(G.spheres, G.n_spheres);
+    S.spheres = copy(G.spheres, G.n_spheres);                      // the shade kernel never touches the node arrays
     S.quads = copy(G.quads, 4 * G.n_quads);
     S.sphere_meta = (const uint4*)copy((const float4*)G.sphere_meta, G.n_spheres);
     S.quad_meta = (const uint4*)copy((const float4*)G.quad_meta, G.n_quads);
@@ -179,9 +180,13 @@ __global__ void __launch_bounds__(WF_THREADS) k_wf_shade(const WfArgs A) {
 }
 
 // ------------------------------------------------------------------ extend: persistent warps, per-lane ray replacement
-template <bool ORDERED, bool SMEM>
+// KIND as in the megakernel: 0 / 1 = TRT_BVH_REFERENCE / TRT_BVH_SAH on binary nodes, 4 / 3 = the same trees on their
+// 4-wide nodes. The ordered kinds replay an order-dependent ray on the reference tree exactly as the megakernel does
+// (DESIGN.md §4.3): inside the loop on wide nodes (begin_replay), by one ordered_replay call on binary nodes — so both
+// variants return the same hit for every ray, and the images differ only in the order of the f64 accumulation.
+template <int KIND, bool SMEM>
 __global__ void __launch_bounds__(WF_THREADS, 3) k_wf_extend(const WfArgs A) {
-    const DevScene S = wf_stage_scene<SMEM>(A.scene);
+    const DevScene S = stage_scene<SMEM, KIND>(A.scene);
     WfCtl* ctl = A.ctl;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t* queue = A.queue[A.q_in ^ 1];
@@ -217,9 +222,14 @@ __global__ void __launch_bounds__(WF_THREADS, 3) k_wf_extend(const WfArgs A) {
         }
         if (idle == 0xFFFFFFFFu) { if (exhausted) break; else continue; }
         if (active) {
-            trav_step<ORDERED, SMEM, false>(T, S, stack_ref, stack_t, &ec);
+            if (KIND == 3 || KIND == 4) {
+                trav4_any_step<KIND == 3, SMEM, false>(T, S, A.p.t_min, stack_ref, stack_t, nullptr);
+                if (KIND == 3 && T.cur == TRT_REF_INVALID && needs_replay(T, S)) begin_replay(T, S);     // rare: DESIGN.md §4.3
+            } else trav_step<KIND == 1, SMEM, false>(T, S, stack_ref, stack_t, &ec);
             if (T.cur == TRT_REF_INVALID) {
-                A.a1[slot] = make_float4(T.d.y, T.d.z, T.best.t, __uint_as_float(T.best.ref));
+                Hit h = T.best;
+                if (KIND == 1 && needs_replay(T, S)) h = ordered_replay(S, T.o, T.d, A.p.t_min);          // rare, binary walk
+                A.a1[slot] = make_float4(T.d.y, T.d.z, h.t, __uint_as_float(h.ref));
                 active = false;
             }
         }
@@ -264,18 +274,23 @@ cudaError_t launch_render_wavefront(const SceneView& v, const trt_camera& cam, c
     uint32_t n_start = (uint32_t)(A.total_paths < n_slots ? A.total_paths : n_slots);
     n_start = (n_start + 31u) & ~31u; if (n_start > n_slots) n_start = n_slots;
     k_wf_init<<<(n_slots + 255) / 256, 256, 0, st>>>(A.queue[0], A.rk, n_slots, A.ctl, n_start); ++launches;
-    size_t smem = 16ull * (4ull * v.n_nodes + v.n_spheres + 4ull * v.n_quads + v.n_spheres + 2ull * v.n_quads + 2ull * v.n_materials);
-    bool use_smem = smem <= 64 * 1024;
+    // shade stages the per-hit data, extend the traversal arrays of the kind it walks (wide nodes when the scene has them)
+    size_t smem_shade = 16ull * (v.n_spheres + 4ull * v.n_quads + v.n_spheres + 2ull * v.n_quads + 2ull * v.n_materials);
+    const bool shade_smem = smem_shade <= 64 * 1024;
+    if (!shade_smem) smem_shade = 0;
+    uint32_t kind = walk_kind(v, (p.flags & TRT_FLAG_BINARY_NODES) != 0);
+    if (kind == 2) kind = 0;                                   // a flat-list scene is walked on its reference-topology tree
+    size_t smem = scene_smem_bytes(v, kind);
+    const bool use_smem = smem <= 64 * 1024;
     if (!use_smem) smem = 0;
-    bool ordered = v.kind == 1;
-    const void* f_shade = use_smem ? (const void*)k_wf_shade<true> : (const void*)k_wf_shade<false>;
-    const void* f_ext = ordered ? (use_smem ? (const void*)k_wf_extend<true, true> : (const void*)k_wf_extend<true, false>)
-                                : (use_smem ? (const void*)k_wf_extend<false, true> : (const void*)k_wf_extend<false, false>);
+    const void* f_shade = shade_smem ? (const void*)k_wf_shade<true> : (const void*)k_wf_shade<false>;
+    const void* f_ext = nullptr;
+#define WF_PICK(K) (use_smem ? (const void*)k_wf_extend<K, true> : (const void*)k_wf_extend<K, false>)
+    f_ext = kind == 3 ? WF_PICK(3) : kind == 4 ? WF_PICK(4) : kind == 1 ? WF_PICK(1) : WF_PICK(0);
+#undef WF_PICK
     cudaError_t e;
-    if (smem > 48 * 1024) {
-        if ((e = cudaFuncSetAttribute(f_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(f_ext, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    }
+    if (smem_shade > 48 * 1024 && (e = cudaFuncSetAttribute(f_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shade)) != cudaSuccess) return e;
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(f_ext, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     int bps = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, f_ext, WF_THREADS, smem)) != cudaSuccess) return e;
     if (bps < 1) bps = 1;
@@ -289,7 +304,7 @@ cudaError_t launch_render_wavefront(const SceneView& v, const trt_camera& cam, c
     for (;;) {
         for (int it = 0; it < CHECK; ++it) {
             void* args[] = {(void*)&A};
-            if ((e = cudaLaunchKernel(f_shade, dim3(shade_grid), dim3(WF_THREADS), args, smem, st)) != cudaSuccess) break;
+            if ((e = cudaLaunchKernel(f_shade, dim3(shade_grid), dim3(WF_THREADS), args, smem_shade, st)) != cudaSuccess) break;
             if ((e = cudaLaunchKernel(f_ext, dim3(ext_grid), dim3(WF_THREADS), args, smem, st)) != cudaSuccess) break;
             launches += 2;
             A.q_in ^= 1;

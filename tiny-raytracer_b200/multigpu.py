@@ -34,4 +34,20 @@ def render_share(ctx, scene, cam, make_params_fn, spp_total: int, world_size: in
     if count == 0:
         return None
     p = make_params_fn(count, offset, spp_total)
-    return scene.render_accumulate(ctx, cam, p, acc.data_ptr(), want_stats=want_stats)
+    st = scene.render_accumulate(ctx, cam, p, acc.data_ptr(), want_stats=want_stats)
+    _order_after_render(ctx)
+    return st
+
+
+def _order_after_render(ctx):
+    """The render kernel runs on the ctx's stream; whatever consumes `acc` next (the NCCL reduce, a torch op) runs on
+    torch's current stream. Unless the two are the same stream (`ctx.set_stream(torch.cuda.current_stream().cuda_stream)`,
+    what bench.py does), wait for the render here so that the consumer cannot race with it."""
+    try:
+        import torch
+        same = torch.cuda.is_available() and ctx.stream_handle is not None and \
+            int(ctx.stream_handle) == int(torch.cuda.current_stream(ctx.device).cuda_stream)
+    except Exception:
+        same = False
+    if not same:
+        ctx.synchronize()
