@@ -822,3 +822,22 @@ def test_render_multi_on_one_device_equals_render(trt, orc, ctx):
         sc.render_multi([], cam, p)
     with pytest.raises(trt.TrtError):
         sc.render_multi([99], cam, p)
+
+
+def test_cpp_multi_gpu_example_equals_one_gpu(trt, orc, ctx, tmp_path):
+    """examples/cornell_multi.cpp: a plain C++ host (no Python, no NCCL) renders the Cornell box on ALL GPUs of the box through
+    trt::Renderer -> trt_render_multi and on one GPU through trt_render; it exits 0 only if ray counts are equal and the images
+    agree to <= 1 ulp / <= 1 LSB. (On a one-GPU box the device list has one entry and both renders take the single-GPU path.)"""
+    import json, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "tiny-raytracer_b200")
+    exe = str(tmp_path / "cornell_multi")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "cornell_multi.cpp"),
+                           "-o", exe, "-L" + pkg, "-ltrt_b200", "-Wl,-rpath," + pkg])
+    r = subprocess.run([exe, "0", "480", "270", "64"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["rays_1gpu"] == d["rays_ngpu"] and d["linear_max_ulp_vs_1gpu"] <= 1 and d["rgb8_max_lsb_vs_1gpu"] <= 1
+    desc = trt.scenes.cornell(480, 270, 64, 50)
+    _, _, ost, _ = orc.Scene.from_desc(desc).render(orc.make_camera(**desc.camera), orc.make_params(480, 270, 64, 50, desc.background, 1))
+    assert d["rays_ngpu"] == ost.rays

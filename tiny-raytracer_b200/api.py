@@ -101,11 +101,11 @@ class MultiContext:
         L.check(self._lib.trt_multi_device_count(self._h, C.byref(n), C.byref(d)))
         return bool(d.value)
 
-    def render(self, scene: "Scene", cam: L.Camera, params: L.Params, want_linear=True, want_rgb8=True):
+    def render(self, scene: "Scene", cam: L.Camera, params: L.Params, want_linear=True, want_rgb8=True, out_linear=None, out_rgb8=None):
         """trt_multi_render: HOST buffers out; with both outputs off the result stays on the devices (timing)."""
         n = params.width * params.height * 3
-        lin = np.empty(n, np.float32) if want_linear else None
-        u8 = np.empty(n, np.uint8) if want_rgb8 else None
+        lin = (out_linear if out_linear is not None else np.empty(n, np.float32)) if want_linear else None
+        u8 = (out_rgb8 if out_rgb8 is not None else np.empty(n, np.uint8)) if want_rgb8 else None
         st = L.Stats()
         L.check(self._lib.trt_multi_render(self._h, scene._h, C.byref(cam), C.byref(params), _ptr(lin), _ptr(u8), C.byref(st)))
         shape = (params.height, params.width, 3)
@@ -218,10 +218,14 @@ class Scene:
         return {"host_commit_ms": h.value, "device_build_ms": d.value}
 
     # ---- rendering entry points (HOST buffers)
-    def render(self, ctx: Context, cam: L.Camera, params: L.Params, want_linear=True, want_rgb8=True):
+    def render(self, ctx: Context, cam: L.Camera, params: L.Params, want_linear=True, want_rgb8=True, out_linear=None, out_rgb8=None):
+        """trt_render: HOST buffers out. `out_linear` / `out_rgb8` let the caller supply the buffers (flat float32 / uint8
+        arrays of H*W*3 values, e.g. views of pinned memory) instead of fresh numpy arrays."""
         n = params.width * params.height * 3
-        lin = np.empty(n, np.float32) if want_linear else None
-        u8 = np.empty(n, np.uint8) if want_rgb8 else None
+        lin = (out_linear if out_linear is not None else np.empty(n, np.float32)) if want_linear else None
+        u8 = (out_rgb8 if out_rgb8 is not None else np.empty(n, np.uint8)) if want_rgb8 else None
+        assert lin is None or (lin.dtype == np.float32 and lin.size == n and lin.flags.c_contiguous)
+        assert u8 is None or (u8.dtype == np.uint8 and u8.size == n and u8.flags.c_contiguous)
         st = L.Stats()
         L.check(self._lib.trt_render(ctx._h, self._h, C.byref(cam), C.byref(params), _ptr(lin), _ptr(u8), C.byref(st)))
         shape = (params.height, params.width, 3)
