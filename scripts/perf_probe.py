@@ -16,6 +16,7 @@ ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--c4n", type=int, default=1_000_000)
 ap.add_argument("--flags", type=int, default=0, help="extra trt_params.flags bits (2 = no tail split)")
+ap.add_argument("--stats", action="store_true", help="also print the event counters of the best run")
 ap.add_argument("--regen", default="0", help="comma list of regen_min overrides (0 = auto)")
 a = ap.parse_args()
 
@@ -45,4 +46,7 @@ for wl in a.workloads.split(","):
             print("%-3s kind=%d variant=%d spp=%d regen=%d  build %.2fs  nodes %d  %.2f ms  %.1f Mpaths/s  %.1f Mrays/s  rays/path %.2f" % (
                 wl, kind, a.variant, a.spp, regen, t_build, sc.bvh_info()["nodes"], best.device_ms, best.paths / best.device_ms / 1e3,
                 best.rays / best.device_ms / 1e3, best.rays / max(best.paths, 1)), flush=True)
+            if a.stats:
+                r = max(best.rays, 1)
+                print("    events per ray: nodes %.2f  sphere tests %.2f  quad tests %.2f" % (best.node_visits / r, best.sphere_tests / r, best.quad_tests / r), flush=True)
         sc.close()

@@ -18,7 +18,7 @@ for ln in sass.splitlines():
         cur = re.sub(r"\(.*", "", cur).replace("void ", "")
         hist = res.setdefault(cur, collections.Counter())
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", ln)
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", ln)
     if m and hist is not None:
         hist[m.group(1)] += 1
         hist["_total"] += 1

@@ -4,6 +4,7 @@
 #   TRT_OUT=<path>            output library (default ../libtrt_b200.so)
 #   TRT_OBJDIR=<dir>          object directory (default: this directory) — lets A/B variants build side by side
 #   TRT_EXTRA_DEVFLAGS="..."  extra nvcc flags (e.g. -DTRT_DEBUG_BOUNDS), TRT_PTXAS_V=1 adds -Xptxas -v
+#   TRT_EXTRA_DEFS="-D..."    macros for BOTH the device and the host translation units (layout constants)
 set -euo pipefail
 cd "$(dirname "$0")"
 CUDA=${CUDA_HOME:-/usr/local/cuda}
@@ -12,8 +13,8 @@ CXX=${CXX:-g++}
 OUT=${TRT_OUT:-../libtrt_b200.so}
 OBJ=${TRT_OBJDIR:-.}
 mkdir -p "$OBJ"
-DEVFLAGS="${TRT_EXTRA_DEVFLAGS:-} -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -fmad=false -prec-div=true -prec-sqrt=true -ftz=false"
-HOSTFLAGS="-std=c++17 -O2 -fPIC -ffp-contract=off -fno-fast-math -Wall -pthread"
+DEVFLAGS="${TRT_EXTRA_DEVFLAGS:-} ${TRT_EXTRA_DEFS:-} -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -fmad=false -prec-div=true -prec-sqrt=true -ftz=false"
+HOSTFLAGS="${TRT_EXTRA_DEFS:-} -std=c++17 -O2 -fPIC -ffp-contract=off -fno-fast-math -Wall -pthread"
 # the translation units are independent: compile them side by side
 pids=(); objs=()
 while read -r src kind; do

@@ -263,7 +263,7 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
     v.nodes = b + off[0]; v.spheres = b + off[1]; v.quads = b + off[2]; v.sphere_meta = b + off[3]; v.quad_meta = b + off[4]; v.quad_nn = b + off[7]; v.materials = b + off[5];
     v.root = f.root; v.n_nodes = f.n_nodes; v.n_spheres = (uint32_t)f.spheres.size(); v.n_quads = (uint32_t)f.quad_meta.size();
     v.n_materials = (uint32_t)(f.materials.size() / 2); v.kind = device_build ? 1u : (uint32_t)f.bvh_kind;   // the device-built tree is walked near-child-first like SAH
-    v.flat = f.flat.empty() ? nullptr : b + off[6]; v.n_flat = (uint32_t)(f.flat.size() / 6);
+    v.flat = f.flat.empty() ? nullptr : b + off[6]; v.n_flat = (uint32_t)(f.flat.size() / TRT_FLAT_F4); v.flat_qmask[0] = f.flat_qmask[0]; v.flat_qmask[1] = f.flat_qmask[1];
     v.nodes4 = f.nodes4.empty() ? nullptr : b + off[9]; v.n_nodes4 = f.n_nodes4;
     v.nodes_ref4 = f.nodes_ref4.empty() ? nullptr : b + off[10]; v.n_nodes_ref4 = f.n_nodes_ref4; v.root_ref4 = 0;
     if (device_build || f.ref_on_device) { v.nodes_ref4 = b + off[10]; v.n_nodes_ref4 = (uint32_t)(n_prims - 1); v.root_ref4 = dc.root_ref4; }

@@ -127,6 +127,7 @@ struct DevScene {
     const uint4* sphere_meta; const uint4* quad_meta; const float4* materials;
     const float4* quad_nn;                      // unit normal of every quad, precomputed on the host with HitRecord::new's operations
     const FlatPrim* flat; uint32_t n_flat;      // TRT_BVH_FLAT: primitives in reference leaf order (else null / 0)
+    uint32_t flat_qmask[2];                     // TRT_BVH_FLAT: bit r = record r is a quad
     const float4* nodes4; uint32_t n_nodes4;    // tree kinds: 4-wide nodes (8 float4 each, trt_scene.cpp collapse4) or null
     const float4* nodes_ref4; uint32_t n_nodes_ref4, root_ref4;   // ordered kinds: the REFERENCE-topology tree's wide nodes, for the rare replay (ordered_replay)
     const float4* g_spheres; const float4* g_quads;    // global-memory copies of spheres / quads (the staged scene overrides those two)
@@ -300,6 +301,16 @@ struct Hit { float t; uint32_t ref; };
 #endif
 TRT_DEV float cull_limit(float best) { return best + fabsf(best) * TRT_SAH_CULL_MARGIN; }
 
+// The traversal stack: (child ref, box entry) pairs in ONE array of 8-byte entries in local memory, so that a push or a pop is
+// one STL.64 / LDL.64 (two 32-bit arrays, round 1: two accesses each; merged: 10^6 spheres +2.9 %, final scene +0.6 %).
+// Measured and rejected: the first 12 / 16 / 24 entries of every thread in shared memory ([entry][thread], conflict-free):
+// 10^6 spheres -3 / -3 / -8 %, final scene -9 % — the shared memory it takes costs more L1 than the stack traffic did.
+struct TravStack {
+    uint2 e_[TRT_MAX_STACK];
+    TRT_DEV void put(int i, uint32_t ref, float s) { e_[i] = make_uint2(ref, __float_as_uint(s)); }
+    TRT_DEV void get(int i, uint32_t* ref, float* s) const { const uint2 v = e_[i]; *ref = v.x; *s = __uint_as_float(v.y); }
+};
+
 // Resumable form: trav_begin() sets the state up, every trav_step() runs one iteration of the loop (region A, region B,
 // pop). closest_hit() is begin + step until done; the wavefront extend kernel interleaves steps of different rays.
 struct Trav {
@@ -327,7 +338,7 @@ TRT_DEV void trav_begin(Trav& T, const DevScene& S, V3 o, V3 d, float t_min, Eve
 }
 
 template <bool ORDERED, bool SMEM, bool COUNT>
-TRT_DEV void trav_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* stack_t, EventCounters* ec) {
+TRT_DEV void trav_step(Trav& T, const DevScene& S, TravStack& K, EventCounters* ec) {
     uint32_t cur = T.cur;
     const V3 o = T.o, d = T.d, inv = T.inv; const float t_min = T.t_min;
     if (!(cur & TRT_REF_LEAF)) {
@@ -354,7 +365,7 @@ TRT_DEV void trav_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* s
         bool p0 = right_first ? pr : pl, p1 = right_first ? pl : pr;
         if (p0) {
             cur = c0; if (ORDERED) T.cur_s = right_first ? sr : sl;
-            if (p1) { TRT_ASSERT(T.sp < TRT_MAX_STACK); stack_ref[T.sp] = c1; stack_t[T.sp] = s1; ++T.sp; }
+            if (p1) { TRT_ASSERT(T.sp < TRT_MAX_STACK); K.put(T.sp, c1, s1); ++T.sp; }
         } else if (p1 && (ORDERED || T.best.t > s1)) { cur = c1; if (ORDERED) T.cur_s = s1; }
         else cur = TRT_REF_INVALID;
     }
@@ -380,8 +391,9 @@ TRT_DEV void trav_step(Trav& T, const DevScene& S, uint32_t* stack_ref, float* s
     // ---- pop: skip entries that the closest hit found meanwhile has cut off
     while (cur == TRT_REF_INVALID && T.sp > 0) {
         --T.sp;
-        float s = stack_t[T.sp];
-        if (ORDERED ? !(cull_limit(T.best.t) < s) : (T.best.t > s)) { cur = stack_ref[T.sp]; if (ORDERED) T.cur_s = s; }
+        uint32_t r; float s;
+        K.get(T.sp, &r, &s);
+        if (ORDERED ? !(cull_limit(T.best.t) < s) : (T.best.t > s)) { cur = r; if (ORDERED) T.cur_s = s; }
     }
     T.cur = cur;
 }
@@ -405,8 +417,8 @@ template <bool ORDERED, bool SMEM, bool COUNT>
 TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
     Trav T;
     trav_begin<COUNT>(T, S, o, d, t_min, ec);
-    uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
-    while (T.cur != TRT_REF_INVALID) trav_step<ORDERED, SMEM, COUNT>(T, S, stack_ref, stack_t, ec);
+    TravStack K;
+    while (T.cur != TRT_REF_INVALID) trav_step<ORDERED, SMEM, COUNT>(T, S, K, ec);
     if (ORDERED && needs_replay(T, S)) return ordered_replay(S, o, d, t_min);   // also when counting: the replay's own events are not counted, the RESULT must not depend on the flag
     return T.best;
 }
@@ -424,7 +436,7 @@ TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounter
 // COUNT (TRT_FLAG_COUNT_WALKED): ec->node_visits counts the wide records fetched (7 x 16 B each), sphere_tests / quad_tests the
 // primitive tests — the traffic of THIS walk, for the memory roofline of big scenes (bench.py); results are unaffected.
 template <bool ORDERED, bool SMEM, bool COUNT = false>
-TRT_DEV void trav4_step(Trav& T, const DevScene& S, float t_min, uint32_t* stack_ref, float* stack_t, EventCounters* ec = nullptr) {   // t_min: the caller's (uniform) value, not a per-lane copy
+TRT_DEV void trav4_step(Trav& T, const DevScene& S, float t_min, TravStack& K, EventCounters* ec = nullptr) {   // t_min: the caller's (uniform) value, not a per-lane copy
     uint32_t cur = T.cur;
     const V3 o = T.o, d = T.d, inv = T.inv;
     if (!(cur & TRT_REF_LEAF)) {
@@ -457,15 +469,15 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, float t_min, uint32_t* stack
             TRT_CSWAP(s0, r0, s1, r1) TRT_CSWAP(s2, r2, s3, r3) TRT_CSWAP(s0, r0, s2, r2) TRT_CSWAP(s1, r1, s3, r3) TRT_CSWAP(s1, r1, s2, r2)
 #undef TRT_CSWAP
             // the ref, not the key, says whether a slot is occupied
-            if (r3 != TRT_REF_INVALID) { stack_ref[T.sp] = r3; stack_t[T.sp] = s3; ++T.sp; }
-            if (r2 != TRT_REF_INVALID) { stack_ref[T.sp] = r2; stack_t[T.sp] = s2; ++T.sp; }
-            if (r1 != TRT_REF_INVALID) { stack_ref[T.sp] = r1; stack_t[T.sp] = s1; ++T.sp; }
+            if (r3 != TRT_REF_INVALID) { K.put(T.sp, r3, s3); ++T.sp; }
+            if (r2 != TRT_REF_INVALID) { K.put(T.sp, r2, s2); ++T.sp; }
+            if (r1 != TRT_REF_INVALID) { K.put(T.sp, r1, s1); ++T.sp; }
             cur = r0; T.cur_s = s0;
         } else {
             // bvh.rs:97: a later sibling is searched with the range end narrowed by everything before it -> re-checked when popped
-            if (e3 > s3 && r3 != TRT_REF_INVALID) { stack_ref[T.sp] = r3; stack_t[T.sp] = s3; ++T.sp; }
-            if (e2 > s2 && r2 != TRT_REF_INVALID) { stack_ref[T.sp] = r2; stack_t[T.sp] = s2; ++T.sp; }
-            if (e1 > s1 && r1 != TRT_REF_INVALID) { stack_ref[T.sp] = r1; stack_t[T.sp] = s1; ++T.sp; }
+            if (e3 > s3 && r3 != TRT_REF_INVALID) { K.put(T.sp, r3, s3); ++T.sp; }
+            if (e2 > s2 && r2 != TRT_REF_INVALID) { K.put(T.sp, r2, s2); ++T.sp; }
+            if (e1 > s1 && r1 != TRT_REF_INVALID) { K.put(T.sp, r1, s1); ++T.sp; }
             cur = (e0 > s0 && best > s0) ? r0 : TRT_REF_INVALID;
         }
     }
@@ -490,8 +502,9 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, float t_min, uint32_t* stack
     }
     while (cur == TRT_REF_INVALID && T.sp > 0) {
         --T.sp;
-        const float s = stack_t[T.sp];
-        if (ORDERED ? !(cull_limit(T.best.t) < s) : (T.best.t > s)) { cur = stack_ref[T.sp]; if (ORDERED) T.cur_s = s; }
+        uint32_t r; float s;
+        K.get(T.sp, &r, &s);
+        if (ORDERED ? !(cull_limit(T.best.t) < s) : (T.best.t > s)) { cur = r; if (ORDERED) T.cur_s = s; }
     }
     T.cur = cur;
 }
@@ -499,12 +512,12 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, float t_min, uint32_t* stack
 // reference tree's wide nodes in global memory. Sharing the loop and the stack keeps the rare replay out of the hot path's
 // register budget.
 template <bool ORDERED, bool SMEM, bool COUNT = false>
-TRT_DEV void trav4_any_step(Trav& T, const DevScene& S, float t_min, uint32_t* stack_ref, float* stack_t, EventCounters* ec = nullptr) {
+TRT_DEV void trav4_any_step(Trav& T, const DevScene& S, float t_min, TravStack& K, EventCounters* ec = nullptr) {
     if (ORDERED && T.replay) {
         DevScene R = S;
         R.nodes4 = S.nodes_ref4; R.n_nodes4 = S.n_nodes_ref4; R.spheres = S.g_spheres; R.quads = S.g_quads;
-        trav4_step<false, false, COUNT>(T, R, t_min, stack_ref, stack_t, ec);
-    } else trav4_step<ORDERED, SMEM, COUNT>(T, S, t_min, stack_ref, stack_t, ec);
+        trav4_step<false, false, COUNT>(T, R, t_min, K, ec);
+    } else trav4_step<ORDERED, SMEM, COUNT>(T, S, t_min, K, ec);
 }
 // restart the ray of a finished ordered walk in replay mode
 TRT_DEV void begin_replay(Trav& T, const DevScene& S) {
@@ -515,9 +528,9 @@ template <bool ORDERED, bool SMEM, bool COUNT>
 TRT_DEV Hit closest_hit4(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
     Trav T;
     trav_begin<false>(T, S, o, d, t_min, ec);
-    uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
+    TravStack K;
     for (;;) {
-        while (T.cur != TRT_REF_INVALID) trav4_any_step<ORDERED, SMEM, COUNT>(T, S, t_min, stack_ref, stack_t, ec);
+        while (T.cur != TRT_REF_INVALID) trav4_any_step<ORDERED, SMEM, COUNT>(T, S, t_min, K, ec);
         if (!(ORDERED && needs_replay(T, S))) break;
         begin_replay(T, S);
     }
@@ -638,7 +651,8 @@ TRT_DEV bool shade(const DevScene& S, const DevParams& P, Hit h, uint32_t pixel,
 //            returns W whatever it visited before (nothing valid is closer; a tie is lower-ranked). Otherwise, and for
 //            rays whose slab arithmetic can overflow or produce NaN, the lane replays the reference's scan literally
 //            (flat_scan_reference). No hit candidate at all means no valid primitive: a miss. Exact by construction.
-struct FlatPrim { float4 g0, g1, g2, g3, b0, b1; };   // geometry as in trt_layout.h; b0 = (bmin.xyz, bmax.x), b1 = (bmax.yz, ref bits, 0)
+struct FlatPrim { float4 f[TRT_FLAT_F4]; };   // trt_layout.h: f[0..3] geometry; f[4] = (mn.x, mx.x, mn.y, mx.y), f[5] = (mn.z, mx.z, ref bits, 0); f[6] spare
+static_assert(sizeof(FlatPrim) == 16 * TRT_FLAT_F4, "FlatPrim must match TRT_FLAT_F4");
 
 // Phase A does not need the exact box test: a SUPERSET of the crossed boxes gives the same winner as long as the winner's
 // own box is then tested exactly (the check below), because a primitive that is not the closest valid one never decides
@@ -661,12 +675,14 @@ TRT_DEV bool ray_is_flat_fast(V3 o, V3 inv) {
 
 template <bool DSMEM> TRT_DEV float4 ldf(const float4* p) { return ld4<DSMEM>(p); }
 
-// one primitive against [t_min, hi): returns t or false. hi_cut only feeds the quad pre-reject (see quad_hit).
+// one primitive against [t_min, hi): returns t or false. hi_cut (>= every t the caller could still accept) only feeds the
+// conservative pre-rejects, which skip the IEEE division (quad) or square root and divisions (sphere) when the result is
+// clearly out of range; a pre-reject never changes an accepted t.
 template <bool DSMEM>
-TRT_DEV bool flat_prim_hit(const float4* p, uint32_t ref, V3 o, V3 d, float t_min, float hi, float hi_cut, float* t_out) {
+TRT_DEV bool flat_prim_hit(const float4* p, bool is_quad, V3 o, V3 d, float t_min, float hi, float hi_cut, float* t_out) {
     float4 g0 = ldf<DSMEM>(p);
     float t;
-    if (ref & TRT_REF_QUAD) {
+    if (is_quad) {
         V3 nrm = mk(g0.x, g0.y, g0.z);
         float dn = dot(d, nrm), num = g0.w - dot(o, nrm);
         float ta = num * rcp_approx(dn);
@@ -698,19 +714,19 @@ TRT_DEV Hit flat_scan_reference(const FlatPrim* Dv, uint32_t n, V3 o, V3 d, V3 i
         const float4* p = (const float4*)(Dv + i);
         float4 b0 = ldf<DSMEM>(p + 4), b1 = ldf<DSMEM>(p + 5);
         float s, e;
-        slab(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, o, inv, t_min, &s, &e);
+        slab(b0.x, b0.z, b1.x, b0.y, b0.w, b1.y, o, inv, t_min, &s, &e);
         if (!(e > s && best.t > s)) continue;
         uint32_t ref = __float_as_uint(b1.z);
         float t;
-        if (flat_prim_hit<DSMEM>(p, ref, o, d, t_min, best.t, best.t, &t)) { best.t = t; best.ref = ref; }
+        if (flat_prim_hit<DSMEM>(p, (ref & TRT_REF_QUAD) != 0, o, d, t_min, best.t, best.t, &t)) { best.t = t; best.ref = ref; }
     }
     return best;
 }
 
 // CB: the conservative boxes as seen by uniform (same-address) loads — kernel parameters in the megakernel;
-// Dv: the primitive list for per-lane indexed loads.
+// Dv: the primitive list for per-lane indexed loads; qm0 / qm1: bit r = record r is a quad.
 template <bool DSMEM>
-TRT_DEV Hit closest_hit_flat(const float4* __restrict__ CB, float bound, const FlatPrim* Dv, uint32_t n, V3 o, V3 d, float t_min) {
+TRT_DEV Hit closest_hit_flat(const float4* __restrict__ CB, float bound, const FlatPrim* Dv, uint32_t n, uint32_t qm0, uint32_t qm1, V3 o, V3 d, float t_min) {
     Hit best; best.t = TRT_INF; best.ref = TRT_REF_INVALID;
     const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     if (!(ray_is_flat_fast(o, inv) && bound >= 0.0f)) return flat_scan_reference<DSMEM>(Dv, n, o, d, inv, t_min);
@@ -744,27 +760,35 @@ TRT_DEV Hit closest_hit_flat(const float4* __restrict__ CB, float bound, const F
             if (e1 + E > s1) mask[half] |= 2u << (2 * j);
         }
     }
-    // ---- phase B: primitive tests of the candidates, in rank order
-    uint32_t best_i = 0;
+    uint32_t best_i = 0xFFFFFFFFu;
+    // ---- phase B: primitive tests of the candidates, in rank order, keeping the smallest t (a tie keeps the lower rank).
+    // (A two-pass form — cheap can-it-be-hit pass over all candidates, then the exact test of the approximately nearest one first —
+    // was measured 19 % SLOWER on Cornell, 18.0 vs 22.2 Grays/s: the second loop's overhead outweighs the exact-test rounds it saves.)
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         uint32_t m = mask[half];
+        const uint32_t qm = half ? qm1 : qm0;
         while (m) {
-            const uint32_t i = (uint32_t)__ffs((int)m) - 1u + 32u * half;
+            const uint32_t bit = (uint32_t)__ffs((int)m) - 1u;
+            const uint32_t i = bit + 32u * half;
             m &= m - 1u;
             TRT_ASSERT(i < n);
-            const float4* p = (const float4*)(Dv + i);
-            const uint32_t ref = __float_as_uint(ldf<DSMEM>(p + 5).z);
             float t;
-            if (flat_prim_hit<DSMEM>(p, ref, o, d, t_min, TRT_INF, best.t, &t) && t < best.t) { best.t = t; best.ref = ref; best_i = i; }
+            if (flat_prim_hit<DSMEM>((const float4*)(Dv + i), (qm >> bit) & 1u, o, d, t_min, TRT_INF, best.t, &t) && t < best.t) { best.t = t; best_i = i; }
         }
     }
-    if (best.ref == TRT_REF_INVALID) return best;
-    // ---- check: the winner's own box, exactly (bvh.rs:89), and its entry against its t
+    if (best_i == 0xFFFFFFFFu) return best;
+    // ---- check: the winner's own box, exactly (bvh.rs:89), and its entry against its t. (min, max) pairs per axis: the
+    // reference's `(b - o) * inv` for both planes of an axis in one FADD2 + one FMUL2 (bit-identical to slab_tame)
     const float4* p = (const float4*)(Dv + best_i);
-    float4 b0 = ldf<DSMEM>(p + 4), b1 = ldf<DSMEM>(p + 5);
-    float s, e;
-    slab_tame(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, o, inv, t_min, &s, &e);
+    const float4 b0 = ldf<DSMEM>(p + 4), b1 = ldf<DSMEM>(p + 5);
+    best.ref = __float_as_uint(b1.z);
+    float ax, bx, ay, by, az, bz;
+    upk2(mul2(sub2(pk2(b0.x, b0.y), pk2(o.x, o.x)), pk2(inv.x, inv.x)), &ax, &bx);
+    upk2(mul2(sub2(pk2(b0.z, b0.w), pk2(o.y, o.y)), pk2(inv.y, inv.y)), &ay, &by);
+    upk2(mul2(sub2(pk2(b1.x, b1.y), pk2(o.z, o.z)), pk2(inv.z, inv.z)), &az, &bz);
+    const float s = fmaxf(fmaxf(t_min, fminf(ax, bx)), fmaxf(fminf(ay, by), fminf(az, bz)));
+    const float e = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
     if (!(e > s) || s > best.t) return flat_scan_reference<DSMEM>(Dv, n, o, d, inv, t_min);
     return best;
 }
@@ -773,7 +797,7 @@ TRT_DEV Hit closest_hit_flat(const float4* __restrict__ CB, float bound, const F
 // KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH (binary nodes), 2 = TRT_BVH_FLAT, 3 / 4 = SAH / REFERENCE on their 4-wide nodes
 template <int KIND, bool SMEM, bool COUNT>
 TRT_DEV Hit closest_hit_any(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
-    if (KIND == 2) return closest_hit_flat<false>(S.flat_cbox, S.flat_bound, S.flat, S.n_flat, o, d, t_min);
+    if (KIND == 2) return closest_hit_flat<false>(S.flat_cbox, S.flat_bound, S.flat, S.n_flat, S.flat_qmask[0], S.flat_qmask[1], o, d, t_min);
     if (KIND == 3 || KIND == 4) return closest_hit4<KIND == 3, SMEM, COUNT>(S, o, d, t_min, ec);
     return closest_hit<KIND == 1, SMEM, COUNT>(S, o, d, t_min, ec);
 }
@@ -834,7 +858,7 @@ __device__ __forceinline__ DevScene stage_scene(const DevScene& G) {
         S.quad_nn = copy(G.quad_nn, G.n_quads);
         S.materials = copy(G.materials, 2 * G.n_materials);
     }
-    S.flat = (const FlatPrim*)copy((const float4*)G.flat, 6 * G.n_flat);
+    S.flat = (const FlatPrim*)copy((const float4*)G.flat, TRT_FLAT_F4 * G.n_flat);
     __syncthreads();
     return S;
 }

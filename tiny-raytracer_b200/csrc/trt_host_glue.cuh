@@ -12,7 +12,7 @@ inline DevScene dev_scene(const SceneView& v) {
     DevScene s;
     s.nodes = (const float4*)v.nodes; s.spheres = (const float4*)v.spheres; s.quads = (const float4*)v.quads;
     s.sphere_meta = (const uint4*)v.sphere_meta; s.quad_meta = (const uint4*)v.quad_meta; s.quad_nn = (const float4*)v.quad_nn; s.materials = (const float4*)v.materials;
-    s.flat = (const FlatPrim*)v.flat; s.n_flat = v.n_flat; s.flat_cbox = (const float4*)v.flat_cbox; s.flat_bound = v.flat_bound;
+    s.flat = (const FlatPrim*)v.flat; s.n_flat = v.n_flat; s.flat_cbox = (const float4*)v.flat_cbox; s.flat_bound = v.flat_bound; s.flat_qmask[0] = v.flat_qmask[0]; s.flat_qmask[1] = v.flat_qmask[1];
     s.nodes4 = (const float4*)v.nodes4; s.n_nodes4 = v.n_nodes4;
     s.nodes_ref4 = (const float4*)v.nodes_ref4; s.n_nodes_ref4 = v.n_nodes_ref4; s.root_ref4 = v.root_ref4; s.g_spheres = s.spheres; s.g_quads = s.quads;
     s.root = v.root; s.n_nodes = v.n_nodes; s.n_spheres = v.n_spheres; s.n_quads = v.n_quads; s.n_materials = v.n_materials;

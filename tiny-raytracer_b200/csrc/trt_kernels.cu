@@ -82,7 +82,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& A, const float4* U) {
         // ---- T: cpu.rs:48
         Hit h; h.t = TRT_INF; h.ref = TRT_REF_INVALID;
         if (alive) {
-            if (KIND == 2) h = closest_hit_flat<true>(U, S.flat_bound, S.flat, S.n_flat, o, d, P.t_min);
+            if (KIND == 2) h = closest_hit_flat<true>(U, S.flat_bound, S.flat, S.n_flat, S.flat_qmask[0], S.flat_qmask[1], o, d, P.t_min);
             else if (KIND == 3 || KIND == 4) h = closest_hit4<KIND == 3, SMEM, COUNT>(S, o, d, P.t_min, &ec);
             else h = closest_hit<KIND == 1, SMEM, COUNT>(S, o, d, P.t_min, &ec);
             ++n_rays;
@@ -173,7 +173,7 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
     const uint32_t lane = threadIdx.x & 31u;
     Trav T; T.cur = TRT_REF_INVALID; T.sp = 0; T.best.t = TRT_INF; T.best.ref = TRT_REF_INVALID;
     T.o = mk(0, 0, 0); T.d = mk(0, 0, 1); T.inv = mk(0, 0, 1); T.t_min = P.t_min; T.tame = false;
-    uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
+    TravStack K;
     V3 atten = mk(1, 1, 1), color = mk(0, 0, 0);
     uint32_t pixel = 0, px = 0, py = 0, s_cur = 0, s_end = 0, remain = 0, k = 0;
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
@@ -186,10 +186,10 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
         // ---- T: one step of cpu.rs:48 for every lane whose ray is in flight
         if (T.cur != TRT_REF_INVALID) {
             if (KIND == 3 || KIND == 4) {
-                trav4_any_step<KIND == 3, SMEM, COUNT>(T, S, P.t_min, stack_ref, stack_t, &ec);
+                trav4_any_step<KIND == 3, SMEM, COUNT>(T, S, P.t_min, K, &ec);
                 if (KIND == 3 && T.cur == TRT_REF_INVALID && needs_replay(T, S)) begin_replay(T, S);     // rare: DESIGN.md §4.3
             }
-            else trav_step<KIND == 1, SMEM, COUNT>(T, S, stack_ref, stack_t, &ec);
+            else trav_step<KIND == 1, SMEM, COUNT>(T, S, K, &ec);
         }
         const bool tracing = T.cur != TRT_REF_INVALID;
         const unsigned tm = __ballot_sync(0xFFFFFFFFu, tracing);
@@ -372,7 +372,7 @@ size_t scene_smem_bytes(const SceneView& v, uint32_t kind) {
     size_t aux = aux_f4(v.n_spheres, v.n_quads, v.n_materials);
     if (aux > TRT_AUX_SMEM_F4) aux = 0;
     size_t nodes = (kind == 3 || kind == 4) ? 8ull * v.n_nodes4 : 4ull * v.n_nodes;
-    return 16ull * (nodes + v.n_spheres + 4ull * v.n_quads + 6ull * v.n_flat + aux);
+    return 16ull * (nodes + v.n_spheres + 4ull * v.n_quads + (size_t)TRT_FLAT_F4 * v.n_flat + aux);
 }
 
 template <int KIND, bool SMEM, bool COUNT>

@@ -12,7 +12,8 @@ namespace trtk {
 
 struct SceneView {   // device copy of trt::FlatScene
     const void* nodes; const void* spheres; const void* quads; const void* sphere_meta; const void* quad_meta; const void* materials; const void* quad_nn;
-    const void* flat;          // device copy of the flat list (6 float4 per primitive, reference leaf order) or null
+    const void* flat;          // device copy of the flat list (TRT_FLAT_F4 float4 per primitive, reference leaf order) or null
+    uint32_t flat_qmask[2];    // bit r = record r of the flat list is a quad
     const void* flat_cbox;     // device copy of the flat list's conservative phase-A boxes (TRT_FLAT_CBOX_F4 float4) or null
     const void* flat_cbox_host;// the same boxes on the host: copied into the kernel parameters of k_render_mega_flat
     float flat_bound;          // largest |coordinate| of any flat-list box, or < 0: phase A disabled (literal scan only)

@@ -37,8 +37,16 @@
 #define TRT_MAX_STACK 64   /* traversal stack entries; trt_scene_commit rejects deeper trees */
 #define TRT_AUTO_DEVICE_BUILD_MIN 65536u   /* TRT_BVH_AUTO: from this many primitives on the trees are built on the GPU
                                                (10^6 spheres: 5 ms instead of 1.1 s on the host, traversal -3 %, same results) */
-#define TRT_FLAT_MAX 64    /* TRT_BVH_FLAT: largest primitive count handled as a flat list (6 float4 = 96 B each:
-                              the four geometry float4 above, then (bmin.xyz, bmax.x), (bmax.yz, child-ref bits, 0)) */
+#define TRT_FLAT_MAX 64    /* TRT_BVH_FLAT: largest primitive count handled as a flat list */
+#ifndef TRT_FLAT_F4
+#define TRT_FLAT_F4 7
+#endif
+                           /* float4 per flat-list record (112 B): the four geometry float4 above, then the primitive's own padded
+                              box as (min, max) pairs (mn.x, mx.x, mn.y, mx.y), (mn.z, mx.z, child-ref bits, 0) — each 64-bit half
+                              is one operand of a packed FADD2 / FMUL2 in the exact box test —, then one spare. An ODD number of
+                              16-byte slots, so that lanes reading the same field of different records hit different
+                              shared-memory bank groups (96-byte records put every other record on the same banks: 37 % of
+                              the flat kernel's shared-memory wavefronts were bank conflicts, profiles/r1y) */
 
 struct trt_f4 { float x, y, z, w; };
 struct trt_u4 { uint32_t x, y, z, w; };

@@ -470,14 +470,16 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
     }
     if (bvh_kind == 2) {
         // the list, in reference leaf order: geometry, then the primitive's own padded box and its child-ref bits
-        flat.flat.resize(6 * n);
+        flat.flat.assign(TRT_FLAT_F4 * n, trt_f4{0.f, 0.f, 0.f, 0.f});
+        flat.flat_qmask[0] = flat.flat_qmask[1] = 0u;
         for (size_t i = 0; i < n; ++i) {
             const HostPrim& p = prims[i];
-            trt_f4* f = &flat.flat[6 * (size_t)leaf_rank[i]];
+            const size_t r = leaf_rank[i];
+            trt_f4* f = &flat.flat[TRT_FLAT_F4 * r];
             if (p.type == 0) { f[0] = {p.a[0], p.a[1], p.a[2], p.r}; f[1] = f[2] = f[3] = {0.f, 0.f, 0.f, 0.f}; }
-            else { for (int k = 0; k < 4; ++k) f[k] = flat.quads[4 * (size_t)p.type_index + k]; }
-            f[4] = {p.bmin[0], p.bmin[1], p.bmin[2], p.bmax[0]};
-            f[5] = {p.bmax[1], p.bmax[2], as_float(leaf_ref(p)), 0.f};
+            else { for (int k = 0; k < 4; ++k) f[k] = flat.quads[4 * (size_t)p.type_index + k]; flat.flat_qmask[r >> 5] |= 1u << (r & 31); }
+            f[4] = {p.bmin[0], p.bmax[0], p.bmin[1], p.bmax[1]};
+            f[5] = {p.bmin[2], p.bmax[2], as_float(leaf_ref(p)), 0.f};
         }
         // phase-A boxes: [mid - half, mid + half] must contain the padded box in real arithmetic, so `half` is computed in
         // double from the rounded float `mid` and then rounded up (two float steps cover the double rounding as well)

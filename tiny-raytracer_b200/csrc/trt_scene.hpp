@@ -32,7 +32,8 @@ struct FlatScene {
     std::vector<trt_u4> sphere_meta, quad_meta;
     std::vector<trt_f4> quad_nn;       // per quad: n / |n| (what HitRecord::new computes at every hit, hittable/mod.rs:36-40), same IEEE ops
     std::vector<trt_f4> materials;     // 2 per material
-    std::vector<trt_f4> flat;          // TRT_BVH_FLAT: 6 per primitive, reference leaf order (trt_layout.h)
+    std::vector<trt_f4> flat;          // TRT_BVH_FLAT: TRT_FLAT_F4 per primitive, reference leaf order (trt_layout.h)
+    uint32_t flat_qmask[2] = {0u, 0u}; // TRT_BVH_FLAT: bit r = the record of leaf rank r is a quad (uniform type lookup without a load)
     std::vector<trt_f4> flat_cbox;     // TRT_BVH_FLAT: conservative centre/half-width boxes for phase A (trt_device.cuh), 3 per pair, NaN padded
     float flat_bound = -1.f;           // largest |coordinate| of those boxes; < 0 = phase A disabled (coordinates beyond 2^30 or not finite)
     std::vector<trt_f4> lbvh_boxes;    // TRT_BVH_LBVH_DEVICE: 2 per primitive, (bmin, leaf-ref bits), (bmax, 0): input of the device builder

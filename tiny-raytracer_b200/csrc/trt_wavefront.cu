@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(WF_THREADS, 3) k_wf_extend(const WfArgs A) {
     const uint32_t n = ctl->q_count[A.q_in ^ 1];
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->q_count[A.q_in] = 0;   // the next shade pass appends to this queue
     Trav T; T.cur = TRT_REF_INVALID; T.sp = 0;
-    uint32_t stack_ref[TRT_MAX_STACK]; float stack_t[TRT_MAX_STACK];
+    TravStack K;
     uint32_t slot = 0; bool active = false, exhausted = false;
     uint32_t n_rays = 0;
     EventCounters ec;
@@ -223,9 +223,9 @@ __global__ void __launch_bounds__(WF_THREADS, 3) k_wf_extend(const WfArgs A) {
         if (idle == 0xFFFFFFFFu) { if (exhausted) break; else continue; }
         if (active) {
             if (KIND == 3 || KIND == 4) {
-                trav4_any_step<KIND == 3, SMEM, false>(T, S, A.p.t_min, stack_ref, stack_t, nullptr);
+                trav4_any_step<KIND == 3, SMEM, false>(T, S, A.p.t_min, K, nullptr);
                 if (KIND == 3 && T.cur == TRT_REF_INVALID && needs_replay(T, S)) begin_replay(T, S);     // rare: DESIGN.md §4.3
-            } else trav_step<KIND == 1, SMEM, false>(T, S, stack_ref, stack_t, &ec);
+            } else trav_step<KIND == 1, SMEM, false>(T, S, K, &ec);
             if (T.cur == TRT_REF_INVALID) {
                 Hit h = T.best;
                 if (KIND == 1 && needs_replay(T, S)) h = ordered_replay(S, T.o, T.d, A.p.t_min);          // rare, binary walk
