@@ -17,6 +17,7 @@
 // message, so nothing unwinds across the C boundary.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -69,10 +70,48 @@ inline std::vector<Geometry> new_box(Vec3 a, Vec3 b, std::shared_ptr<Material> m
             Quad({lo.x, lo.y, lo.z}, dz, dy, m), Quad({lo.x, hi.y, hi.z}, dx, ndz, m), Quad({lo.x, lo.y, lo.z}, dx, dz, m)};
 }
 
+// math::transform::Transform (math/transform.rs:10-111): 4x4 f32 matrix, new(translation, rotation, scale) = T * S * (Rz * Ry * Rx).
+// Dead code in the reference; here it also places instances: World::add_instance(geometries, transform) adds transformed
+// copies (quad: corner through the matrix, edges through its linear part; sphere: similarity transforms only).
+struct Transform {
+    float m[4][4];
+    Transform() { for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) m[i][j] = i == j ? 1.f : 0.f; }
+    static Transform identity() { return Transform(); }
+    static Transform translate(Vec3 d) { Transform t; t.m[0][3] = d.x; t.m[1][3] = d.y; t.m[2][3] = d.z; return t; }
+    static Transform scale(Vec3 s) { Transform t; t.m[0][0] = s.x; t.m[1][1] = s.y; t.m[2][2] = s.z; return t; }
+    static Transform rotate_x(float a) { Transform t; float c = std::cos(a), s = std::sin(a); t.m[1][1] = c; t.m[1][2] = -s; t.m[2][1] = s; t.m[2][2] = c; return t; }
+    static Transform rotate_y(float a) { Transform t; float c = std::cos(a), s = std::sin(a); t.m[0][0] = c; t.m[0][2] = s; t.m[2][0] = -s; t.m[2][2] = c; return t; }
+    static Transform rotate_z(float a) { Transform t; float c = std::cos(a), s = std::sin(a); t.m[0][0] = c; t.m[0][1] = -s; t.m[1][0] = s; t.m[1][1] = c; return t; }
+    static Transform rotate(Vec3 a) { return rotate_z(a.z) * rotate_y(a.y) * rotate_x(a.x); }
+    static Transform make(Vec3 translation, Vec3 rotation, Vec3 scales) { return translate(translation) * scale(scales) * rotate(rotation); }   // Transform::new
+    friend Transform operator*(const Transform& a, const Transform& b) {
+        Transform r;
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { float s = 0.f; for (int k = 0; k < 4; ++k) s += a.m[i][k] * b.m[k][j]; r.m[i][j] = s; }
+        return r;
+    }
+    Vec3 operator*(Vec3 v) const { return Vec3(m[0][0] * v.x + m[0][1] * v.y + m[0][2] * v.z + m[0][3], m[1][0] * v.x + m[1][1] * v.y + m[1][2] * v.z + m[1][3],
+                                               m[2][0] * v.x + m[2][1] * v.y + m[2][2] * v.z + m[2][3]); }
+    Vec3 linear(Vec3 v) const { return Vec3(m[0][0] * v.x + m[0][1] * v.y + m[0][2] * v.z, m[1][0] * v.x + m[1][1] * v.y + m[1][2] * v.z, m[2][0] * v.x + m[2][1] * v.y + m[2][2] * v.z); }
+    Geometry apply(const Geometry& g) const {
+        if (g.is_quad) return Geometry{true, (*this) * g.a, linear(g.u), linear(g.v), 0.f, g.material};
+        double k2 = 0; bool sim = true;
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+            double d = 0; for (int k = 0; k < 3; ++k) d += (double)m[k][i] * m[k][j];
+            if (i == 0 && j == 0) k2 = d;
+            if (std::fabs(d - (i == j ? k2 : 0.0)) > 1e-5 * (k2 > 0 ? k2 : 1.0)) sim = false;
+        }
+        if (!sim || k2 <= 0) throw Error(TRT_ERR_INVALID, "Transform::apply: a sphere needs a similarity transform");
+        return Geometry{false, (*this) * g.a, Vec3(), Vec3(), g.radius * (float)std::sqrt(k2), g.material};
+    }
+};
+
 class World {                                                   // hittable/world.rs:10-55
 public:
     void add_geometry(Geometry g) { geometries_.push_back(std::move(g)); }
     void add_geometry(const std::vector<Geometry>& list) { for (auto& g : list) geometries_.push_back(g); }
+    // instanced geometry: transformed copies of a template (math/transform.rs)
+    void add_instance(const std::vector<Geometry>& list, const Transform& t) { for (auto& g : list) geometries_.push_back(t.apply(g)); }
+    void add_instance(const Geometry& g, const Transform& t) { geometries_.push_back(t.apply(g)); }
     void add_material(const std::string& name, std::shared_ptr<Material> m) {
         if (materials_.count(name)) throw Error(TRT_ERR_INVALID, name + " key is already in the material table");   // world.rs:29-31
         materials_[name] = std::move(m);

@@ -15,6 +15,7 @@ KEYS = [
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
     "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "dram__bytes_read.sum", "dram__bytes_write.sum",
     "dram__bytes_read.sum.per_second", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sectors.sum", "lts__t_requests.sum", "lts__t_requests_srcunit_tex_op_read.sum", "lts__t_requests_srcunit_tex_op_write.sum", "lts__t_sector_op_read_hit_rate.pct",
     "lts__t_bytes.sum", "lts__t_bytes.sum.per_second", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "l1tex__t_bytes.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
@@ -44,6 +45,8 @@ for r in rows[2:]:
             e[k] = num(d[k]); e[k + "__unit"] = units[hdr.index(k)]
     e["stalls_per_issue"] = {h[len(STALL):-len("_per_issue_active.ratio")]: num(d[h]) for h in hdr
                              if h.startswith(STALL) and h.endswith("_per_issue_active.ratio") and d[h] not in ("", "0")}
+    if "lts__t_sectors.sum" in e:
+        e["l2_bytes"] = 32.0 * e["lts__t_sectors.sum"]          # 32-byte sectors through the L2 tag stage
     res.append(e)
 json.dump(res, open(out, "w"), indent=1)
 print("wrote", out, len(res), "launches")

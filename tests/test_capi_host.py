@@ -206,3 +206,50 @@ def test_header_is_plain_c99_and_host_calls_work_from_c(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "2 prims, 1 node(s), sample point 32 bytes" in r.stdout and "unknown material id" in r.stdout, r.stdout + r.stderr
 
+
+
+def test_transform_kats_and_instancing(trt):
+    """math/transform.rs:113-167 — the reference's own tests (translation, scale, the three rotations, the complex transform),
+    with Vec3's approximate equality (|delta| < 1e-7 per component, vec3.rs:189-201 + :32-35) — on the Python mirror; plus
+    instancing: a transformed new_box equals the box built in place, and a sphere refuses a non-similarity."""
+    T, V = trt.Transform, trt.Vec3
+    near = lambda a, b: all(abs(x - y) < 1e-7 for x, y in zip(a, b))
+    rad = lambda d: float(np.float32(d) * (np.float32(np.pi) / np.float32(180.0)))        # f32::to_radians
+    delta = V.new(1.0, -2.0, 3.0)
+    for v in (V.zero(), V.new(10.0, 15.0, 20.0)):
+        assert near(T.translate(delta) * v, (v.x + 1.0, v.y - 2.0, v.z + 3.0))
+        assert near(T.scale(delta) * v, (v.x * 1.0, v.y * -2.0, v.z * 3.0))
+    v1, v2 = V.new(1.0, 0.0, 0.0), V.new(0.0, 1.0, 1.0)
+    r1, r2, r3 = T.rotate_x(rad(90)), T.rotate_y(rad(90)), T.rotate_z(rad(90))
+    assert near(r1 * V.zero(), (0, 0, 0)) and near(r1 * v1, (1, 0, 0)) and near(r2 * v1, (0, 0, -1)) and near(r3 * v1, (0, 1, 0))
+    assert near(r1 * v2, (0, -1, 1)) and near(r2 * v2, (1, 1, 0)) and near(r3 * v2, (-1, 0, 1))
+    t = T.new(V.new(1.0, 2.0, 3.0), V.new(rad(90), rad(-90), rad(-90)), V.new(2.0, 3.0, 4.0))
+    assert near(t * V.zero(), (1, 2, 3))
+    got = t * V.new(1.0, 1.0, 0.0)
+    assert all(abs(a - b) < 1e-5 for a, b in zip(got, (1.0, 5.0, 7.0)))       # three chained f32 rotations: 1e-6 off, the reference's 1e-7 test is for its own libm
+    white = trt.Lambertian((0.73, 0.73, 0.73))
+    w = trt.World.new()
+    w.add_instance(trt.new_box((0, 0, 0), (30, 60, 30), white), T.translate((25, 0, 50)))
+    d = w.to_desc()
+    ref = trt.scenes.cornell()
+    assert np.array_equal(d.prim_data, ref.prim_data[6:12])                    # == new_box((25,0,50), (55,60,80)) of main.rs:66-70
+    s = T.new((1, 2, 3), (0.3, -0.2, 0.9), (2, 2, 2)).apply(trt.Sphere((1, 0, 0), 0.5, white))
+    assert abs(s.radius - 1.0) < 1e-6
+    with pytest.raises(ValueError):
+        T.scale((1, 2, 1)).apply(trt.Sphere((0, 0, 0), 1.0, white))
+
+
+def test_cpp_transform_mirror(tmp_path):
+    """The C++ mirror of math/transform.rs (include/trt.hpp): the reference's complex_transform test and box instancing."""
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "trt.hpp"\n#include <cstdio>\nint main() { using namespace trt; const float r = 90.0f * (3.14159265358979323846f / 180.0f);\n'
+                   '  Transform t = Transform::make({1, 2, 3}, {r, -r, -r}, {2, 3, 4}); Vec3 a = t * Vec3(0, 0, 0), b = t * Vec3(1, 1, 0);\n'
+                   '  World w; auto m = Lambertian({0.5f, 0.5f, 0.5f}); w.add_instance(new_box({0, 0, 0}, {30, 60, 30}, m), Transform::translate({25, 0, 50}));\n'
+                   '  const Geometry& g = w.geometries()[0]; bool thrown = false; try { Transform::scale({1, 2, 1}).apply(Sphere({0, 0, 0}, 1, m)); } catch (const Error&) { thrown = true; }\n'
+                   '  std::printf("%.5f %.5f %.5f | %.5f %.5f %.5f | %zu %.1f %.1f %.1f | %d\\n", a.x, a.y, a.z, b.x, b.y, b.z, w.geometries().size(), g.a.x, g.a.y, g.a.z, (int)thrown); return 0; }\n')
+    exe, pkg = str(tmp_path / "t"), os.path.join(ROOT, "tiny-raytracer_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe, "-L" + pkg, "-ltrt_b200", "-Wl,-rpath," + pkg])
+    out = subprocess.run([exe], capture_output=True, text=True).stdout.split("|")
+    a = [float(x) for x in out[0].split()]; b = [float(x) for x in out[1].split()]; c = out[2].split()
+    assert all(abs(x - y) < 1e-4 for x, y in zip(a, (1, 2, 3))) and all(abs(x - y) < 1e-4 for x, y in zip(b, (1, 5, 7)))
+    assert c == ["6", "25.0", "0.0", "80.0"] and out[3].strip() == "1"         # first face of the box: corner (25, 0, 80), main.rs:99-103

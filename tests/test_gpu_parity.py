@@ -217,15 +217,19 @@ def test_render_matches_oracle(trt, orc, ctx, kind, case):
 @pytest.mark.parametrize("regen_min", [1, 5, 16, 31])
 def test_async_regeneration_threshold_does_not_change_results(trt, orc, ctx, kind, regen_min):
     """TRT_FLAG_REGEN_MIN switches the megakernel to its step-wise form (shade/regenerate as soon as n lanes are waiting),
-    the schedule used automatically for big trees. It must not change a single bit of a single-lane-per-pixel image."""
+    the schedule used automatically for big trees. It must not change a single bit of a whole-pixel-item image."""
+    extra = 0
     for desc in (trt.scenes.cornell_spheres(96, 64, 6, 20), trt.scenes.final_scene(80, 45, 5, 50)):
         osc, ocam, cam = both(trt, orc, desc)
         sc = trt.Scene.from_desc(desc, kind)
-        p, op = params(trt, orc, desc, flags=(regen_min << 8))
+        p, op = params(trt, orc, desc, flags=(regen_min << 8) | extra | 2)
         lin, u8, st = sc.render(ctx, cam, p)
         olin, ou8, ost, _ = osc.render(ocam, op)
         assert (st.paths, st.rays) == (ost.paths, ost.rays)
-        assert ulp_diff(lin, olin).max() <= 1 and np.abs(u8.astype(np.int32) - ou8.astype(np.int32)).max() <= 1
+        assert np.array_equal(bits(lin), bits(olin)) and np.abs(u8.astype(np.int32) - ou8.astype(np.int32)).max() <= 1
+        p, op = params(trt, orc, desc, flags=(regen_min << 8) | extra)          # with the tail split: f64 atomics, <= 1 ulp
+        lin, u8, st = sc.render(ctx, cam, p)
+        assert (st.paths, st.rays) == (ost.paths, ost.rays) and ulp_diff(lin, olin).max() <= 1
 
 
 @pytest.mark.parametrize("kind", [0, 1])
@@ -256,11 +260,13 @@ def test_big_tree_render_matches_oracle(trt, orc, ctx):
     olin, ou8, ost, _ = osc.render(ocam, op)
     for kind in (0, 1):
         sc = trt.Scene.from_desc(desc, kind)
-        lin, u8, st = sc.render(ctx, cam, p)
-        assert st.paths == ost.paths
-        bad = (ulp_diff(lin, olin) > 1).any(axis=2)
-        assert st.rays == ost.rays and not bad.any()
-        assert psnr8(u8, ou8) >= PSNR_MIN_DB
+        for flags in (0, 1, 8):      # plain, and both event-counting builds
+            p, _ = params(trt, orc, desc, flags=flags)
+            lin, u8, st = sc.render(ctx, cam, p)
+            assert st.paths == ost.paths
+            bad = (ulp_diff(lin, olin) > 1).any(axis=2)
+            assert st.rays == ost.rays and not bad.any()
+            assert psnr8(u8, ou8) >= PSNR_MIN_DB
 
 
 @pytest.mark.parametrize("kind", [0, 1, 3])
@@ -389,15 +395,19 @@ def test_empty_scene_and_zero_work(trt, orc, ctx):
     cam = trt.make_camera(**empty.camera)
     for kind in (0, 1):
         sc = trt.Scene.from_desc(empty, kind)
-        lin, u8, st = sc.render(ctx, cam, trt.make_params(16, 8, 4, 20, empty.background, 3))
-        assert np.array_equal(lin.reshape(-1, 3), np.tile(np.float32([0.25, 0.5, 0.75]), (128, 1))) and st.rays == st.paths == 512
-        assert int(u8[0, 0, 1]) == orc.tonemap(0.5)
+        for flags in (0, 9 << 8):        # T-then-S and the step-wise loop
+            lin, u8, st = sc.render(ctx, cam, trt.make_params(16, 8, 4, 20, empty.background, 3, flags=flags))
+            assert np.array_equal(lin.reshape(-1, 3), np.tile(np.float32([0.25, 0.5, 0.75]), (128, 1))) and st.rays == st.paths == 512
+            assert int(u8[0, 0, 1]) == orc.tonemap(0.5)
     sc = trt.Scene.from_desc(desc, 1)
     cam = trt.make_camera(**desc.camera)
-    lin, _, st = sc.render(ctx, cam, trt.make_params(16, 8, 4, 0, desc.background, 1))
-    assert not lin.any() and st.rays == 0 and st.paths == 512
-    lin, _, st = sc.render(ctx, cam, trt.make_params(16, 8, 0, 20, desc.background, 1))
-    assert not lin.any() and st.rays == 0 and st.paths == 0
+    for flags in (0, 9 << 8):
+        lin, _, st = sc.render(ctx, cam, trt.make_params(16, 8, 4, 0, desc.background, 1, flags=flags))
+        assert not lin.any() and st.rays == 0 and st.paths == 512
+        lin, _, st = sc.render(ctx, cam, trt.make_params(16, 8, 0, 20, desc.background, 1, flags=flags))
+        assert not lin.any() and st.rays == 0 and st.paths == 0
+        lin, _, st = sc.render(ctx, cam, trt.make_params(16, 8, 1, 1, desc.background, 1, flags=flags))      # one sample, one bounce
+        assert st.rays == st.paths == 128
 
 
 def test_reference_api_renderer(trt, orc, ctx):
@@ -841,3 +851,39 @@ def test_cpp_multi_gpu_example_equals_one_gpu(trt, orc, ctx, tmp_path):
     desc = trt.scenes.cornell(480, 270, 64, 50)
     _, _, ost, _ = orc.Scene.from_desc(desc).render(orc.make_camera(**desc.camera), orc.make_params(480, 270, 64, 50, desc.background, 1))
     assert d["rays_ngpu"] == ost.rays
+
+
+def test_instanced_geometry_renders_like_explicit_geometry(trt, orc, ctx):
+    """`Transform`-instanced geometry. The Cornell box with its two boxes placed as INSTANCES of one
+    template box (translation only, exact in f32) is the same scene as main.rs builds explicitly: bit-identical to the oracle.
+    A rotated + uniformly scaled instance of a sphere-and-box template renders like the same primitives added explicitly."""
+    T = trt.Transform
+    def walls(world):
+        world.add_material("red", trt.Lambertian((0.65, 0.05, 0.05))); world.add_material("white", trt.Lambertian((0.73, 0.73, 0.73)))
+        world.add_material("green", trt.Lambertian((0.12, 0.45, 0.15))); world.add_material("light", trt.Light((15.0, 15.0, 15.0)))
+        q = lambda c, u, v, m: world.add_geometry(trt.Quad(c, u, v, world.get_material(m)))
+        q((100, 0, 0), (0, 100, 0), (0, 0, 100), "green"); q((0, 0, 0), (0, 100, 0), (0, 0, 100), "red")
+        q((65, 100, 60), (-30, 0, 0), (0, 0, -20), "light"); q((0, 0, 0), (100, 0, 0), (0, 0, 100), "white")
+        q((100, 100, 100), (-100, 0, 0), (0, 0, -100), "white"); q((0, 0, 100), (100, 0, 0), (0, 100, 0), "white")
+    world = trt.World.new(); walls(world)
+    white = world.get_material("white")
+    world.add_instance(trt.new_box((0, 0, 0), (30, 60, 30), white), T.translate((25, 0, 50)))
+    world.add_instance(trt.new_box((0, 0, 0), (30, 30, 30), white), T.translate((45, 0, 10)))
+    camera = trt.Camera.new(140.0, 0.6, (50, 50, -140), (50, 50, 0), (0, 1, 0), 40.0, 96, 96)
+    img = trt.Renderer.new(8, 8, 20, True, (0.001, 0.001, 0.001), seed=1).render(camera, world)
+    desc = trt.scenes.cornell(96, 96, 8, 20)
+    olin, ou8, _, _ = orc.Scene.from_desc(desc).render(orc.make_camera(**desc.camera), orc.make_params(96, 96, 8, 20, desc.background, 1))
+    assert np.array_equal(bits(img.linear), bits(olin))
+    # a general similarity: the instance equals the explicitly transformed primitives (same host arithmetic), and the oracle agrees
+    t = T.new((50, 20, 50), (0.4, 0.7, -0.2), (1.5, 1.5, 1.5))
+    glass = trt.Dielectric((1.0, 1.0, 1.0), 1.5)
+    template = trt.new_box((-5, -5, -5), (5, 5, 5), white) + [trt.Sphere((0, 9, 0), 4.0, glass)]
+    w2 = trt.World.new(); walls(w2); w2.add_material("glass", glass); w2.add_instance(template, t)
+    d2 = w2.to_desc()
+    assert d2.n_prims == 13 and abs(float(d2.prim_data[12, 3]) - 6.0) < 1e-5
+    d2 = trt.scenes.SceneDesc("instanced", d2.materials, d2.prim_type, d2.prim_data, d2.prim_mat, dict(desc.camera), 6, 20, desc.background, 3)
+    osc, ocam, cam = both(trt, orc, d2)
+    p, op = params(trt, orc, d2)
+    lin, u8, st = trt.Scene.from_desc(d2, trt.BVH_AUTO).render(ctx, cam, p)
+    olin, ou8, ost, _ = osc.render(ocam, op)
+    assert st.rays == ost.rays and ulp_diff(lin, olin).max() <= 1

@@ -425,6 +425,83 @@ def new_box(a, b, mat: Material):
             Quad((mn[0], mx[1], mx[2]), dx, ndz, mat), Quad((mn[0], mn[1], mn[2]), dx, dz, mat)]
 
 
+class Transform:
+    """math::transform::Transform (math/transform.rs:10-111): a 4x4 f32 matrix; `new(translation, rotation, scale)` =
+    translate * scale * rotate with rotate = Rz * Ry * Rx (transform.rs:15-21,78-80); `t * v` transforms a point (:104-111).
+    The reference never applies it to geometry (dead code upstream). Here it also instances geometry:
+    `World.add_instance(geometries, transform)` adds transformed COPIES — a quad's corner goes through the matrix, its edges
+    through the linear part; a sphere needs a similarity (rotation + uniform |scale|) — so one template (e.g. `new_box`)
+    can be placed many times. Instances are flattened on the host like `new_box` is: the device sees ordinary primitives."""
+
+    def __init__(self, mat=None):
+        self.mat = np.eye(4, dtype=np.float32) if mat is None else np.asarray(mat, np.float32).reshape(4, 4)
+
+    @classmethod
+    def new(cls, translation, rotation, scale):
+        return cls.translate(translation) * cls.scale(scale) * cls.rotate(rotation)
+
+    @classmethod
+    def identity(cls): return cls()
+
+    @classmethod
+    def translate(cls, delta):
+        m = np.eye(4, dtype=np.float32); m[0, 3], m[1, 3], m[2, 3] = _v(delta); return cls(m)
+
+    @classmethod
+    def scale(cls, scales):
+        m = np.eye(4, dtype=np.float32); m[0, 0], m[1, 1], m[2, 2] = _v(scales); return cls(m)
+
+    @staticmethod
+    def _cs(angle):
+        a = np.float32(angle)
+        return np.float32(np.cos(a)), np.float32(np.sin(a))
+
+    @classmethod
+    def rotate_x(cls, angle):
+        c, s = cls._cs(angle); m = np.eye(4, dtype=np.float32); m[1, 1], m[1, 2], m[2, 1], m[2, 2] = c, -s, s, c; return cls(m)
+
+    @classmethod
+    def rotate_y(cls, angle):
+        c, s = cls._cs(angle); m = np.eye(4, dtype=np.float32); m[0, 0], m[0, 2], m[2, 0], m[2, 2] = c, s, -s, c; return cls(m)
+
+    @classmethod
+    def rotate_z(cls, angle):
+        c, s = cls._cs(angle); m = np.eye(4, dtype=np.float32); m[0, 0], m[0, 1], m[1, 0], m[1, 1] = c, -s, s, c; return cls(m)
+
+    @classmethod
+    def rotate(cls, angles):
+        ax, ay, az = _v(angles)
+        return cls.rotate_z(az) * cls.rotate_y(ay) * cls.rotate_x(ax)
+
+    def __mul__(self, rhs):
+        if isinstance(rhs, Transform):
+            return Transform(self.mat @ rhs.mat)
+        x, y, z = _v(rhs)
+        r = self.mat @ np.array([x, y, z, 1.0], np.float32)
+        return Vec3(r[0], r[1], r[2])
+
+    def linear(self, v):
+        """The matrix without its translation column applied to a direction / edge vector."""
+        x, y, z = _v(v)
+        r = self.mat[:3, :3] @ np.array([x, y, z], np.float32)
+        return Vec3(r[0], r[1], r[2])
+
+    def apply(self, geometry):
+        """A transformed copy of a Sphere / Quad (or list of them)."""
+        if isinstance(geometry, (list, tuple)):
+            return [self.apply(g) for g in geometry]
+        if isinstance(geometry, Quad):
+            return Quad(self * geometry.corner, self.linear(geometry.u), self.linear(geometry.v), geometry.material)
+        if isinstance(geometry, Sphere):
+            L3 = self.mat[:3, :3].astype(np.float64)
+            g = L3.T @ L3                                            # similarity <=> L^T L = k^2 I
+            k2 = float(g[0, 0])
+            if k2 <= 0.0 or not np.allclose(g, k2 * np.eye(3), rtol=1e-5, atol=1e-6 * k2):
+                raise ValueError("Transform.apply: a sphere needs a similarity transform (rotation + uniform scale)")
+            return Sphere(self * geometry.center, float(np.float32(geometry.radius) * np.float32(np.sqrt(k2))), geometry.material)
+        raise TypeError("unsupported geometry %r" % (geometry,))
+
+
 class World:
     """hittable::world::World (hittable/world.rs:10-55)."""
 
@@ -439,6 +516,10 @@ class World:
             self.geometries.extend(geometry)
         else:
             self.geometries.append(geometry)
+
+    def add_instance(self, geometry, transform: "Transform"):
+        """Instanced geometry: a transformed copy of `geometry` (one Sphere / Quad or a list such as `new_box(...)`)."""
+        self.add_geometry(transform.apply(geometry))
 
     def add_material(self, name: str, material: Material):
         if name in self.materials:                  # world.rs:29-31 panics

@@ -238,20 +238,35 @@ TRT_DEV float rcp_approx(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"
 
 // ------------------------------------------------------------------ primitives
 // Sphere::hit, hittable/sphere.rs:29-45. Returns t in [t_min, hi) or NaN-free "miss" as false.
+// Three shortcuts skip work whose outcome is already decided; each is EXACT — it returns what the literal sequence would — for
+// t_min > 0 (the reference's 0.001, cpu.rs:48) and is switched off otherwise:
+//  (1) half_b > 0 and c >= 0 (origin on or outside the sphere, moving away: every ray leaving the sphere it starts on — the
+//      commonest sphere test of all, because the origin lies inside that sphere's own box): a*c >= 0, so disc = fl(hb*hb - a*c)
+//      <= fl(hb*hb) and sqrt(disc) <= sqrt(fl(hb*hb)) = |hb| (sqrt(fl(x*x)) == |x| in binary round-to-nearest) -> both
+//      numerators -hb -+ sq are <= 0 -> both roots <= 0 < t_min: a miss, without the square root and the two divisions.
+//  (2) c < 0 (origin inside): a*c <= 0 -> sqrt(disc) >= |hb| -> the first numerator -hb - sq <= 0 -> root 1 <= 0 < t_min: its
+//      division is skipped, root 2 is computed as usual.
+//  (3) root 1 >= hi: root 2 >= root 1 (same positive divisor, larger numerator, correctly rounded division is monotone) -> miss.
+//  A NaN anywhere fails the comparisons of (1) and (2) and takes the literal path.
 template <bool SMEM> TRT_DEV bool sphere_hit(const DevScene& S, uint32_t idx, V3 o, V3 d, float t_min, float hi, float* t_out) {
     float4 s = ld4<SMEM>(S.spheres + idx);
     V3 oc = o - mk(s.x, s.y, s.z);
     float a = dot(d, d);
     float half_b = dot(oc, d);
     float c = dot(oc, oc) - s.w * s.w;
+    const bool pos = t_min > 0.0f && a > 0.0f;
+    if (pos && half_b > 0.0f && c >= 0.0f) return false;                     // (1)
     float disc = half_b * half_b - a * c;
     if (disc < 0.0f) return false;
     float sq = sqrtf(disc);
-    float t = (-half_b - sq) / a;
-    if (!(t_min <= t && t < hi)) {
-        t = (-half_b + sq) / a;
-        if (!(t_min <= t && t < hi)) return false;
+    float t;
+    if (!(pos && c < 0.0f)) {                                                 // (2)
+        t = (-half_b - sq) / a;
+        if (t_min <= t && t < hi) { *t_out = t; return true; }
+        if (pos && t >= hi) return false;                                     // (3)
     }
+    t = (-half_b + sq) / a;
+    if (!(t_min <= t && t < hi)) return false;
     *t_out = t; return true;
 }
 // Quad::hit, hittable/quad.rs:33-41
@@ -296,6 +311,7 @@ struct Hit { float t; uint32_t ref; };
 // visiting order, and the walk must at least FIND it to notice (needs_replay below). Culling only beyond (1 + 2^-8) x the
 // closest hit keeps every primitive whose t/entry disagreement is below 0.4 % in play (a sphere's is bounded by
 // ~sqrt(20 * 2^-24) = 0.1 %), at the price of a few extra node visits.
+#define TRT_WIDE_SMEM_F4 7u         /* float4 per wide node in SHARED memory (8 in global memory), see stage_scene */
 #ifndef TRT_SAH_CULL_MARGIN
 #define TRT_SAH_CULL_MARGIN 0.00390625f
 #endif
@@ -442,7 +458,7 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, float t_min, TravStack& K, E
     if (!(cur & TRT_REF_LEAF)) {
         TRT_ASSERT(cur < S.n_nodes4);
         if (COUNT) ec->node_visits += 1;
-        const float4* np = S.nodes4 + 8 * (size_t)cur;
+        const float4* np = S.nodes4 + (size_t)(SMEM ? TRT_WIDE_SMEM_F4 : 8) * cur;
         const float4 a0 = ld4<SMEM>(np), a1 = ld4<SMEM>(np + 1), a2 = ld4<SMEM>(np + 2);
         const float4 b0 = ld4<SMEM>(np + 3), b1 = ld4<SMEM>(np + 4), b2 = ld4<SMEM>(np + 5), rf = ld4<SMEM>(np + 6);
         float s0, e0, s1, e1, s2, e2, s3, e3;
@@ -697,11 +713,18 @@ TRT_DEV bool flat_prim_hit(const float4* p, bool is_quad, V3 o, V3 d, float t_mi
     } else {
         V3 oc = o - mk(g0.x, g0.y, g0.z);
         float a = dot(d, d), half_b = dot(oc, d), c = dot(oc, oc) - g0.w * g0.w;
+        const bool pos = t_min > 0.0f && a > 0.0f;                           // the three exact shortcuts of sphere_hit
+        if (pos && half_b > 0.0f && c >= 0.0f) return false;
         float disc = half_b * half_b - a * c;
         if (disc < 0.0f) return false;
         float sq = sqrtf(disc);
-        t = (-half_b - sq) / a;
-        if (!(t_min <= t && t < hi)) { t = (-half_b + sq) / a; if (!(t_min <= t && t < hi)) return false; }
+        bool have = false;
+        if (!(pos && c < 0.0f)) {
+            t = (-half_b - sq) / a;
+            have = t_min <= t && t < hi;
+            if (!have && pos && t >= hi) return false;
+        }
+        if (!have) { t = (-half_b + sq) / a; if (!(t_min <= t && t < hi)) return false; }
     }
     *t_out = t; return true;
 }
@@ -837,7 +860,8 @@ TRT_DEV uint8_t tonemap_u8(float lin) {
 __host__ __device__ inline uint32_t aux_f4(uint32_t n_spheres, uint32_t n_quads, uint32_t n_materials) { return n_spheres + 2u * n_quads + 2u * n_materials; }
 // layout: [nodes or wide nodes | spheres | quads | sphere_meta | quad_meta | quad_nn | materials (the four per-hit arrays only while small) | flat list]
 template <bool SMEM, int KIND>
-__device__ __forceinline__ DevScene stage_scene(const DevScene& G) {
+__device__ __forceinline__ DevScene stage_scene(const DevScene& G, uint32_t* used_f4 = nullptr) {
+    if (used_f4) *used_f4 = 0;
     if (!SMEM) return G;
     extern __shared__ float4 smem_f4[];
     DevScene S = G;
@@ -848,8 +872,15 @@ __device__ __forceinline__ DevScene stage_scene(const DevScene& G) {
         off += n;
         return dst;
     };
-    if (KIND == 3 || KIND == 4) S.nodes4 = copy(G.nodes4, 8 * G.n_nodes4);          // the walk reads only one of the two node arrays
-    else S.nodes = copy(G.nodes, 4 * G.n_nodes);
+    if (KIND == 3 || KIND == 4) {          // the walk reads only one of the two node arrays
+        // wide records are re-strided to 7 float4 (their 8th is unused): an ODD stride puts the same field of different nodes on
+        // different bank groups (128-byte records: every lane of a quarter-warp on the same four banks, 53 % of the final scene's
+        // shared-memory wavefronts were conflicts, profiles/r2a) and the staged tree is 1/8 smaller
+        float4* dst = smem_f4 + off;
+        const uint32_t n = TRT_WIDE_SMEM_F4 * G.n_nodes4;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { const uint32_t node = i / TRT_WIDE_SMEM_F4; dst[i] = G.nodes4[8u * node + (i - TRT_WIDE_SMEM_F4 * node)]; }
+        off += n; S.nodes4 = dst;
+    } else S.nodes = copy(G.nodes, 4 * G.n_nodes);
     S.spheres = copy(G.spheres, G.n_spheres);
     S.quads = copy(G.quads, 4 * G.n_quads);
     if (aux_f4(G.n_spheres, G.n_quads, G.n_materials) <= TRT_AUX_SMEM_F4) {   // else: left in global memory (generic loads)
@@ -859,6 +890,7 @@ __device__ __forceinline__ DevScene stage_scene(const DevScene& G) {
         S.materials = copy(G.materials, 2 * G.n_materials);
     }
     S.flat = (const FlatPrim*)copy((const float4*)G.flat, TRT_FLAT_F4 * G.n_flat);
+    if (used_f4) *used_f4 = off;
     __syncthreads();
     return S;
 }

@@ -272,9 +272,15 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
     }
 }
 
-template <int KIND, bool SMEM, bool COUNT>
+// MODE: 0 = T-then-S (small trees), 1 = step-wise (big trees). Separate kernels, so that each loop gets its own register
+// allocation (one kernel holding both loops spilled 244 bytes in the step-wise loop, its own kernel 94).
+// Measured and rejected (round 2): a step-wise loop with TWO paths per lane whose state lives in shared memory, so that a lane
+// traces its second path while the hit of the first waits for the S block: correct (bit-identical sums, in sample order), but
+// 10^6 spheres 1 666 vs 2 128 Mrays/s and the final scene 4 209 vs 7 710 — the 35 KB of shared memory per CTA it needs cost
+// L1 capacity (10^6 spheres) or a whole CTA of occupancy (final scene), and the ray-swap block runs at low lane counts.
+template <int KIND, bool SMEM, bool COUNT, int MODE>
 __global__ void __launch_bounds__(MEGA_THREADS, TRT_MEGA_MIN_BLOCKS) k_render_mega(const __grid_constant__ MegaArgs A) {
-    if (A.regen_min >= 32u) mega_body<KIND, SMEM, COUNT>(A, nullptr);
+    if (MODE == 0) mega_body<KIND, SMEM, COUNT>(A, nullptr);
     else mega_body_async<KIND, SMEM, COUNT>(A);
 }
 __global__ void __launch_bounds__(TRT_FLAT_THREADS, TRT_FLAT_MIN_BLOCKS) k_render_mega_flat(const __grid_constant__ MegaArgs A, const __grid_constant__ FlatList L) {
@@ -371,19 +377,25 @@ uint32_t walk_kind(const SceneView& v, bool binary_only) {
 size_t scene_smem_bytes(const SceneView& v, uint32_t kind) {
     size_t aux = aux_f4(v.n_spheres, v.n_quads, v.n_materials);
     if (aux > TRT_AUX_SMEM_F4) aux = 0;
-    size_t nodes = (kind == 3 || kind == 4) ? 8ull * v.n_nodes4 : 4ull * v.n_nodes;
+    size_t nodes = (kind == 3 || kind == 4) ? (size_t)TRT_WIDE_SMEM_F4 * v.n_nodes4 : 4ull * v.n_nodes;
     return 16ull * (nodes + v.n_spheres + 4ull * v.n_quads + (size_t)TRT_FLAT_F4 * v.n_flat + aux);
 }
 
-template <int KIND, bool SMEM, bool COUNT>
-static cudaError_t mega_fn(const void** fn, int* blocks_per_sm, size_t smem) {
-    auto kern = k_render_mega<KIND, SMEM, COUNT>;
+template <int KIND, bool SMEM, bool COUNT, int MODE>
+static cudaError_t mega_fn3(const void** fn, int* blocks_per_sm, size_t smem) {
+    auto kern = k_render_mega<KIND, SMEM, COUNT, MODE>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
+    // big scenes stage nothing: give the whole configurable L1 / shared-memory array to L1 (their node and stack traffic lives there)
+    if (!SMEM) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxL1); if (e != cudaSuccess) return e; }
     *fn = (const void*)kern;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, MEGA_THREADS, smem);
+}
+template <int KIND, bool SMEM, bool COUNT>
+static cudaError_t mega_fn(int mode, const void** fn, int* blocks_per_sm, size_t smem) {
+    return mode == 1 ? mega_fn3<KIND, SMEM, COUNT, 1>(fn, blocks_per_sm, smem) : mega_fn3<KIND, SMEM, COUNT, 0>(fn, blocks_per_sm, smem);
 }
 
 cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const trt_params& p, double* d_sum64,
@@ -408,23 +420,24 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     bool use_smem = smem <= 64 * 1024;
     if (v.kind == 2 && (!use_smem || v.n_flat > TRT_FLAT_MAX || !v.flat_cbox_host)) return cudaErrorInvalidValue;
     if (!use_smem) smem = 0;
+    const int mega_mode = A.regen_min >= 32u ? 0 : 1;
     const void* fn = nullptr; int blocks_per_sm = 0; cudaError_t e;
     if (v.kind == 2) {
         if (smem > 48 * 1024) { e = cudaFuncSetAttribute(k_render_mega_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
         fn = (const void*)k_render_mega_flat;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_render_mega_flat, TRT_FLAT_THREADS, smem);
     } else if (kind == 3) {
-        if (count) e = use_smem ? mega_fn<3, true, true>(&fn, &blocks_per_sm, smem) : mega_fn<3, false, true>(&fn, &blocks_per_sm, smem);
-        else e = use_smem ? mega_fn<3, true, false>(&fn, &blocks_per_sm, smem) : mega_fn<3, false, false>(&fn, &blocks_per_sm, smem);
+        if (count) e = use_smem ? mega_fn<3, true, true>(mega_mode, &fn, &blocks_per_sm, smem) : mega_fn<3, false, true>(mega_mode, &fn, &blocks_per_sm, smem);
+        else e = use_smem ? mega_fn<3, true, false>(mega_mode, &fn, &blocks_per_sm, smem) : mega_fn<3, false, false>(mega_mode, &fn, &blocks_per_sm, smem);
     } else if (kind == 4) {
-        if (count) e = use_smem ? mega_fn<4, true, true>(&fn, &blocks_per_sm, smem) : mega_fn<4, false, true>(&fn, &blocks_per_sm, smem);
-        else e = use_smem ? mega_fn<4, true, false>(&fn, &blocks_per_sm, smem) : mega_fn<4, false, false>(&fn, &blocks_per_sm, smem);
+        if (count) e = use_smem ? mega_fn<4, true, true>(mega_mode, &fn, &blocks_per_sm, smem) : mega_fn<4, false, true>(mega_mode, &fn, &blocks_per_sm, smem);
+        else e = use_smem ? mega_fn<4, true, false>(mega_mode, &fn, &blocks_per_sm, smem) : mega_fn<4, false, false>(mega_mode, &fn, &blocks_per_sm, smem);
     } else if (v.kind == 1) {
-        if (use_smem) e = count ? mega_fn<1, true, true>(&fn, &blocks_per_sm, smem) : mega_fn<1, true, false>(&fn, &blocks_per_sm, smem);
-        else e = count ? mega_fn<1, false, true>(&fn, &blocks_per_sm, smem) : mega_fn<1, false, false>(&fn, &blocks_per_sm, smem);
+        if (use_smem) e = count ? mega_fn<1, true, true>(mega_mode, &fn, &blocks_per_sm, smem) : mega_fn<1, true, false>(mega_mode, &fn, &blocks_per_sm, smem);
+        else e = count ? mega_fn<1, false, true>(mega_mode, &fn, &blocks_per_sm, smem) : mega_fn<1, false, false>(mega_mode, &fn, &blocks_per_sm, smem);
     } else {
-        if (use_smem) e = count ? mega_fn<0, true, true>(&fn, &blocks_per_sm, smem) : mega_fn<0, true, false>(&fn, &blocks_per_sm, smem);
-        else e = count ? mega_fn<0, false, true>(&fn, &blocks_per_sm, smem) : mega_fn<0, false, false>(&fn, &blocks_per_sm, smem);
+        if (use_smem) e = count ? mega_fn<0, true, true>(mega_mode, &fn, &blocks_per_sm, smem) : mega_fn<0, true, false>(mega_mode, &fn, &blocks_per_sm, smem);
+        else e = count ? mega_fn<0, false, true>(mega_mode, &fn, &blocks_per_sm, smem) : mega_fn<0, false, false>(mega_mode, &fn, &blocks_per_sm, smem);
     }
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) blocks_per_sm = 1;
@@ -447,7 +460,7 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     } else if (p.spp >= 32 && !(p.flags & TRT_FLAG_NO_TAIL_SPLIT)) {
         tiles_rest = (2 * resident + 31) / 32;                 // ~2 pixels per lane are handed out in pieces
         if (tiles_rest > n_tiles) tiles_rest = n_tiles;
-        chunk = (p.spp + 7) / 8; if (chunk < 4) chunk = 4;
+        chunk = (p.spp + 31) / 32; if (chunk < 4) chunk = 4;     // 1/32 of a pixel: the job ends within ~half a chunk per lane (1/8: -0.35 % at 1024 spp)
     }
     A.chunk = chunk; A.n_chunks = p.spp ? (p.spp + chunk - 1) / chunk : 0;
     A.tiles_whole = (uint32_t)(n_tiles - tiles_rest);
