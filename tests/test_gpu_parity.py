@@ -812,6 +812,13 @@ def test_two_gpus_equal_one_gpu_equal_oracle(trt, orc, ctx):
         assert ulp_diff(mlin, one).max() <= 1 and ulp_diff(mlin, olin).max() <= 1
         assert np.abs(mu8.astype(int) - ou8.astype(int)).max() <= 1 and psnr8(mu8, ou8) >= PSNR_MIN_DB
         ctxs[1].close()
+    # trees built on both devices at once (parallel uploads inside trt_multi_render)
+    big = trt.scenes.random_spheres(70_000, 96, 54, 4, 8)
+    osc, ocam, cam = both(trt, orc, big)
+    p, op = params(trt, orc, big)
+    olin, _, ost, _ = osc.render(ocam, op)
+    lin, u8, st = trt.Scene.from_desc(big, trt.BVH_AUTO).render_multi([0, 1], cam, p)
+    assert (st.paths, st.rays) == (ost.paths, ost.rays) and ulp_diff(lin, olin).max() <= 1
 
 
 def test_render_multi_on_one_device_equals_render(trt, orc, ctx):
@@ -832,6 +839,25 @@ def test_render_multi_on_one_device_equals_render(trt, orc, ctx):
         sc.render_multi([], cam, p)
     with pytest.raises(trt.TrtError):
         sc.render_multi([99], cam, p)
+    # fewer samples than shares: one share is empty and still takes part in the reduce
+    p2, op2 = params(trt, orc, desc, spp=2)
+    o2, _, ost2, _ = osc.render(ocam, op2)
+    lin, u8, st = sc.render_multi([0, 0, 0], cam, p2)
+    assert (st.paths, st.rays) == (ost2.paths, ost2.rays) and ulp_diff(lin, o2).max() <= 1
+    # a persistent handle renders several frames and several scenes (buffers and contexts are reused); trees built on the device
+    mc = trt.MultiContext([0, 0])
+    big = trt.scenes.random_spheres(70_000, 96, 54, 3, 8)
+    bosc, bocam, bcam = both(trt, orc, big)
+    bp, bop = params(trt, orc, big)
+    bolin, _, bost, _ = bosc.render(bocam, bop)
+    bsc = trt.Scene.from_desc(big, trt.BVH_AUTO)                 # >= 65 536 primitives: LBVH + reference order built during the upload
+    for _ in range(2):
+        lin, u8, st = mc.render(bsc, bcam, bp)
+        assert (st.paths, st.rays) == (bost.paths, bost.rays) and ulp_diff(lin, bolin).max() <= 1
+        lin, u8, st = mc.render(sc, cam, p)
+        assert st.rays == ost.rays and ulp_diff(lin, olin).max() <= 1
+    assert np.array_equal(bsc.leaf_ranks(), orc.Scene.from_desc(big).leaf_ranks())
+    mc.close()
 
 
 def test_cpp_multi_gpu_example_equals_one_gpu(trt, orc, ctx, tmp_path):

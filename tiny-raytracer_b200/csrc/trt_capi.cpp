@@ -32,6 +32,9 @@ struct DeviceCopy {
 struct trt_scene {
     trt::HostScene host;
     std::map<int, DeviceCopy> on_device;   // device ordinal -> copy
+    std::mutex host_mutex;                 // trt_scene_upload writes a little host-side state (device-computed leaf ranks, build
+                                           // times, tree depth): trt_multi_render uploads to all devices at once (entries of
+                                           // on_device are created beforehand on the calling thread; the map itself is not resized)
 };
 struct trt_ctx {
     int device = 0; int sm_count = 0; cudaStream_t stream = nullptr; cudaStream_t own_stream = nullptr; cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -220,7 +223,7 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
         std::vector<trt_u4> meta(f.sphere_meta.size() + f.quad_meta.size());     // meta = (material, rank, prim_id, 0)
         if (sz[3]) e = cudaMemcpy(meta.data(), (char*)dc.buf + off[3], sz[3], cudaMemcpyDeviceToHost);
         if (e == cudaSuccess && sz[4]) e = cudaMemcpy(meta.data() + f.sphere_meta.size(), (char*)dc.buf + off[4], sz[4], cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess) for (const trt_u4& m : meta) if (m.z < s->host.leaf_rank.size()) s->host.leaf_rank[m.z] = m.y;
+        if (e == cudaSuccess) { std::lock_guard<std::mutex> lk(s->host_mutex); for (const trt_u4& m : meta) if (m.z < s->host.leaf_rank.size()) s->host.leaf_rank[m.z] = m.y; }
         return e;
     };
     if (f.wide_on_device) {
@@ -234,7 +237,7 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
         if (e == cudaSuccess) e = ref_order(d_boxes, &ms_ref);
         if (d_boxes) cudaFree(d_boxes);
         if (e != cudaSuccess) return fail_cuda("trt_scene_upload: device reference order", e);
-        s->host.device_build_ms = ms_ref;
+        { std::lock_guard<std::mutex> lk(s->host_mutex); s->host.device_build_ms = ms_ref; }
     }
     if (device_build) {
         // the walked tree on the GPU: Morton codes + radix sort + Karras hierarchy + bottom-up boxes (trt_lbvh.cu)
@@ -255,7 +258,7 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
         if (e == cudaSuccess) e = ref_order(d_boxes, &ms_ref);
         if (d_boxes) cudaFree(d_boxes);
         if (e != cudaSuccess) return fail_cuda("trt_scene_upload: device BVH build", e);
-        s->host.flat.max_depth = depth; s->host.device_build_ms = ms + ms_ref;
+        { std::lock_guard<std::mutex> lk(s->host_mutex); s->host.flat.max_depth = depth; s->host.device_build_ms = ms + ms_ref; }
         if (depth > TRT_MAX_STACK) return fail(TRT_ERR_UNSUPPORTED, "trt_scene_upload: device-built tree deeper than the traversal stack; commit with TRT_BVH_SAH");
     }
     trtk::SceneView& v = dc.view;
@@ -499,7 +502,8 @@ int trt_multi_render(trt_multi* m, trt_scene* s, const trt_camera* cam, const tr
     size_t max_slice = 0;
     for (int k = 0; k < N; ++k) max_slice = std::max(max_slice, cut[(size_t)k + 1] - cut[(size_t)k]);
     max_slice = (max_slice + 1) & ~(size_t)1;
-    // buffers and the scene's device copies: serially, on the calling thread (trt_scene_upload also writes host-side state)
+    // buffers: serially, on the calling thread; the scene's device copies are made by the workers, all devices at once
+    // (one upload per DEVICE: a device listed twice is uploaded by its first slot, the others wait at the barrier below)
     for (MultiSlot& k : m->slot) {
         CU(cudaSetDevice(k.device));
         if (k.cap_values < n_values) {
@@ -514,7 +518,7 @@ int trt_multi_render(trt_multi* m, trt_scene* s, const trt_camera* cam, const tr
             if (k.d_stage) { cudaFree(k.d_stage); k.d_stage = nullptr; k.cap_stage = 0; }
             CU(cudaMalloc((void**)&k.d_stage, max_slice * (size_t)N * sizeof(double))); k.cap_stage = max_slice * (size_t)N;
         }
-        if ((rc = trt_scene_upload(k.ctx, s))) return rc;
+        (void)s->on_device[k.device];                                // create the map entry here: the workers only look it up
     }
     Barrier bar(N);
     std::vector<int> failed_flag(1, 0);
@@ -525,6 +529,12 @@ int trt_multi_render(trt_multi* m, trt_scene* s, const trt_camera* cam, const tr
         auto bad = [&](int code) { k.rc = code; k.err = g_last_error; std::lock_guard<std::mutex> lk(fail_m); failed_flag[0] = 1; };
         auto cu = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && k.rc == TRT_OK) bad(fail_cuda(what, e)); return e == cudaSuccess; };
         cudaStream_t st = k.ctx->stream;
+        // ---- the scene on this device (upload + device-side builds), once per device
+        bool first_of_device = true;
+        for (int q = 0; q < r; ++q) if (m->slot[(size_t)q].device == k.device) first_of_device = false;
+        if (first_of_device && cu(cudaSetDevice(k.device), "cudaSetDevice")) { int rc2 = trt_scene_upload(k.ctx, s); if (rc2) bad(rc2); }
+        bar.wait();
+        if (failed_flag[0]) return;
         // ---- this rank's share of the samples: contiguous, balanced (first spp % N ranks get one more)
         const uint32_t base = p->spp / (uint32_t)N, extra = p->spp % (uint32_t)N;
         const uint32_t cnt = base + ((uint32_t)r < extra ? 1u : 0u), off = (uint32_t)r * base + std::min((uint32_t)r, extra);

@@ -10,8 +10,22 @@
 #include <cstring>
 #include <future>
 #include <limits>
+#include <thread>
 
 namespace trt {
+
+// Independent per-element loops over big scenes (10^6 primitives: the plain loops of a commit took 80 ms on one core)
+template <class F> static void parallel_for(size_t n, F f) {
+    const size_t min_chunk = 65536;
+    size_t parts = n / min_chunk; if (parts > 8) parts = 8;
+    unsigned hw = std::thread::hardware_concurrency(); if (hw && parts > hw) parts = hw;
+    if (parts < 2) { f((size_t)0, n); return; }
+    std::vector<std::thread> th;
+    const size_t step = (n + parts - 1) / parts;
+    for (size_t k = 1; k < parts; ++k) th.emplace_back([=] { f(k * step, std::min(n, (k + 1) * step)); });
+    f((size_t)0, std::min(n, step));
+    for (std::thread& t : th) t.join();
+}
 
 // ------------------------------------------------------------------ primitives
 static inline void padded_box(const float a[3], const float b[3], float mn[3], float mx[3]) {
@@ -387,7 +401,7 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
     uint32_t ns = 0, nq = 0;
     for (auto& p : prims) p.type_index = p.type ? nq++ : ns++;
     leaf_rank.assign(n, 0);
-    flat = FlatScene(); flat.bvh_kind = bvh_kind;
+    flat.reset(bvh_kind);
 
     const bool timing = getenv("TRT_COMMIT_TIMING") != nullptr;      // stderr: where the commit time goes
     auto t_last = std::chrono::steady_clock::now();
@@ -408,13 +422,15 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
     if (device_build || ref_on_device) {
         // TRT_BVH_LBVH_DEVICE: no host tree at all. The node arrays AND the reference leaf ranks (meta.y, placeholder here)
         // are produced by trt_lbvh.cu during trt_scene_upload from these per-primitive boxes.
-        for (size_t i = 0; i < n; ++i) leaf_rank[i] = (uint32_t)i;
         flat.lbvh_boxes.resize(2 * n);
-        for (size_t i = 0; i < n; ++i) {
-            const HostPrim& p = prims[i];
-            flat.lbvh_boxes[2 * i] = {p.bmin[0], p.bmin[1], p.bmin[2], as_float(leaf_ref(p))};
-            flat.lbvh_boxes[2 * i + 1] = {p.bmax[0], p.bmax[1], p.bmax[2], 0.f};
-        }
+        parallel_for(n, [&](size_t i0, size_t i1) {
+            for (size_t i = i0; i < i1; ++i) {
+                const HostPrim& p = prims[i];
+                leaf_rank[i] = (uint32_t)i;
+                flat.lbvh_boxes[2 * i] = {p.bmin[0], p.bmin[1], p.bmin[2], as_float(leaf_ref(p))};
+                flat.lbvh_boxes[2 * i + 1] = {p.bmax[0], p.bmax[1], p.bmax[2], 0.f};
+            }
+        });
         if (device_build) { flat.root = 0; flat.n_nodes = (uint32_t)(n - 1); flat.max_depth = 0; flat.sah_cost = 0.f; }
     } else if (n) {
         RefBuilder rb{prims, ref_tree, order, {}};
@@ -450,24 +466,26 @@ bool HostScene::commit(int bvh_kind, std::string* err) {
     if (flat.max_depth > TRT_MAX_STACK) { *err = "trt_scene_commit: tree deeper than the traversal stack"; return false; }
 
     flat.spheres.resize(ns); flat.sphere_meta.resize(ns); flat.quads.resize(4 * (size_t)nq); flat.quad_nn.resize(nq); flat.quad_meta.resize(nq);
-    for (size_t i = 0; i < n; ++i) {
-        const HostPrim& p = prims[i];
-        trt_u4 meta = {p.mat, leaf_rank[i], (uint32_t)i, 0u};
-        if (p.type == 0) {
-            flat.spheres[p.type_index] = {p.a[0], p.a[1], p.a[2], p.r};
-            flat.sphere_meta[p.type_index] = meta;
-        } else {
-            trt_f4* q = &flat.quads[4 * (size_t)p.type_index];
-            q[0] = {p.n[0], p.n[1], p.n[2], p.d};
-            q[1] = {p.a[0], p.a[1], p.a[2], p.w[0]};
-            q[2] = {p.b[0], p.b[1], p.b[2], p.w[1]};
-            q[3] = {p.c[0], p.c[1], p.c[2], p.w[2]};
-            flat.quad_meta[p.type_index] = meta;
-            // outward_normal.normalized() of hittable/mod.rs:36-40 for this quad: v / sqrt(v.v), true divisions (vec3.rs:45-47)
-            float len = std::sqrt(p.n[0] * p.n[0] + p.n[1] * p.n[1] + p.n[2] * p.n[2]);
-            flat.quad_nn[p.type_index] = {p.n[0] / len, p.n[1] / len, p.n[2] / len, 0.f};
+    parallel_for(n, [&](size_t i0, size_t i1) {       // every primitive writes its own slots of its type's arrays
+        for (size_t i = i0; i < i1; ++i) {
+            const HostPrim& p = prims[i];
+            trt_u4 meta = {p.mat, leaf_rank[i], (uint32_t)i, 0u};
+            if (p.type == 0) {
+                flat.spheres[p.type_index] = {p.a[0], p.a[1], p.a[2], p.r};
+                flat.sphere_meta[p.type_index] = meta;
+            } else {
+                trt_f4* q = &flat.quads[4 * (size_t)p.type_index];
+                q[0] = {p.n[0], p.n[1], p.n[2], p.d};
+                q[1] = {p.a[0], p.a[1], p.a[2], p.w[0]};
+                q[2] = {p.b[0], p.b[1], p.b[2], p.w[1]};
+                q[3] = {p.c[0], p.c[1], p.c[2], p.w[2]};
+                flat.quad_meta[p.type_index] = meta;
+                // outward_normal.normalized() of hittable/mod.rs:36-40 for this quad: v / sqrt(v.v), true divisions (vec3.rs:45-47)
+                float len = std::sqrt(p.n[0] * p.n[0] + p.n[1] * p.n[1] + p.n[2] * p.n[2]);
+                flat.quad_nn[p.type_index] = {p.n[0] / len, p.n[1] / len, p.n[2] / len, 0.f};
+            }
         }
-    }
+    });
     if (bvh_kind == 2) {
         // the list, in reference leaf order: geometry, then the primitive's own padded box and its child-ref bits
         flat.flat.assign(TRT_FLAT_F4 * n, trt_f4{0.f, 0.f, 0.f, 0.f});

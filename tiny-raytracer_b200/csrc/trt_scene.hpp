@@ -41,6 +41,14 @@ struct FlatScene {
     uint32_t n_nodes = 0, max_depth = 0;
     float sah_cost = 0.f;
     int bvh_kind = 0;
+    // back to the empty state WITHOUT giving the arrays' memory back: a re-commit of a big scene then writes into pages it
+    // already owns (10^6 primitives: 64 MB of fresh page faults per commit otherwise)
+    void reset(int kind) {
+        nodes.clear(); nodes4.clear(); nodes_ref4.clear(); spheres.clear(); quads.clear(); sphere_meta.clear(); quad_meta.clear();
+        quad_nn.clear(); materials.clear(); flat.clear(); flat_cbox.clear(); lbvh_boxes.clear();
+        n_nodes4 = max_depth4 = n_nodes_ref4 = 0; wide_on_device = ref_on_device = false; flat_qmask[0] = flat_qmask[1] = 0u;
+        flat_bound = -1.f; root = TRT_REF_INVALID; n_nodes = max_depth = 0; sah_cost = 0.f; bvh_kind = kind;
+    }
     size_t bytes() const {
         return (nodes.size() + spheres.size() + quads.size() + materials.size()) * sizeof(trt_f4) +
                (sphere_meta.size() + quad_meta.size()) * sizeof(trt_u4);
