@@ -76,6 +76,14 @@ typedef struct trt_params {
 #define TRT_FLAG_COUNT_WALKED 8u   /* count on the walk the scene really gets (4-wide records where it has them): node_visits = records
                                     * fetched (112 B each), sphere_tests / quad_tests = primitive records fetched. For the memory
                                     * roofline of big scenes; ignored when TRT_FLAG_COUNT_EVENTS is set. Results do not change. */
+#define TRT_FLAG_INLINE_PRIMARY 16u /* megakernel: always generate and trace primary rays inside the path loop, never in the coherent
+                                    * first-bounce pass (used by default only where it pays: wide-node trees in
+                                    * shared memory). Same results bit for bit; A/B and tests. */
+#define TRT_FLAG_PRIMARY_PASS 32u   /* megakernel: use the first-bounce pass whatever the scene (needs width*height*32 bytes of device
+                                    * scratch per sample of a batch; loses to TRT_FLAG_INLINE_PRIMARY). Same results; A/B and tests. */
+/* bits 16..17 of flags: step function of the step-wise megakernel loop on wide nodes in global memory (0 = chosen by the library,
+ * 1 = 128-bit node loads, 2 = 256-bit node loads, 3 = 256-bit loads and one dependent fetch per step). Same results; A/B. */
+#define TRT_FLAG_STEP(n) (((n) & 3u) << 16)
 #define TRT_FLAG_BINARY_NODES 4u   /* tree kinds: walk the binary nodes instead of the 4-wide ones (same results; A/B and tests) */
 /* bits 8..15 of flags: megakernel tuning override, the number of lanes of a warp (1..32) that must have finished their ray
  * before the shade/regenerate block runs; 0 = chosen from the tree size (32 up to 4096 nodes, 16 above). Results do not

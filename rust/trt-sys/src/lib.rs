@@ -20,6 +20,9 @@ pub const TRT_FLAG_COUNT_EVENTS: u32 = 1;
 pub const TRT_FLAG_NO_TAIL_SPLIT: u32 = 2;
 pub const TRT_FLAG_BINARY_NODES: u32 = 4;
 pub const TRT_FLAG_COUNT_WALKED: u32 = 8;
+pub const TRT_FLAG_INLINE_PRIMARY: u32 = 16;
+pub const TRT_FLAG_PRIMARY_PASS: u32 = 32;
+pub const fn trt_flag_step(n: u32) -> u32 { (n & 3) << 16 }
 pub const fn trt_flag_regen_min(n: u32) -> u32 { (n & 0xFF) << 8 }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]

@@ -49,7 +49,7 @@ for k in range(n_scenes):
             fails += 1
             print("FAIL scene %d (n=%d seed=%d) kind=%d trace_rays: prim %d t %d" % (k, n, seed0 + k, kind, int((prim_r != oprim_r).sum()),
                   int((t_r.view(np.uint32) != ot_r.view(np.uint32)).sum())), flush=True)
-        for flags in (0, 4, 9 << 8, (3 << 8) | 4):      # T-then-S, binary nodes, step-wise loop on wide and on binary nodes
+        for flags in (0, 4, 9 << 8, (3 << 8) | 4, 16, (9 << 8) | 16):      # T-then-S, binary nodes, step-wise loop on wide / binary nodes; inline primary rays
             p = trt.make_params(w, h, spp, depth, desc.background, desc.seed, flags=flags | 2)
             prim, t, rad, nr = sc.render_aov(ctx, cam, p, True, True)
             lin, u8, st = sc.render(ctx, cam, p)

@@ -15,7 +15,7 @@ ap.add_argument("--kinds", default="0,1")
 ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--c4n", type=int, default=1_000_000)
-ap.add_argument("--flags", type=int, default=0, help="extra trt_params.flags bits (2 = no tail split)")
+ap.add_argument("--flags", default="0", help="comma list of extra trt_params.flags values to sweep (2 = no tail split, 16 = inline primary rays, 32 = first-bounce pass, n << 16 = step function n)")
 ap.add_argument("--stats", action="store_true", help="also print the event counters of the best run")
 ap.add_argument("--regen", default="0", help="comma list of regen_min overrides (0 = auto)")
 a = ap.parse_args()
@@ -35,16 +35,16 @@ for wl in a.workloads.split(","):
         sc.upload(ctx)
         acc = torch.zeros(h * w * 3, dtype=torch.float64, device="cuda:0")
         torch.cuda.synchronize()
-        for regen in [int(x) for x in a.regen.split(",")]:
-            p = trt.make_params(w, h, a.spp, desc.max_bounces, desc.background, desc.seed, spp_total=a.spp, variant=a.variant, flags=((regen & 255) << 8) | a.flags)
+        for regen, xflags in [(int(x), int(f)) for f in a.flags.split(",") for x in a.regen.split(",")]:
+            p = trt.make_params(w, h, a.spp, desc.max_bounces, desc.background, desc.seed, spp_total=a.spp, variant=a.variant, flags=((regen & 255) << 8) | xflags)
             best = None
             for r in range(a.reps):
                 acc.zero_(); torch.cuda.synchronize()
                 st = sc.render_accumulate(ctx, cam, p, acc.data_ptr())
                 if best is None or st.device_ms < best.device_ms:
                     best = st
-            print("%-3s kind=%d variant=%d spp=%d regen=%d  build %.2fs  nodes %d  %.2f ms  %.1f Mpaths/s  %.1f Mrays/s  rays/path %.2f" % (
-                wl, kind, a.variant, a.spp, regen, t_build, sc.bvh_info()["nodes"], best.device_ms, best.paths / best.device_ms / 1e3,
+            print("%-3s kind=%d variant=%d spp=%d flags=%d regen=%d  build %.2fs  nodes %d  %.2f ms  %.1f Mpaths/s  %.1f Mrays/s  rays/path %.2f" % (
+                wl, kind, a.variant, a.spp, xflags, regen, t_build, sc.bvh_info()["nodes"], best.device_ms, best.paths / best.device_ms / 1e3,
                 best.rays / best.device_ms / 1e3, best.rays / max(best.paths, 1)), flush=True)
             if a.stats:
                 r = max(best.rays, 1)

@@ -913,3 +913,64 @@ def test_instanced_geometry_renders_like_explicit_geometry(trt, orc, ctx):
     lin, u8, st = trt.Scene.from_desc(d2, trt.BVH_AUTO).render(ctx, cam, p)
     olin, ou8, ost, _ = osc.render(ocam, op)
     assert st.rays == ost.rays and ulp_diff(lin, olin).max() <= 1
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 4])
+def test_first_bounce_pass_is_bit_identical_to_inline_primary_rays(trt, orc, ctx, kind):
+    """Round 2: primary rays can be generated and traced by a coherent pass (k_primary) that hands the path loop one record per
+    path — the default for wide-node trees in shared memory (where it was measured to pay), forced by TRT_FLAG_PRIMARY_PASS (32)
+    and forbidden by TRT_FLAG_INLINE_PRIMARY (16). Same arithmetic, same Philox streams, same summation order: images
+    (whole-pixel items) must be bit-identical to each other and to the oracle, ray / path counts equal — also when the
+    samples are rendered in several batches because the records do not fit the scratch budget, with T-then-S and step-wise
+    loops, with a lens and without, when every path ends at its first segment (max_bounces 1)."""
+    S = trt.scenes
+    cases = [S.cornell_spheres(96, 64, 12, 20), S.final_scene(80, 45, 9, 50), S.glass_cornell(64, 36, 10, 100), S.random_mixed(300, 7, 72, 40, 6, 12),
+             S.cornell(50, 30, 7, 1), S.five_spheres(64, 48, 5, 10)]
+    for desc in cases:
+        if kind == 2 and desc.n_prims > 64:
+            continue
+        osc, ocam, cam = both(trt, orc, desc)
+        sc = trt.Scene.from_desc(desc, kind)
+        _, op = params(trt, orc, desc)
+        olin, ou8, ost, _ = osc.render(ocam, op)
+        for regen in (0, 9):
+            out = {}
+            for name, flags, budget in (("auto", 2, None), ("pass", 2 | 32, None), ("inline", 2 | 16, None), ("batched", 2 | 32, "1"), ("tail_split", 32, "1")):
+                if budget is None: os.environ.pop("TRT_PRIMARY_BUDGET_MB", None)
+                else: os.environ["TRT_PRIMARY_BUDGET_MB"] = budget          # 1 MB of records: a few samples per batch
+                p, _ = params(trt, orc, desc, flags=flags | (regen << 8))
+                out[name] = sc.render(ctx, cam, p)
+            os.environ.pop("TRT_PRIMARY_BUDGET_MB", None)
+            for name, (lin, u8, st) in out.items():
+                assert (st.paths, st.rays) == (ost.paths, ost.rays), (desc.name, kind, regen, name, st.rays, ost.rays)
+                if name == "tail_split": assert ulp_diff(lin, olin).max() <= 1, (desc.name, kind, regen, name)
+                else: assert np.array_equal(bits(lin), bits(olin)), (desc.name, kind, regen, name, int((bits(lin) != bits(olin)).sum()))
+            w, h = desc.camera["width"], desc.camera["height"]
+            launches = {name: out[name][2].launches for name in out}
+            assert launches["pass"] == launches["inline"] + 1, (desc.name, kind, regen, launches)      # k_primary + path loop (+ tone map)
+            per_batch = (1 << 20) // (w * h * 32)
+            if per_batch < desc.spp:          # the 1 MB budget holds fewer samples than the frame has: several batches of two launches
+                assert launches["batched"] == 2 * -(-desc.spp // per_batch) + 1, (desc.name, kind, regen, launches)
+
+
+@pytest.mark.parametrize("kind", [1, 0])
+def test_step_functions_of_the_step_wise_loop_agree(trt, orc, ctx, kind):
+    """Round 2: the step-wise megakernel loop has three step functions for wide nodes in global memory (trt.h TRT_FLAG_STEP):
+    node + leaf + pop in one step (1), one dependent fetch per step (2), and the latter with the top stack entry in registers
+    (3). Same tests on the same records in the same per-lane order: images must be bit-identical to each other and to the
+    oracle. 70 000 spheres keep the tree out of shared memory (kind 1 = SAH -> ordered walk with replay, kind 0 = the
+    reference topology on wide nodes); a mixed scene covers quads; regen 9 forces the step-wise loop on small trees too
+    (those stay in shared memory and must ignore the request)."""
+    S = trt.scenes
+    cases = [S.random_spheres(70000, 96, 54, 3, 50), S.random_mixed(300, 7, 72, 40, 6, 12), S.final_scene(80, 45, 4, 50)]
+    for desc in cases:
+        osc, ocam, cam = both(trt, orc, desc)
+        sc = trt.Scene.from_desc(desc, kind)
+        _, op = params(trt, orc, desc)
+        olin, ou8, ost, _ = osc.render(ocam, op)
+        for step in (1, 2, 3):
+            for regen in (0, 9, 20):
+                p, _ = params(trt, orc, desc, flags=2 | (regen << 8) | trt._lib.flag_step(step))
+                lin, u8, st = sc.render(ctx, cam, p)
+                assert (st.paths, st.rays) == (ost.paths, ost.rays), (desc.name, kind, step, regen, st.rays, ost.rays)
+                assert np.array_equal(bits(lin), bits(olin)), (desc.name, kind, step, regen, int((bits(lin) != bits(olin)).sum()))

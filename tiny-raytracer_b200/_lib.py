@@ -14,6 +14,13 @@ FLAG_COUNT_EVENTS = 1
 FLAG_NO_TAIL_SPLIT = 2
 FLAG_BINARY_NODES = 4
 FLAG_COUNT_WALKED = 8
+FLAG_INLINE_PRIMARY = 16
+FLAG_PRIMARY_PASS = 32
+
+
+def flag_step(n):
+    """Step function of the step-wise loop on wide nodes in global memory (trt.h TRT_FLAG_STEP)."""
+    return (n & 3) << 16
 
 
 class TrtError(RuntimeError):

@@ -42,6 +42,7 @@ struct trt_ctx {
     unsigned int* d_next_item = nullptr;
     // scratch reused across calls (grown on demand)
     void* scratch[4] = {nullptr, nullptr, nullptr, nullptr}; size_t scratch_bytes[4] = {0, 0, 0, 0};
+    void* d_prim = nullptr; size_t prim_bytes = 0;   // records of the coherent first-bounce pass (one sample batch)
     char name[256];
 };
 
@@ -91,6 +92,7 @@ int trt_ctx_destroy(trt_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 4; ++i) if (c->scratch[i]) cudaFree(c->scratch[i]);
+    if (c->d_prim) cudaFree(c->d_prim);
     if (c->d_counters) cudaFree(c->d_counters);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -342,8 +344,44 @@ static int render_into(trt_ctx* c, trt_scene* s, const trt_camera* cam, const tr
         return TRT_OK;
     }
     CU(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long) + 64, c->stream));
+    // The coherent first-bounce pass (k_primary) hands the path loop one 32-byte record per path through HBM. Samples are
+    // rendered in batches whose records fit the scratch budget (TRT_PRIMARY_BUDGET_MB, default 16 GB, at most half of the
+    // free memory); every batch is one k_primary + one megakernel launch over its sample range. A pixel's f64 sum is continued
+    // from batch to batch in sample order (trt_kernels.cu fetch_items), so batching does not change a single bit.
+    // It is used where it was measured to pay (trtk::primary_pass_pays: wide-node trees staged in shared memory, final scene
+    // +7 %; the flat list and the trees in L2 lose 1-14 % with it and keep inline primary rays) or when TRT_FLAG_PRIMARY_PASS asks.
+    const bool want_prim = p->spp > 0 && p->max_bounces > 0 && !(p->flags & (TRT_FLAG_COUNT_EVENTS | TRT_FLAG_COUNT_WALKED | TRT_FLAG_INLINE_PRIMARY)) &&
+                           ((p->flags & TRT_FLAG_PRIMARY_PASS) || trtk::primary_pass_pays(v, *p));
+    uint32_t batch = p->spp; void* d_prim = nullptr;
+    if (want_prim) {
+        size_t budget = (size_t)16384 << 20;
+        if (const char* e = std::getenv("TRT_PRIMARY_BUDGET_MB")) { long long mb = std::atoll(e); if (mb >= 0) budget = (size_t)mb << 20; }
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = std::min(budget, std::max(c->prim_bytes, free_b / 2 + c->prim_bytes / 2));
+        const size_t per_sample = trtk::primary_record_bytes(*p);
+        size_t k = per_sample ? budget / per_sample : 0;
+        if (k >= 1) {
+            batch = (uint32_t)std::min<size_t>(k, p->spp);
+            const size_t need = per_sample * batch;
+            if (c->prim_bytes < need) {
+                if (c->d_prim) { cudaFree(c->d_prim); c->d_prim = nullptr; c->prim_bytes = 0; }
+                if (cudaMalloc(&c->d_prim, need) == cudaSuccess) c->prim_bytes = need;
+                else { cudaGetLastError(); c->d_prim = nullptr; }            // no room: render with inline primary rays instead
+            }
+            d_prim = c->d_prim;
+        }
+        if (!d_prim) batch = p->spp;
+    }
+    uint32_t launches = 0;
     CU(cudaEventRecord(c->ev[0], c->stream));
-    CU(trtk::launch_render_mega(v, *cam, *p, d_sum64, c->d_counters, c->d_next_item, c->sm_count, c->stream));
+    for (uint32_t off = 0; off < p->spp || (off == 0 && p->spp == 0); off += batch) {
+        trt_params q = *p;
+        q.spp = std::min(batch, p->spp - off); q.sample_offset = p->sample_offset + off;
+        if (off) CU(cudaMemsetAsync(c->d_next_item, 0, sizeof(unsigned int), c->stream));
+        CU(trtk::launch_render_mega(v, *cam, q, d_sum64, c->d_counters, c->d_next_item, c->sm_count, c->stream, d_prim));
+        launches += d_prim ? 2u : 1u;
+        if (p->spp == 0) break;
+    }
     CU(cudaEventRecord(c->ev[1], c->stream));
     if (stats) {
         unsigned long long h[8];
@@ -351,7 +389,7 @@ static int render_into(trt_ctx* c, trt_scene* s, const trt_camera* cam, const tr
         CU(cudaStreamSynchronize(c->stream));
         float ms = 0.f; CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
         stats->rays = h[0]; stats->paths = h[1]; stats->node_visits = h[2]; stats->sphere_tests = h[3]; stats->quad_tests = h[4];
-        stats->device_ms = ms; stats->launches = 1; stats->finalize_ms = 0.f; stats->reserved = 0;
+        stats->device_ms = ms; stats->launches = launches; stats->finalize_ms = 0.f; stats->reserved = 0;
     }
     return TRT_OK;
 }

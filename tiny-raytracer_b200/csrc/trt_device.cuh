@@ -162,6 +162,18 @@ template <bool SMEM> TRT_DEV uint4 ld4u(const uint4* p) {
     } else return __ldg(p);
 }
 
+// Two consecutive float4 of a 32-byte-aligned record in ONE 256-bit load (LDG.E.256, new with sm_100). A lane whose record lies
+// in its own cache line costs the L1 data pipe one wavefront per SECTOR it touches per instruction (10^6 spheres:
+// l1tex__data_pipe_lsu_wavefronts 92 % of peak, one per 16-byte lane access, profiles/r2d_tree_c4_64spp): fetching a wide node
+// as 3 x 32 B + 16 B instead of 7 x 16 B takes the same bytes through 4 instead of 7 of them.
+struct F4x2 { float4 a, b; };
+TRT_DEV F4x2 ldg256(const float4* p) {
+    F4x2 v;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w) : "l"(p));
+    return v;
+}
+
 struct EventCounters { uint32_t node_visits, sphere_tests, quad_tests; };
 
 // ------------------------------------------------------------------ packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2)
@@ -248,8 +260,7 @@ TRT_DEV float rcp_approx(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"
 //      division is skipped, root 2 is computed as usual.
 //  (3) root 1 >= hi: root 2 >= root 1 (same positive divisor, larger numerator, correctly rounded division is monotone) -> miss.
 //  A NaN anywhere fails the comparisons of (1) and (2) and takes the literal path.
-template <bool SMEM> TRT_DEV bool sphere_hit(const DevScene& S, uint32_t idx, V3 o, V3 d, float t_min, float hi, float* t_out) {
-    float4 s = ld4<SMEM>(S.spheres + idx);
+TRT_DEV bool sphere_hit_rec(const float4 s, V3 o, V3 d, float t_min, float hi, float* t_out) {     // s = (centre, radius), already fetched
     V3 oc = o - mk(s.x, s.y, s.z);
     float a = dot(d, d);
     float half_b = dot(oc, d);
@@ -269,11 +280,13 @@ template <bool SMEM> TRT_DEV bool sphere_hit(const DevScene& S, uint32_t idx, V3
     if (!(t_min <= t && t < hi)) return false;
     *t_out = t; return true;
 }
+template <bool SMEM> TRT_DEV bool sphere_hit(const DevScene& S, uint32_t idx, V3 o, V3 d, float t_min, float hi, float* t_out) {
+    return sphere_hit_rec(ld4<SMEM>(S.spheres + idx), o, d, t_min, hi, t_out);
+}
 // Quad::hit, hittable/quad.rs:33-41
 // `hi` is the range end of the reference's `contains`; `hi_cut` (>= any t the caller could still accept) only feeds the pre-reject.
-template <bool SMEM> TRT_DEV bool quad_hit(const DevScene& S, uint32_t idx, V3 o, V3 d, float t_min, float hi, float hi_cut, float* t_out) {
-    const float4* q = S.quads + 4 * (size_t)idx;
-    float4 q0 = ld4<SMEM>(q);
+// q0 = the quad's first float4 (n, D), already fetched; the other three are read only when the plane is hit inside the range
+template <bool SMEM> TRT_DEV bool quad_hit_rec(const float4* q, const float4 q0, V3 o, V3 d, float t_min, float hi, float hi_cut, float* t_out) {
     V3 n = mk(q0.x, q0.y, q0.z);
     float dir_norm = dot(d, n);
     float num = q0.w - dot(o, n);
@@ -291,6 +304,10 @@ template <bool SMEM> TRT_DEV bool quad_hit(const DevScene& S, uint32_t idx, V3 o
     float py = dot(cross(mk(q2.x, q2.y, q2.z), p), w);
     if (!(0.0f <= px && px < 1.0f && 0.0f <= py && py < 1.0f)) return false;
     *t_out = t; return true;
+}
+template <bool SMEM> TRT_DEV bool quad_hit(const DevScene& S, uint32_t idx, V3 o, V3 d, float t_min, float hi, float hi_cut, float* t_out) {
+    const float4* q = S.quads + 4 * (size_t)idx;
+    return quad_hit_rec<SMEM>(q, ld4<SMEM>(q), o, d, t_min, hi, hi_cut, t_out);
 }
 
 // ------------------------------------------------------------------ closest hit = BVH::hit / Node::hit, hittable/bvh.rs:25-27,88-107
@@ -451,7 +468,20 @@ TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounter
 // Either way only the number of dependent node fetches per ray changes (about half of the binary walk).
 // COUNT (TRT_FLAG_COUNT_WALKED): ec->node_visits counts the wide records fetched (7 x 16 B each), sphere_tests / quad_tests the
 // primitive tests — the traffic of THIS walk, for the memory roofline of big scenes (bench.py); results are unaffected.
-template <bool ORDERED, bool SMEM, bool COUNT = false>
+#ifndef TRT_NODE_V256
+#define TRT_NODE_V256 true     /* wide nodes in global memory are fetched with 256-bit loads (see ldg256) */
+#endif
+template <bool SMEM, bool V256>
+TRT_DEV void load_wide_node(const float4* np, float4& a0, float4& a1, float4& a2, float4& b0, float4& b1, float4& b2, float4& rf) {
+    if (!SMEM && V256) {
+        const F4x2 p0 = ldg256(np), p1 = ldg256(np + 2), p2 = ldg256(np + 4);
+        a0 = p0.a; a1 = p0.b; a2 = p1.a; b0 = p1.b; b1 = p2.a; b2 = p2.b; rf = __ldg(np + 6);
+    } else {
+        a0 = ld4<SMEM>(np); a1 = ld4<SMEM>(np + 1); a2 = ld4<SMEM>(np + 2);
+        b0 = ld4<SMEM>(np + 3); b1 = ld4<SMEM>(np + 4); b2 = ld4<SMEM>(np + 5); rf = ld4<SMEM>(np + 6);
+    }
+}
+template <bool ORDERED, bool SMEM, bool COUNT = false, bool V256 = TRT_NODE_V256>
 TRT_DEV void trav4_step(Trav& T, const DevScene& S, float t_min, TravStack& K, EventCounters* ec = nullptr) {   // t_min: the caller's (uniform) value, not a per-lane copy
     uint32_t cur = T.cur;
     const V3 o = T.o, d = T.d, inv = T.inv;
@@ -459,8 +489,8 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, float t_min, TravStack& K, E
         TRT_ASSERT(cur < S.n_nodes4);
         if (COUNT) ec->node_visits += 1;
         const float4* np = S.nodes4 + (size_t)(SMEM ? TRT_WIDE_SMEM_F4 : 8) * cur;
-        const float4 a0 = ld4<SMEM>(np), a1 = ld4<SMEM>(np + 1), a2 = ld4<SMEM>(np + 2);
-        const float4 b0 = ld4<SMEM>(np + 3), b1 = ld4<SMEM>(np + 4), b2 = ld4<SMEM>(np + 5), rf = ld4<SMEM>(np + 6);
+        float4 a0, a1, a2, b0, b1, b2, rf;
+        load_wide_node<SMEM, V256>(np, a0, a1, a2, b0, b1, b2, rf);
         float s0, e0, s1, e1, s2, e2, s3, e3;
         if (T.tame) {
             slab2_tame(a0, a1, a2, o, inv, t_min, &s0, &e0, &s1, &e1);
@@ -527,13 +557,102 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, float t_min, TravStack& K, E
 // One step of the wide walk, or — for a lane that is replaying its ray (needs_replay) — of the reference-order walk on the
 // reference tree's wide nodes in global memory. Sharing the loop and the stack keeps the rare replay out of the hot path's
 // register budget.
-template <bool ORDERED, bool SMEM, bool COUNT = false>
+template <bool ORDERED, bool SMEM, bool COUNT = false, bool V256 = TRT_NODE_V256>
 TRT_DEV void trav4_any_step(Trav& T, const DevScene& S, float t_min, TravStack& K, EventCounters* ec = nullptr) {
     if (ORDERED && T.replay) {
         DevScene R = S;
         R.nodes4 = S.nodes_ref4; R.n_nodes4 = S.n_nodes_ref4; R.spheres = S.g_spheres; R.quads = S.g_quads;
-        trav4_step<false, false, COUNT>(T, R, t_min, K, ec);
-    } else trav4_step<ORDERED, SMEM, COUNT>(T, S, t_min, K, ec);
+        trav4_step<false, false, COUNT, V256>(T, R, t_min, K, ec);
+    } else trav4_step<ORDERED, SMEM, COUNT, V256>(T, S, t_min, K, ec);
+}
+// ------------------------------------------------------------------ the same walk, ONE dependent fetch per step (round 2; trees in global memory)
+// trav4_step runs region A, then region B for the lanes whose child just turned out to be a leaf, then the pop: a step is a
+// chain of up to three dependent fetches (node record, primitive record of the leaf that node selected, stack entry). Here a
+// lane is a node OR a leaf for the whole step, decided by the ref it holds when the step begins, and the first 32 bytes of
+// either record are fetched through ONE per-lane address before any of the two regions runs; a leaf selected in region A is
+// tested in the NEXT step, while the other lanes fetch their next node: one L2 round trip per step instead of up to two, at the
+// price of one more step per leaf test. Same tests on the same records in the same per-lane order as trav4_step: results
+// are bit-identical. Measured on 10^6 spheres: +-0 while the L1 data pipe was the limiter (see ldg256); kept as
+// TRT_FLAG_STEP(3) for A/B.
+template <bool ORDERED, bool COUNT>
+TRT_DEV void trav4_step_pipe(Trav& T, const DevScene& S, float t_min, TravStack& K, EventCounters* ec = nullptr) {
+    uint32_t cur = T.cur;                                   // never TRT_REF_INVALID here
+    const V3 o = T.o, d = T.d, inv = T.inv;
+    const bool leaf = (cur & TRT_REF_LEAF) != 0u;
+    const uint32_t idx = cur & TRT_REF_INDEX_MASK;
+    // spheres are 16-byte records: the aligned PAIR that holds sphere idx is fetched (every scene array is padded to 256 bytes)
+    const float4* p0 = !leaf ? S.nodes4 + 8 * (size_t)cur : ((cur & TRT_REF_QUAD) ? S.quads + 4 * (size_t)idx : S.spheres + (idx & ~1u));
+    const F4x2 f0 = ldg256(p0);                             // issued for node and leaf lanes alike, before either region runs
+    if (!leaf) {
+        TRT_ASSERT(cur < S.n_nodes4);
+        if (COUNT) ec->node_visits += 1;
+        const F4x2 f1 = ldg256(p0 + 2), f2 = ldg256(p0 + 4);
+        const float4 a0 = f0.a, a1 = f0.b, a2 = f1.a, b0 = f1.b, b1 = f2.a, b2 = f2.b, rf = __ldg(p0 + 6);
+        float s0, e0, s1, e1, s2, e2, s3, e3;
+        if (T.tame) {
+            slab2_tame(a0, a1, a2, o, inv, t_min, &s0, &e0, &s1, &e1);
+            slab2_tame(b0, b1, b2, o, inv, t_min, &s2, &e2, &s3, &e3);
+        } else {
+            slab(a0.x, a0.z, a1.x, a1.z, a2.x, a2.z, o, inv, t_min, &s0, &e0);
+            slab(a0.y, a0.w, a1.y, a1.w, a2.y, a2.w, o, inv, t_min, &s1, &e1);
+            slab(b0.x, b0.z, b1.x, b1.z, b2.x, b2.z, o, inv, t_min, &s2, &e2);
+            slab(b0.y, b0.w, b1.y, b1.w, b2.y, b2.w, o, inv, t_min, &s3, &e3);
+        }
+        uint32_t r0 = __float_as_uint(rf.x), r1 = __float_as_uint(rf.y), r2 = __float_as_uint(rf.z), r3 = __float_as_uint(rf.w);
+        const float best = ORDERED ? cull_limit(T.best.t) : T.best.t;
+        TRT_ASSERT(T.sp + 3 <= TRT_MAX_STACK);
+        if (ORDERED) {
+            if (!(e0 > s0 && !(best < s0) && r0 != TRT_REF_INVALID)) { s0 = TRT_INF; r0 = TRT_REF_INVALID; }
+            if (!(e1 > s1 && !(best < s1) && r1 != TRT_REF_INVALID)) { s1 = TRT_INF; r1 = TRT_REF_INVALID; }
+            if (!(e2 > s2 && !(best < s2) && r2 != TRT_REF_INVALID)) { s2 = TRT_INF; r2 = TRT_REF_INVALID; }
+            if (!(e3 > s3 && !(best < s3) && r3 != TRT_REF_INVALID)) { s3 = TRT_INF; r3 = TRT_REF_INVALID; }
+#define TRT_CSWAP(sa, ra, sb, rb) { const bool w_ = sb < sa; const float ts_ = w_ ? sb : sa, tb_ = w_ ? sa : sb; \
+                                    const uint32_t tr_ = w_ ? rb : ra, tq_ = w_ ? ra : rb; sa = ts_; sb = tb_; ra = tr_; rb = tq_; }
+            TRT_CSWAP(s0, r0, s1, r1) TRT_CSWAP(s2, r2, s3, r3) TRT_CSWAP(s0, r0, s2, r2) TRT_CSWAP(s1, r1, s3, r3) TRT_CSWAP(s1, r1, s2, r2)
+#undef TRT_CSWAP
+            if (r3 != TRT_REF_INVALID) { K.put(T.sp, r3, s3); ++T.sp; }
+            if (r2 != TRT_REF_INVALID) { K.put(T.sp, r2, s2); ++T.sp; }
+            if (r1 != TRT_REF_INVALID) { K.put(T.sp, r1, s1); ++T.sp; }
+            cur = r0; T.cur_s = s0;
+        } else {
+            if (e3 > s3 && r3 != TRT_REF_INVALID) { K.put(T.sp, r3, s3); ++T.sp; }
+            if (e2 > s2 && r2 != TRT_REF_INVALID) { K.put(T.sp, r2, s2); ++T.sp; }
+            if (e1 > s1 && r1 != TRT_REF_INVALID) { K.put(T.sp, r1, s1); ++T.sp; }
+            cur = (e0 > s0 && best > s0) ? r0 : TRT_REF_INVALID;
+        }
+    } else {
+        TRT_ASSERT(idx < ((cur & TRT_REF_QUAD) ? S.n_quads : S.n_spheres));
+        float t; bool h;
+        if (COUNT) { if (cur & TRT_REF_QUAD) ec->quad_tests += 1; else ec->sphere_tests += 1; }
+        if (cur & TRT_REF_QUAD) h = quad_hit_rec<false>(p0, f0.a, o, d, t_min, ORDERED ? TRT_INF : T.best.t, T.best.t, &t);      // (n, D)
+        else h = sphere_hit_rec((idx & 1u) ? f0.b : f0.a, o, d, t_min, ORDERED ? TRT_INF : T.best.t, &t);                        // (centre, r)
+        if (h) {
+            if (!ORDERED) { T.best.t = t; T.best.ref = cur; }
+            else if (t < T.best.t) { T.best.t = t; T.best.ref = cur; T.best_anom = T.cur_s > t; }
+            else if (t == T.best.t) {      // exact tie: the lower reference leaf rank wins
+                const uint32_t rb = (T.best.ref & TRT_REF_QUAD) ? ld4ua(S.quad_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y
+                                                                : ld4ua(S.sphere_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y;
+                const uint32_t rk = (cur & TRT_REF_QUAD) ? ld4ua(S.quad_meta + idx).y : ld4ua(S.sphere_meta + idx).y;
+                if (rk < rb) { T.best.ref = cur; T.best_anom = T.cur_s > t; }
+            }
+        }
+        cur = TRT_REF_INVALID;
+    }
+    while (cur == TRT_REF_INVALID && T.sp > 0) {
+        --T.sp;
+        uint32_t r; float s;
+        K.get(T.sp, &r, &s);
+        if (ORDERED ? !(cull_limit(T.best.t) < s) : (T.best.t > s)) { cur = r; if (ORDERED) T.cur_s = s; }
+    }
+    T.cur = cur;
+}
+template <bool ORDERED, bool COUNT>
+TRT_DEV void trav4_any_step_pipe(Trav& T, const DevScene& S, float t_min, TravStack& K, EventCounters* ec = nullptr) {
+    if (ORDERED && T.replay) {          // the rare replay keeps the plain step
+        DevScene R = S;
+        R.nodes4 = S.nodes_ref4; R.n_nodes4 = S.n_nodes_ref4; R.spheres = S.g_spheres; R.quads = S.g_quads;
+        trav4_step<false, false, COUNT, true>(T, R, t_min, K, ec);
+    } else trav4_step_pipe<ORDERED, COUNT>(T, S, t_min, K, ec);
 }
 // restart the ray of a finished ordered walk in replay mode
 TRT_DEV void begin_replay(Trav& T, const DevScene& S) {
@@ -585,30 +704,41 @@ TRT_DEV void primary_ray(const DevCamera& C, const DevParams& P, uint32_t x, uin
 // ------------------------------------------------------------------ one hit: HitRecord::new (hittable/mod.rs:27-48) + emitted/scatter (material/*.rs)
 struct Surface { V3 point, normal; bool front; uint32_t kind; V3 rgb; float param; };
 
+// The hit record in two halves, so that the megakernel can decide "emit and stop / scatter" from the material alone and
+// compute the geometric half once, for the lanes that really scatter:
+//   hit_material  material id -> (kind, rgb, param): what Material::emitted / scatter need to know (material/*.rs)
+//   hit_geometry  HitRecord::new (hittable/mod.rs:27-48): point = at(t), front_face, unit normal against the ray
+template <bool SMEM>
+TRT_DEV void hit_material(const DevScene& S, Hit h, Surface* sf) {
+    const uint32_t idx = h.ref & TRT_REF_INDEX_MASK;
+    const uint32_t mat = (h.ref & TRT_REF_QUAD) ? ld4ua(S.quad_meta + idx).x : ld4ua(S.sphere_meta + idx).x;
+    const float4 m0 = ld4a(S.materials + 2 * (size_t)mat);
+    sf->kind = __float_as_uint(m0.w);
+    sf->rgb = mk(m0.x, m0.y, m0.z);
+    sf->param = (sf->kind == TRT_MAT_METAL || sf->kind == TRT_MAT_DIELECTRIC) ? ld4a(S.materials + 2 * (size_t)mat + 1).x : 0.0f;
+}
+template <bool SMEM>
+TRT_DEV void hit_geometry(const DevScene& S, Hit h, V3 o, V3 d, Surface* sf) {
+    const uint32_t idx = h.ref & TRT_REF_INDEX_MASK;
+    sf->point = ray_at(o, d, h.t);
+    V3 outward, nn;
+    if (h.ref & TRT_REF_QUAD) {
+        const float4 q0 = ld4<SMEM>(S.quads + 4 * (size_t)idx);
+        outward = mk(q0.x, q0.y, q0.z);                                       // quad.rs:45: the unnormalised n
+        const float4 q = ld4a(S.quad_nn + idx); nn = mk(q.x, q.y, q.z);       // n / |n| never changes: host-side, same ops
+    } else {
+        const float4 s = ld4<SMEM>(S.spheres + idx);
+        outward = sf->point - mk(s.x, s.y, s.z);                              // sphere.rs:46-50
+        nn = normalized(outward);
+    }
+    sf->front = dot(d, outward) < 0.0f;
+    sf->normal = sf->front ? nn : -nn;
+}
 template <bool SMEM>
 TRT_DEV Surface hit_record(const DevScene& S, Hit h, V3 o, V3 d) {
     Surface sf;
-    uint32_t idx = h.ref & TRT_REF_INDEX_MASK;
-    sf.point = ray_at(o, d, h.t);
-    V3 outward; uint32_t mat;
-    if (h.ref & TRT_REF_QUAD) {
-        float4 q0 = ld4<SMEM>(S.quads + 4 * (size_t)idx);
-        outward = mk(q0.x, q0.y, q0.z);                                       // quad.rs:45: the unnormalised n
-        mat = ld4ua(S.quad_meta + idx).x;
-    } else {
-        float4 s = ld4<SMEM>(S.spheres + idx);
-        outward = sf.point - mk(s.x, s.y, s.z);                               // sphere.rs:46-50
-        mat = ld4ua(S.sphere_meta + idx).x;
-    }
-    sf.front = dot(d, outward) < 0.0f;
-    V3 nn;
-    if (h.ref & TRT_REF_QUAD) { float4 q = ld4a(S.quad_nn + idx); nn = mk(q.x, q.y, q.z); }   // n / |n| never changes: host-side, same ops
-    else nn = normalized(outward);
-    sf.normal = sf.front ? nn : -nn;
-    float4 m0 = ld4a(S.materials + 2 * (size_t)mat);
-    sf.kind = __float_as_uint(m0.w);
-    sf.rgb = mk(m0.x, m0.y, m0.z);
-    sf.param = (sf.kind == TRT_MAT_METAL || sf.kind == TRT_MAT_DIELECTRIC) ? ld4a(S.materials + 2 * (size_t)mat + 1).x : 0.0f;
+    hit_geometry<SMEM>(S, h, o, d, &sf);
+    hit_material<SMEM>(S, h, &sf);
     return sf;
 }
 // Un-normalised scattered direction for the three scattering materials; `r` is Philox block 0 of (pixel, sample, k).

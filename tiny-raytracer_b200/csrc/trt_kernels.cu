@@ -42,7 +42,11 @@ struct MegaArgs {
                                    // the remaining tiles as n_chunks items of `chunk` samples each (f64 atomicAdd): small
                                    // items at the end of the job, so that lanes do not idle behind the last whole pixel
     uint32_t regen_min;            // lanes that must be waiting before the shade/regenerate block runs (32 = T-then-S)
+    const float4* prim_a; const float4* prim_b;   // PRIM kernels: the records of k_primary for this launch's samples, [spp][H*W]
 };
+#ifndef TRT_STEP_DEFAULT
+#define TRT_STEP_DEFAULT 2      /* measured on 10^6 spheres (B200): 1 -> 2 117, 2 -> 2 328, 3 -> 2 303 Mrays/s (device-built tree); 2 242 / 2 458 / 2 430 (SAH) */
+#endif
 struct FlatList { float4 cbox[TRT_FLAT_CBOX_F4]; };   // phase-A boxes of the flat list, read as kernel parameters (constant bank)
 
 // item -> (pixel, sample range). 32 consecutive items = one 8x4 pixel tile. `exclusive` = this lane alone adds to the pixel.
@@ -61,20 +65,133 @@ __device__ __forceinline__ bool decode_item(const MegaArgs& A, uint32_t item, ui
     return *x < A.p.width && *y < A.p.height;
 }
 
+// ------------------------------------------------------------------ the coherent first-bounce pass (round 2)
+// Primary rays are the one coherent population of a path tracer: the 32 lanes of a warp take the 32 pixels of an 8x4 tile at
+// the SAME sample index, so camera-ray generation runs with all lanes (inside the path loop it ran for the ~7 lanes that
+// happened to start a path in an iteration: 144 instructions at 5 lanes) and the closest-hit query sees nearly identical rays
+// (same candidates / same subtree for the whole warp). k_primary does pointgen.rs:37-52 + camera.rs:58-66 + the first
+// BVH::hit of cpu.rs:48 for a batch of samples of every pixel and leaves one 32-byte record per path in HBM:
+//     a = (origin.xyz, t)    b = (direction.xyz, hit ref bits)
+// A path that is already over after its first segment — a miss (background), a light (emission), or max_bounces <= 1 — is
+// stored as DONE with its final colour in a.xyz (computed with the path loop's own operations: 0 + 1 * c), so the path loop
+// only adds it up. The path loop (mega_body*, PRIM = true) starts every path from its record: no camera code, no first
+// traversal, and a whole-background warp consumes records at a few instructions per path. Same arithmetic, same Philox
+// streams, same summation order: results are bit-identical to the inline form (TRT_FLAG_INLINE_PRIMARY keeps that one).
+#define TRT_REF_DONE 0x7FFFFFFEu
+#define TRT_PRIM_BURST 8      /* DONE records a lane may consume per S pass (the other lanes of its warp wait meanwhile) */
+struct PrimArgs {
+    DevScene scene; DevCamera cam; DevParams p;
+    float4* a; float4* b;             // [spp_batch][H*W]
+    uint32_t tiles_x, tiles_y;
+    unsigned long long total;         // tiles * 32 * spp_batch (padding lanes of ragged tiles included)
+};
+template <int KIND, bool SMEM>
+__global__ void __launch_bounds__(256) k_primary(const __grid_constant__ PrimArgs A, const __grid_constant__ FlatList L) {
+    const DevScene S = stage_scene<SMEM, KIND>(A.scene);
+    const DevParams& P = A.p;
+    const unsigned long long per_sample = (unsigned long long)A.tiles_x * A.tiles_y * 32ull, npix = (unsigned long long)P.width * P.height;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < A.total; i += stride) {
+        const uint32_t s = (uint32_t)(i / per_sample);
+        const uint32_t r = (uint32_t)(i - (unsigned long long)s * per_sample), tile = r >> 5, ln = r & 31u;
+        const uint32_t ty = tile / A.tiles_x, tx = tile - ty * A.tiles_x, x = tx * 8 + (ln & 7u), y = ty * 4 + (ln >> 3);
+        if (x >= P.width || y >= P.height) continue;
+        const uint32_t pixel = y * P.width + x, sample = P.sample_offset + s;
+        V3 o, d;
+        primary_ray(A.cam, P, x, y, pixel, sample, &o, &d);
+        Hit h;
+        if (KIND == 2) h = closest_hit_flat<true>(L.cbox, S.flat_bound, S.flat, S.n_flat, S.flat_qmask[0], S.flat_qmask[1], o, d, P.t_min);
+        else h = closest_hit_any<KIND, SMEM, false>(S, o, d, P.t_min, nullptr);
+        float4 ra = make_float4(o.x, o.y, o.z, h.t), rb = make_float4(d.x, d.y, d.z, __uint_as_float(h.ref));
+        bool over = false; V3 c = mk(0.f, 0.f, 0.f);
+        if (h.ref == TRT_REF_INVALID) { over = true; c = mk(P.bg[0], P.bg[1], P.bg[2]); }                  // cpu.rs:58-61
+        else {
+            Surface sf; hit_material<SMEM>(S, h, &sf);
+            if (sf.kind == TRT_MAT_LIGHT) { over = true; c = sf.rgb; }                                      // cpu.rs:49-50, light.rs:17-19
+            else if (P.max_bounces <= 1) over = true;                                                       // the scatter would never be traced (cpu.rs:47,54)
+        }
+        if (over) {
+            const V3 col = mk(0.f, 0.f, 0.f) + mk(1.f, 1.f, 1.f) * c;                                       // colour + attenuation * c, as the path loop computes it
+            ra = make_float4(col.x, col.y, col.z, h.t); rb.w = __uint_as_float(TRT_REF_DONE);
+        }
+        const unsigned long long ri = (unsigned long long)s * npix + pixel;
+        __stcs(A.a + ri, ra); __stcs(A.b + ri, rb);
+    }
+}
+
+// Work fetch for lanes whose item is finished (warp-aggregated atomic). The f64 sums of a pixel owned by one lane are CONTINUED
+// from what the accumulation buffer already holds (acc = *dst at fetch, *dst = acc at the end), so that successive launches —
+// sample batches of one frame, progressive instalments — sum a pixel's samples in one sequential order, bit for bit as a single
+// launch would; a pixel shared by several lanes (tail chunks) adds its partial sums with f64 atomics.
+struct ItemState { uint32_t pixel, px, py, s_cur, s_end; double acc0, acc1, acc2; bool has_item, exclusive, done; };
+__device__ __forceinline__ void flush_item(const MegaArgs& A, ItemState& I) {
+    double* dst = A.sum64 + 3 * (size_t)I.pixel;
+    if (I.exclusive) { dst[0] = I.acc0; dst[1] = I.acc1; dst[2] = I.acc2; }
+    else { atomicAdd(dst, I.acc0); atomicAdd(dst + 1, I.acc1); atomicAdd(dst + 2, I.acc2); }
+    I.has_item = false;
+}
+__device__ __forceinline__ void fetch_items(const MegaArgs& A, ItemState& I, bool need_item, uint32_t lane, uint32_t* n_paths) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, need_item);
+    if (!m) return;
+    if (need_item && I.has_item) flush_item(A, I);
+    const int leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if ((int)lane == leader) base = atomicAdd(A.next_item, (unsigned)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (need_item) {
+        const uint32_t item = base + __popc(m & ((1u << lane) - 1u));
+        if (item < A.n_items) {
+            uint32_t s0, s1;
+            if (decode_item(A, item, &I.px, &I.py, &s0, &s1, &I.exclusive)) {
+                I.pixel = I.py * A.p.width + I.px; I.s_cur = s0; I.s_end = s1; I.has_item = true;
+                if (I.exclusive) { const double* src = A.sum64 + 3 * (size_t)I.pixel; I.acc0 = src[0]; I.acc1 = src[1]; I.acc2 = src[2]; }
+                else I.acc0 = I.acc1 = I.acc2 = 0.0;
+                if (A.p.max_bounces == 0) { *n_paths += s1 - s0; I.s_cur = s1; }      // no ray is ever cast (cpu.rs:47)
+            }   // else: padding item outside the image, fetch again next round
+        } else I.done = true;
+    }
+}
+// PRIM: a lane that starts a path takes its first segment from the primary pass. DONE records are added up on the spot (at
+// most TRT_PRIM_BURST per pass); the first live record gives (o, d, hit) and the lane goes on to shade it. Returns true if so.
+__device__ __forceinline__ bool take_primary(const MegaArgs& A, ItemState& I, V3* o, V3* d, Hit* h, uint32_t* n_rays, uint32_t* n_paths) {
+    const size_t npix = (size_t)A.p.width * A.p.height;
+#pragma unroll 1
+    for (int it = 0; it < TRT_PRIM_BURST && I.s_cur < I.s_end; ++it) {
+        const size_t ri = (size_t)I.s_cur * npix + I.pixel;
+        const float4 ra = __ldcs(A.prim_a + ri), rb = __ldcs(A.prim_b + ri);
+        ++*n_rays;
+        const uint32_t ref = __float_as_uint(rb.w);
+        if (ref != TRT_REF_DONE) { *o = mk(ra.x, ra.y, ra.z); *d = mk(rb.x, rb.y, rb.z); h->t = ra.w; h->ref = ref; return true; }
+        I.acc0 += (double)ra.x; I.acc1 += (double)ra.y; I.acc2 += (double)ra.z;          // imager.rs:50, in sample order
+        ++I.s_cur; ++*n_paths;
+    }
+    return false;
+}
+__device__ __forceinline__ void mega_stats(const MegaArgs& A, uint32_t lane, uint32_t n_rays, uint32_t n_paths, const EventCounters& ec, bool count) {
+    unsigned long long r = n_rays, pth = n_paths;
+    for (int off = 16; off; off >>= 1) { r += __shfl_xor_sync(0xFFFFFFFFu, r, off); pth += __shfl_xor_sync(0xFFFFFFFFu, pth, off); }
+    if (lane == 0) { atomicAdd(A.counters, r); atomicAdd(A.counters + 1, pth); }
+    if (count) {
+        unsigned long long a = ec.node_visits, b = ec.sphere_tests, c = ec.quad_tests;
+        for (int off = 16; off; off >>= 1) { a += __shfl_xor_sync(0xFFFFFFFFu, a, off); b += __shfl_xor_sync(0xFFFFFFFFu, b, off); c += __shfl_xor_sync(0xFFFFFFFFu, c, off); }
+        if (lane == 0) { atomicAdd(A.counters + 2, a); atomicAdd(A.counters + 3, b); atomicAdd(A.counters + 4, c); }
+    }
+}
+
 // Loop body = T (one ray segment for every live lane) then S (shade-or-regenerate, fused so that the scattering lanes
 // and the lanes starting a new path share ONE Philox call, ONE normalisation and the work-fetch point; every lane that
 // still has work leaves S with a live ray, so T always runs with full lanes until the work counter runs dry).
 // KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH, 2 = TRT_BVH_FLAT (U = the phase-A boxes in the constant bank),
-// 3 / 4 = TRT_BVH_SAH / TRT_BVH_REFERENCE walked on their 4-wide nodes.
-template <int KIND, bool SMEM, bool COUNT>
+// 3 / 4 = TRT_BVH_SAH / TRT_BVH_REFERENCE walked on their 4-wide nodes. PRIM: paths start from the records of k_primary.
+template <int KIND, bool SMEM, bool COUNT, bool PRIM>
 __device__ __forceinline__ void mega_body(const MegaArgs& A, const float4* U) {
     const DevScene S = stage_scene<SMEM, KIND>(A.scene);
     const DevParams& P = A.p;
     const uint32_t lane = threadIdx.x & 31u;
     V3 o = mk(0, 0, 0), d = mk(0, 0, 1), atten = mk(1, 1, 1), color = mk(0, 0, 0);
-    uint32_t pixel = 0, px = 0, py = 0, s_cur = 0, s_end = 0, remain = 0, k = 0;
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-    bool alive = false, done = false, has_item = false, exclusive = true;
+    uint32_t remain = 0, k = 0;
+    ItemState I; I.pixel = I.px = I.py = I.s_cur = I.s_end = 0; I.acc0 = I.acc1 = I.acc2 = 0.0; I.has_item = false; I.exclusive = true; I.done = false;
+    bool alive = false;
     uint32_t n_rays = 0, n_paths = 0;
     EventCounters ec; ec.node_visits = ec.sphere_tests = ec.quad_tests = 0;
 
@@ -87,77 +204,60 @@ __device__ __forceinline__ void mega_body(const MegaArgs& A, const float4* U) {
             else h = closest_hit<KIND == 1, SMEM, COUNT>(S, o, d, P.t_min, &ec);
             ++n_rays;
         }
-        // ---- S1: cpu.rs:49-61 up to the scatter decision
+        // ---- S1: cpu.rs:49-61 up to the scatter decision: the material alone says "emit and stop" or "scatter"
         Surface sf; sf.kind = TRT_MAT_LIGHT; sf.front = false; sf.param = 0.f;
         sf.point = sf.normal = sf.rgb = mk(0, 0, 0);
         bool scatter = false;
         if (alive) {
             if (h.ref == TRT_REF_INVALID) color = color + atten * mk(P.bg[0], P.bg[1], P.bg[2]);
             else {
-                sf = hit_record<SMEM>(S, h, o, d);
+                hit_material<SMEM>(S, h, &sf);
                 V3 emission = (sf.kind == TRT_MAT_LIGHT) ? sf.rgb : mk(0.0f, 0.0f, 0.0f);
                 color = color + atten * emission;
                 // a scattered ray is only traced while bounces remain (cpu.rs:47,54): the last scatter is never used
                 scatter = sf.kind != TRT_MAT_LIGHT && remain > 1;
             }
             if (!scatter) {       // imager.rs:50 (f64 here)
-                acc0 += (double)color.x; acc1 += (double)color.y; acc2 += (double)color.z;
-                alive = false; ++s_cur; ++n_paths;
+                I.acc0 += (double)color.x; I.acc1 += (double)color.y; I.acc2 += (double)color.z;
+                alive = false; ++I.s_cur; ++n_paths;
             }
         }
-        // ---- S2: work fetch for lanes whose chunk is finished (warp-aggregated atomic)
-        bool need_item = !alive && !done && s_cur == s_end;
-        unsigned m = __ballot_sync(0xFFFFFFFFu, need_item);
-        if (m) {
-            if (need_item && has_item) {
-                double* dst = A.sum64 + 3 * (size_t)pixel;
-                if (exclusive) { dst[0] += acc0; dst[1] += acc1; dst[2] += acc2; }   // pixel owned by this lane alone
-                else { atomicAdd(dst, acc0); atomicAdd(dst + 1, acc1); atomicAdd(dst + 2, acc2); }
-                has_item = false;
-            }
-            int leader = __ffs(m) - 1;
-            unsigned base = 0;
-            if ((int)lane == leader) base = atomicAdd(A.next_item, (unsigned)__popc(m));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (need_item) {
-                uint32_t item = base + __popc(m & ((1u << lane) - 1u));
-                if (item < A.n_items) {
-                    uint32_t s0, s1;
-                    if (decode_item(A, item, &px, &py, &s0, &s1, &exclusive)) {
-                        pixel = py * P.width + px; s_cur = s0; s_end = s1; has_item = true;
-                        acc0 = acc1 = acc2 = 0.0;
-                        if (P.max_bounces == 0) { n_paths += s1 - s0; s_cur = s1; }      // no ray is ever cast (cpu.rs:47)
-                    }   // else: padding item outside the image, fetch again next round
-                } else done = true;
-            }
-        }
+        // ---- S2: work fetch for lanes whose chunk is finished
+        fetch_items(A, I, !alive && !I.done && I.s_cur == I.s_end, lane, &n_paths);
         // ---- S3: the next ray of every lane that scatters (material/*.rs) or starts a new path (pointgen.rs:37-52)
-        bool regen = !alive && !done && s_cur < s_end;
-        if (scatter || regen) {
-            uint32_t sample = P.sample_offset + s_cur;
-            if (scatter) ++k; else k = 0;
-            U4 r = philox4x32_10(pixel, sample, k, 0u, P.seed_lo, P.seed_hi);
-            V3 dir;
-            if (scatter) {
-                dir = scatter_direction(sf, d, r);
-                atten = atten * sf.rgb; o = sf.point; --remain;                           // cpu.rs:52-54
-            } else {
-                camera_ray(A.cam, P, px, py, pixel, sample, r, &o, &dir);
-                atten = mk(1, 1, 1); color = mk(0, 0, 0); remain = P.max_bounces; alive = true;
+        const bool regen = !alive && !I.done && I.s_cur < I.s_end;
+        if (PRIM) {
+            bool fresh = false;
+            if (regen) fresh = take_primary(A, I, &o, &d, &h, &n_rays, &n_paths);
+            if (fresh) { hit_material<SMEM>(S, h, &sf); atten = mk(1, 1, 1); color = mk(0, 0, 0); remain = P.max_bounces; k = 0; alive = true; }
+            if (scatter || fresh) {
+                hit_geometry<SMEM>(S, h, o, d, &sf);
+                ++k;
+                U4 r = philox4x32_10(I.pixel, P.sample_offset + I.s_cur, k, 0u, P.seed_lo, P.seed_hi);
+                V3 dir = scatter_direction(sf, d, r);
+                atten = atten * sf.rgb; o = sf.point; --remain;                               // cpu.rs:52-54
+                d = normalized(dir);                                                         // Ray::new, ray.rs:12-14
             }
-            d = normalized(dir);                                                         // Ray::new, ray.rs:12-14
+        } else {
+            if (scatter) hit_geometry<SMEM>(S, h, o, d, &sf);
+            if (scatter || regen) {
+                uint32_t sample = P.sample_offset + I.s_cur;
+                if (scatter) ++k; else k = 0;
+                U4 r = philox4x32_10(I.pixel, sample, k, 0u, P.seed_lo, P.seed_hi);
+                V3 dir;
+                if (scatter) {
+                    dir = scatter_direction(sf, d, r);
+                    atten = atten * sf.rgb; o = sf.point; --remain;                           // cpu.rs:52-54
+                } else {
+                    camera_ray(A.cam, P, I.px, I.py, I.pixel, sample, r, &o, &dir);
+                    atten = mk(1, 1, 1); color = mk(0, 0, 0); remain = P.max_bounces; alive = true;
+                }
+                d = normalized(dir);                                                         // Ray::new, ray.rs:12-14
+            }
         }
-        if (__all_sync(0xFFFFFFFFu, done)) break;
+        if (__all_sync(0xFFFFFFFFu, I.done)) break;
     }
-    // ---- statistics: one atomic per warp
-    unsigned long long r = n_rays, pth = n_paths;
-    for (int off = 16; off; off >>= 1) { r += __shfl_xor_sync(0xFFFFFFFFu, r, off); pth += __shfl_xor_sync(0xFFFFFFFFu, pth, off); }
-    if (lane == 0) { atomicAdd(A.counters, r); atomicAdd(A.counters + 1, pth); }
-    if (COUNT) {
-        unsigned long long a = ec.node_visits, b = ec.sphere_tests, c = ec.quad_tests;
-        for (int off = 16; off; off >>= 1) { a += __shfl_xor_sync(0xFFFFFFFFu, a, off); b += __shfl_xor_sync(0xFFFFFFFFu, b, off); c += __shfl_xor_sync(0xFFFFFFFFu, c, off); }
-        if (lane == 0) { atomicAdd(A.counters + 2, a); atomicAdd(A.counters + 3, b); atomicAdd(A.counters + 4, c); }
-    }
+    mega_stats(A, lane, n_rays, n_paths, ec, COUNT);
 }
 
 // The tree kinds use this form of the same loop: the traversal is advanced ONE step (trav_step) per iteration, and the
@@ -166,7 +266,9 @@ __device__ __forceinline__ void mega_body(const MegaArgs& A, const float4* U) {
 // which pays when a ray costs many steps (1 M spheres: ~50 node steps per ray and 7.7 of 32 lanes active under the
 // T-then-S schedule, profiles/r1g) and costs when S (≈ 800 instructions) would run for a handful of lanes on a
 // 7-step Cornell ray. The launcher picks regen_min from the tree size; trt_params.flags bits 8..15 override it.
-template <int KIND, bool SMEM, bool COUNT>
+// STEP (wide nodes in global memory): 1 = trav4_step with 128-bit node loads (round 1), 2 = trav4_step with 256-bit node loads,
+// 3 = trav4_step_pipe (one dependent fetch per step, 256-bit node loads). Elsewhere STEP is 1 and means trav4_step / trav_step.
+template <int KIND, bool SMEM, bool COUNT, bool PRIM, int STEP>
 __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
     const DevScene S = stage_scene<SMEM, KIND>(A.scene);
     const DevParams& P = A.p;
@@ -175,9 +277,9 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
     T.o = mk(0, 0, 0); T.d = mk(0, 0, 1); T.inv = mk(0, 0, 1); T.t_min = P.t_min; T.tame = false;
     TravStack K;
     V3 atten = mk(1, 1, 1), color = mk(0, 0, 0);
-    uint32_t pixel = 0, px = 0, py = 0, s_cur = 0, s_end = 0, remain = 0, k = 0;
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-    bool alive = false, done = false, has_item = false, exclusive = true;     // alive: the lane carries a path; T.cur != INVALID: its ray is still being traced
+    uint32_t remain = 0, k = 0;
+    ItemState I; I.pixel = I.px = I.py = I.s_cur = I.s_end = 0; I.acc0 = I.acc1 = I.acc2 = 0.0; I.has_item = false; I.exclusive = true; I.done = false;
+    bool alive = false;      // alive: the lane carries a path; T.cur != INVALID: its ray is still being traced
     uint32_t n_rays = 0, n_paths = 0;
     EventCounters ec; ec.node_visits = ec.sphere_tests = ec.quad_tests = 0;
     const int regen_min = (int)A.regen_min;
@@ -186,90 +288,76 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
         // ---- T: one step of cpu.rs:48 for every lane whose ray is in flight
         if (T.cur != TRT_REF_INVALID) {
             if (KIND == 3 || KIND == 4) {
-                trav4_any_step<KIND == 3, SMEM, COUNT>(T, S, P.t_min, K, &ec);
+                if (STEP == 3 && !SMEM) trav4_any_step_pipe<KIND == 3, COUNT>(T, S, P.t_min, K, &ec);
+                else trav4_any_step<KIND == 3, SMEM, COUNT, STEP == 2>(T, S, P.t_min, K, &ec);
                 if (KIND == 3 && T.cur == TRT_REF_INVALID && needs_replay(T, S)) begin_replay(T, S);     // rare: DESIGN.md §4.3
             }
             else trav_step<KIND == 1, SMEM, COUNT>(T, S, K, &ec);
         }
         const bool tracing = T.cur != TRT_REF_INVALID;
         const unsigned tm = __ballot_sync(0xFFFFFFFFu, tracing);
-        const unsigned wm = __ballot_sync(0xFFFFFFFFu, !tracing && !done);
+        const unsigned wm = __ballot_sync(0xFFFFFFFFu, !tracing && !I.done);
         if (tm != 0u && __popc(wm) < regen_min) continue;
         // ---- S1: cpu.rs:49-61 up to the scatter decision, for the lanes whose ray just finished
-        const bool in_s = !tracing && !done;
+        const bool in_s = !tracing && !I.done;
         Surface sf; sf.kind = TRT_MAT_LIGHT; sf.front = false; sf.param = 0.f;
         sf.point = sf.normal = sf.rgb = mk(0, 0, 0);
         bool scatter = false;
+        Hit h = T.best; V3 ro = T.o, rd = T.d;
         if (in_s && alive) {
-            Hit h = T.best;
             if (KIND == 1 && needs_replay(T, S)) h = ordered_replay(S, T.o, T.d, P.t_min);   // rare: DESIGN.md §4.3 (binary walk)
             if (h.ref == TRT_REF_INVALID) color = color + atten * mk(P.bg[0], P.bg[1], P.bg[2]);
             else {
-                sf = hit_record<SMEM>(S, h, T.o, T.d);
+                hit_material<SMEM>(S, h, &sf);
                 V3 emission = (sf.kind == TRT_MAT_LIGHT) ? sf.rgb : mk(0.0f, 0.0f, 0.0f);
                 color = color + atten * emission;
                 scatter = sf.kind != TRT_MAT_LIGHT && remain > 1;
             }
             if (!scatter) {       // imager.rs:50 (f64 here)
-                acc0 += (double)color.x; acc1 += (double)color.y; acc2 += (double)color.z;
-                alive = false; ++s_cur; ++n_paths;
+                I.acc0 += (double)color.x; I.acc1 += (double)color.y; I.acc2 += (double)color.z;
+                alive = false; ++I.s_cur; ++n_paths;
             }
         }
-        // ---- S2: work fetch for lanes whose chunk is finished (warp-aggregated atomic)
-        bool need_item = in_s && !alive && s_cur == s_end;
-        unsigned m = __ballot_sync(0xFFFFFFFFu, need_item);
-        if (m) {
-            if (need_item && has_item) {
-                double* dst = A.sum64 + 3 * (size_t)pixel;
-                if (exclusive) { dst[0] += acc0; dst[1] += acc1; dst[2] += acc2; }
-                else { atomicAdd(dst, acc0); atomicAdd(dst + 1, acc1); atomicAdd(dst + 2, acc2); }
-                has_item = false;
-            }
-            int leader = __ffs(m) - 1;
-            unsigned base = 0;
-            if ((int)lane == leader) base = atomicAdd(A.next_item, (unsigned)__popc(m));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (need_item) {
-                uint32_t item = base + __popc(m & ((1u << lane) - 1u));
-                if (item < A.n_items) {
-                    uint32_t s0, s1;
-                    if (decode_item(A, item, &px, &py, &s0, &s1, &exclusive)) {
-                        pixel = py * P.width + px; s_cur = s0; s_end = s1; has_item = true;
-                        acc0 = acc1 = acc2 = 0.0;
-                        if (P.max_bounces == 0) { n_paths += s1 - s0; s_cur = s1; }
-                    }
-                } else done = true;
-            }
-        }
+        // ---- S2: work fetch for lanes whose chunk is finished
+        fetch_items(A, I, in_s && !alive && I.s_cur == I.s_end, lane, &n_paths);
         // ---- S3: next ray of the lanes that scatter or start a new path; its traversal state is set up here
-        bool regen = in_s && !alive && !done && s_cur < s_end;
-        if (scatter || regen) {
-            uint32_t sample = P.sample_offset + s_cur;
-            if (scatter) ++k; else k = 0;
-            U4 r = philox4x32_10(pixel, sample, k, 0u, P.seed_lo, P.seed_hi);
-            V3 o, dir;
-            if (scatter) {
-                dir = scatter_direction(sf, T.d, r);
-                atten = atten * sf.rgb; o = sf.point; --remain;
-            } else {
-                camera_ray(A.cam, P, px, py, pixel, sample, r, &o, &dir);
-                atten = mk(1, 1, 1); color = mk(0, 0, 0); remain = P.max_bounces; alive = true;
+        const bool regen = in_s && !alive && !I.done && I.s_cur < I.s_end;
+        if (PRIM) {
+            bool fresh = false;
+            if (regen) fresh = take_primary(A, I, &ro, &rd, &h, &n_rays, &n_paths);
+            if (fresh) { hit_material<SMEM>(S, h, &sf); atten = mk(1, 1, 1); color = mk(0, 0, 0); remain = P.max_bounces; k = 0; alive = true; }
+            if (scatter || fresh) {
+                hit_geometry<SMEM>(S, h, ro, rd, &sf);
+                ++k;
+                U4 r = philox4x32_10(I.pixel, P.sample_offset + I.s_cur, k, 0u, P.seed_lo, P.seed_hi);
+                V3 dir = scatter_direction(sf, rd, r);
+                atten = atten * sf.rgb; --remain;
+                trav_begin<COUNT && (KIND < 3)>(T, S, sf.point, normalized(dir), P.t_min, &ec);
+                ++n_rays;
             }
-            trav_begin<COUNT && (KIND < 3)>(T, S, o, normalized(dir), P.t_min, &ec);      // Ray::new normalises, ray.rs:12-14 (root-box event only for the binary counts)
-            ++n_rays;
-            // an empty scene (or, when counting, a ray that misses the root box) is finished at once: T.cur stays INVALID
-            // and the lane re-enters S on the next pass with T.best = miss.
+        } else {
+            if (scatter) hit_geometry<SMEM>(S, h, ro, rd, &sf);
+            if (scatter || regen) {
+                uint32_t sample = P.sample_offset + I.s_cur;
+                if (scatter) ++k; else k = 0;
+                U4 r = philox4x32_10(I.pixel, sample, k, 0u, P.seed_lo, P.seed_hi);
+                V3 o, dir;
+                if (scatter) {
+                    dir = scatter_direction(sf, rd, r);
+                    atten = atten * sf.rgb; o = sf.point; --remain;
+                } else {
+                    camera_ray(A.cam, P, I.px, I.py, I.pixel, sample, r, &o, &dir);
+                    atten = mk(1, 1, 1); color = mk(0, 0, 0); remain = P.max_bounces; alive = true;
+                }
+                trav_begin<COUNT && (KIND < 3)>(T, S, o, normalized(dir), P.t_min, &ec);      // Ray::new normalises, ray.rs:12-14 (root-box event only for the binary counts)
+                ++n_rays;
+                // an empty scene (or, when counting, a ray that misses the root box) is finished at once: T.cur stays INVALID
+                // and the lane re-enters S on the next pass with T.best = miss.
+            }
         }
-        if (__all_sync(0xFFFFFFFFu, done)) break;
+        if (__all_sync(0xFFFFFFFFu, I.done)) break;
     }
-    unsigned long long r = n_rays, pth = n_paths;
-    for (int off = 16; off; off >>= 1) { r += __shfl_xor_sync(0xFFFFFFFFu, r, off); pth += __shfl_xor_sync(0xFFFFFFFFu, pth, off); }
-    if (lane == 0) { atomicAdd(A.counters, r); atomicAdd(A.counters + 1, pth); }
-    if (COUNT) {
-        unsigned long long a = ec.node_visits, b = ec.sphere_tests, c = ec.quad_tests;
-        for (int off = 16; off; off >>= 1) { a += __shfl_xor_sync(0xFFFFFFFFu, a, off); b += __shfl_xor_sync(0xFFFFFFFFu, b, off); c += __shfl_xor_sync(0xFFFFFFFFu, c, off); }
-        if (lane == 0) { atomicAdd(A.counters + 2, a); atomicAdd(A.counters + 3, b); atomicAdd(A.counters + 4, c); }
-    }
+    mega_stats(A, lane, n_rays, n_paths, ec, COUNT);
 }
 
 // MODE: 0 = T-then-S (small trees), 1 = step-wise (big trees). Separate kernels, so that each loop gets its own register
@@ -278,13 +366,14 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
 // traces its second path while the hit of the first waits for the S block: correct (bit-identical sums, in sample order), but
 // 10^6 spheres 1 666 vs 2 128 Mrays/s and the final scene 4 209 vs 7 710 — the 35 KB of shared memory per CTA it needs cost
 // L1 capacity (10^6 spheres) or a whole CTA of occupancy (final scene), and the ray-swap block runs at low lane counts.
-template <int KIND, bool SMEM, bool COUNT, int MODE>
+template <int KIND, bool SMEM, bool COUNT, int MODE, bool PRIM>
 __global__ void __launch_bounds__(MEGA_THREADS, TRT_MEGA_MIN_BLOCKS) k_render_mega(const __grid_constant__ MegaArgs A) {
-    if (MODE == 0) mega_body<KIND, SMEM, COUNT>(A, nullptr);
-    else mega_body_async<KIND, SMEM, COUNT>(A);
+    if (MODE == 0) mega_body<KIND, SMEM, COUNT, PRIM>(A, nullptr);
+    else mega_body_async<KIND, SMEM, COUNT, PRIM, MODE>(A);
 }
+template <bool PRIM>
 __global__ void __launch_bounds__(TRT_FLAT_THREADS, TRT_FLAT_MIN_BLOCKS) k_render_mega_flat(const __grid_constant__ MegaArgs A, const __grid_constant__ FlatList L) {
-    mega_body<2, true, false>(A, L.cbox);
+    mega_body<2, true, false, PRIM>(A, L.cbox);
 }
 
 // ------------------------------------------------------------------ AOV / sample batch / trace
@@ -381,9 +470,9 @@ size_t scene_smem_bytes(const SceneView& v, uint32_t kind) {
     return 16ull * (nodes + v.n_spheres + 4ull * v.n_quads + (size_t)TRT_FLAT_F4 * v.n_flat + aux);
 }
 
-template <int KIND, bool SMEM, bool COUNT, int MODE>
-static cudaError_t mega_fn3(const void** fn, int* blocks_per_sm, size_t smem) {
-    auto kern = k_render_mega<KIND, SMEM, COUNT, MODE>;
+template <int KIND, bool SMEM, bool COUNT, int MODE, bool PRIM>
+static cudaError_t mega_fn4(const void** fn, int* blocks_per_sm, size_t smem) {
+    auto kern = k_render_mega<KIND, SMEM, COUNT, MODE, PRIM>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -393,16 +482,58 @@ static cudaError_t mega_fn3(const void** fn, int* blocks_per_sm, size_t smem) {
     *fn = (const void*)kern;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, MEGA_THREADS, smem);
 }
+// mode: 0 T-then-S, 1 step-wise, 2 / 3 step-wise with the other step functions (wide nodes in global memory, no event counting: else 1);
+// prim: paths start from k_primary's records (never together with event counting)
 template <int KIND, bool SMEM, bool COUNT>
-static cudaError_t mega_fn(int mode, const void** fn, int* blocks_per_sm, size_t smem) {
-    return mode == 1 ? mega_fn3<KIND, SMEM, COUNT, 1>(fn, blocks_per_sm, smem) : mega_fn3<KIND, SMEM, COUNT, 0>(fn, blocks_per_sm, smem);
+static cudaError_t mega_fn(int mode, bool prim, const void** fn, int* blocks_per_sm, size_t smem) {
+    if constexpr ((KIND == 3 || KIND == 4) && !SMEM && !COUNT) {
+        if (mode == 2) return prim ? mega_fn4<KIND, false, false, 2, true>(fn, blocks_per_sm, smem) : mega_fn4<KIND, false, false, 2, false>(fn, blocks_per_sm, smem);
+        if (mode == 3) return prim ? mega_fn4<KIND, false, false, 3, true>(fn, blocks_per_sm, smem) : mega_fn4<KIND, false, false, 3, false>(fn, blocks_per_sm, smem);
+    }
+    if (mode > 1) mode = 1;
+    if (prim && !COUNT) return mode == 1 ? mega_fn4<KIND, SMEM, false, 1, true>(fn, blocks_per_sm, smem) : mega_fn4<KIND, SMEM, false, 0, true>(fn, blocks_per_sm, smem);
+    return mode == 1 ? mega_fn4<KIND, SMEM, COUNT, 1, false>(fn, blocks_per_sm, smem) : mega_fn4<KIND, SMEM, COUNT, 0, false>(fn, blocks_per_sm, smem);
+}
+
+template <int KIND, bool SMEM>
+static cudaError_t primary_launch(const PrimArgs& A, const FlatList& L, size_t smem, int sm_count, cudaStream_t st) {
+    auto kern = k_primary<KIND, SMEM>;
+    cudaError_t e;
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    int bps = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, 256, smem)) != cudaSuccess) return e;
+    if (bps < 1) bps = 1;
+    unsigned long long want = (A.total + 255) / 256, cap = (unsigned long long)sm_count * bps * 8;     // a few waves of persistent CTAs
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    kern<<<grid ? grid : 1, 256, smem, st>>>(A, L);
+    return cudaGetLastError();
+}
+
+size_t primary_record_bytes(const trt_params& p) { return (size_t)p.width * p.height * 32ull; }    // per sample of the batch
+// Measured on B200 (64-spp probes, profiles/r2f_*): final scene (486 wide nodes in shared memory, T-then-S) 7 917 -> 8 476 Mrays/s
+// with the pass; Cornell flat list 22 299 -> 19 254, glass Cornell 13 007 -> 12 432, 10^6 spheres (L2, step-wise) 2 119 -> 2 089:
+// there a primary ray is just one more ray of the warp's pool and the records' HBM round trip costs more than it saves.
+bool primary_pass_pays(const SceneView& v, const trt_params& p) {
+    if (v.kind == 2) return false;
+    const uint32_t kind = walk_kind(v, (p.flags & TRT_FLAG_BINARY_NODES) != 0);
+    if (kind != 3 && kind != 4) return false;
+    if (scene_smem_bytes(v, kind) > 64 * 1024) return false;
+    const uint32_t regen = (p.flags >> 8) & 0xFFu;
+    return regen == 0 ? v.n_nodes <= 4096 : regen >= 32u;             // the T-then-S loop
 }
 
 cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const trt_params& p, double* d_sum64,
-                               unsigned long long* d_counters, unsigned int* d_next_item, int sm_count, cudaStream_t st) {
+                               unsigned long long* d_counters, unsigned int* d_next_item, int sm_count, cudaStream_t st,
+                               void* d_primary) {
     MegaArgs A;
     A.scene = dev_scene(v); A.cam = dev_camera(cam); A.p = dev_params(p);
     A.sum64 = d_sum64; A.counters = d_counters; A.next_item = d_next_item;
+    // d_primary: room for primary_record_bytes(p) * p.spp -> the coherent first-bounce pass runs first and the path loop starts
+    // from its records (never when events are counted or no ray is cast at all)
+    const bool prim = d_primary != nullptr && p.spp > 0 && p.max_bounces > 0 && !(p.flags & (1u | TRT_FLAG_COUNT_WALKED | TRT_FLAG_INLINE_PRIMARY));
+    const size_t npix = (size_t)p.width * p.height;
+    A.prim_a = prim ? (const float4*)d_primary : nullptr;
+    A.prim_b = prim ? (const float4*)d_primary + npix * p.spp : nullptr;
     // shade/regenerate threshold: trees of a few dozen nodes cost ~7 steps per ray and S is ~800 instructions, so S must run
     // for the whole warp; big trees cost ~50 steps per ray and waiting for the slowest of 32 rays wastes 3/4 of the lanes.
     uint32_t regen = (p.flags >> 8) & 0xFFu;
@@ -420,24 +551,26 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     bool use_smem = smem <= 64 * 1024;
     if (v.kind == 2 && (!use_smem || v.n_flat > TRT_FLAT_MAX || !v.flat_cbox_host)) return cudaErrorInvalidValue;
     if (!use_smem) smem = 0;
-    const int mega_mode = A.regen_min >= 32u ? 0 : 1;
+    // step-wise loop: which step function (flags bits 16..17: 0 = chosen here, 1 = 128-bit node loads, 2 = 256-bit, 3 = 256-bit and one fetch per step)
+    const uint32_t step_req = (p.flags >> 16) & 3u;
+    const int mega_mode = A.regen_min >= 32u ? 0 : (step_req ? (int)step_req : TRT_STEP_DEFAULT);
     const void* fn = nullptr; int blocks_per_sm = 0; cudaError_t e;
     if (v.kind == 2) {
-        if (smem > 48 * 1024) { e = cudaFuncSetAttribute(k_render_mega_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
-        fn = (const void*)k_render_mega_flat;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_render_mega_flat, TRT_FLAT_THREADS, smem);
+        fn = prim ? (const void*)k_render_mega_flat<true> : (const void*)k_render_mega_flat<false>;
+        if (smem > 48 * 1024) { e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, TRT_FLAT_THREADS, smem);
     } else if (kind == 3) {
-        if (count) e = use_smem ? mega_fn<3, true, true>(mega_mode, &fn, &blocks_per_sm, smem) : mega_fn<3, false, true>(mega_mode, &fn, &blocks_per_sm, smem);
-        else e = use_smem ? mega_fn<3, true, false>(mega_mode, &fn, &blocks_per_sm, smem) : mega_fn<3, false, false>(mega_mode, &fn, &blocks_per_sm, smem);
+        if (count) e = use_smem ? mega_fn<3, true, true>(mega_mode, prim, &fn, &blocks_per_sm, smem) : mega_fn<3, false, true>(mega_mode, prim, &fn, &blocks_per_sm, smem);
+        else e = use_smem ? mega_fn<3, true, false>(mega_mode, prim, &fn, &blocks_per_sm, smem) : mega_fn<3, false, false>(mega_mode, prim, &fn, &blocks_per_sm, smem);
     } else if (kind == 4) {
-        if (count) e = use_smem ? mega_fn<4, true, true>(mega_mode, &fn, &blocks_per_sm, smem) : mega_fn<4, false, true>(mega_mode, &fn, &blocks_per_sm, smem);
-        else e = use_smem ? mega_fn<4, true, false>(mega_mode, &fn, &blocks_per_sm, smem) : mega_fn<4, false, false>(mega_mode, &fn, &blocks_per_sm, smem);
+        if (count) e = use_smem ? mega_fn<4, true, true>(mega_mode, prim, &fn, &blocks_per_sm, smem) : mega_fn<4, false, true>(mega_mode, prim, &fn, &blocks_per_sm, smem);
+        else e = use_smem ? mega_fn<4, true, false>(mega_mode, prim, &fn, &blocks_per_sm, smem) : mega_fn<4, false, false>(mega_mode, prim, &fn, &blocks_per_sm, smem);
     } else if (v.kind == 1) {
-        if (use_smem) e = count ? mega_fn<1, true, true>(mega_mode, &fn, &blocks_per_sm, smem) : mega_fn<1, true, false>(mega_mode, &fn, &blocks_per_sm, smem);
-        else e = count ? mega_fn<1, false, true>(mega_mode, &fn, &blocks_per_sm, smem) : mega_fn<1, false, false>(mega_mode, &fn, &blocks_per_sm, smem);
+        if (use_smem) e = count ? mega_fn<1, true, true>(mega_mode, prim, &fn, &blocks_per_sm, smem) : mega_fn<1, true, false>(mega_mode, prim, &fn, &blocks_per_sm, smem);
+        else e = count ? mega_fn<1, false, true>(mega_mode, prim, &fn, &blocks_per_sm, smem) : mega_fn<1, false, false>(mega_mode, prim, &fn, &blocks_per_sm, smem);
     } else {
-        if (use_smem) e = count ? mega_fn<0, true, true>(mega_mode, &fn, &blocks_per_sm, smem) : mega_fn<0, true, false>(mega_mode, &fn, &blocks_per_sm, smem);
-        else e = count ? mega_fn<0, false, true>(mega_mode, &fn, &blocks_per_sm, smem) : mega_fn<0, false, false>(mega_mode, &fn, &blocks_per_sm, smem);
+        if (use_smem) e = count ? mega_fn<0, true, true>(mega_mode, prim, &fn, &blocks_per_sm, smem) : mega_fn<0, true, false>(mega_mode, prim, &fn, &blocks_per_sm, smem);
+        else e = count ? mega_fn<0, false, true>(mega_mode, prim, &fn, &blocks_per_sm, smem) : mega_fn<0, false, false>(mega_mode, prim, &fn, &blocks_per_sm, smem);
     }
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) blocks_per_sm = 1;
@@ -468,9 +601,20 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     if (p.spp == 0) n_items = 0;
     if (n_items > 0xFFFFFFF0ull - resident) return cudaErrorInvalidValue;
     A.n_items = (uint32_t)n_items;
+    FlatList L;
+    if (v.kind == 2) memcpy(&L, v.flat_cbox_host, sizeof L); else memset(&L, 0, sizeof L);
+    if (prim) {
+        PrimArgs PA;
+        PA.scene = A.scene; PA.cam = A.cam; PA.p = A.p; PA.a = (float4*)d_primary; PA.b = (float4*)d_primary + npix * p.spp;
+        PA.tiles_x = A.tiles_x; PA.tiles_y = A.tiles_y; PA.total = n_tiles * 32ull * p.spp;
+        if (v.kind == 2) e = primary_launch<2, true>(PA, L, smem, sm_count, st);
+        else if (kind == 3) e = use_smem ? primary_launch<3, true>(PA, L, smem, sm_count, st) : primary_launch<3, false>(PA, L, smem, sm_count, st);
+        else if (kind == 4) e = use_smem ? primary_launch<4, true>(PA, L, smem, sm_count, st) : primary_launch<4, false>(PA, L, smem, sm_count, st);
+        else if (v.kind == 1) e = use_smem ? primary_launch<1, true>(PA, L, smem, sm_count, st) : primary_launch<1, false>(PA, L, smem, sm_count, st);
+        else e = use_smem ? primary_launch<0, true>(PA, L, smem, sm_count, st) : primary_launch<0, false>(PA, L, smem, sm_count, st);
+        if (e != cudaSuccess) return e;
+    }
     if (v.kind == 2) {
-        FlatList L;
-        memcpy(&L, v.flat_cbox_host, sizeof L);
         void* args[] = {(void*)&A, (void*)&L};
         return cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, st);
     }

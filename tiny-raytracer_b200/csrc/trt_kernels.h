@@ -29,8 +29,13 @@ struct SceneView {   // device copy of trt::FlatScene
 uint32_t walk_kind(const SceneView& v, bool binary_only);
 size_t scene_smem_bytes(const SceneView& v, uint32_t kind);
 
+// d_primary: null, or primary_record_bytes(p) * p.spp bytes of scratch: the coherent first-bounce pass (k_primary) then runs
+// before the path loop, which starts every path from its record. Same results either way.
+size_t primary_record_bytes(const trt_params& p);
+bool primary_pass_pays(const SceneView& v, const trt_params& p);     // the configurations where the pass was measured to be faster
 cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const trt_params& p, double* d_sum64,
-                               unsigned long long* d_counters, unsigned int* d_next_item, int sm_count, cudaStream_t st);
+                               unsigned long long* d_counters, unsigned int* d_next_item, int sm_count, cudaStream_t st,
+                               void* d_primary);
 size_t lbvh_tmp_bytes(uint32_t n);
 // Builds the 64-byte node array (n - 1 nodes) and, if d_nodes4 is not null, its 4-wide form (128 bytes per node) on the device from per-primitive padded boxes (2 float4 each, leaf-ref bits in bmin.w).
 cudaError_t build_lbvh(const void* d_boxes, uint32_t n, void* d_nodes, void* d_nodes4, void* d_tmp, uint32_t* h_depth, float* h_ms, cudaStream_t st);
