@@ -84,6 +84,9 @@ typedef struct trt_params {
 /* bits 16..17 of flags: step function of the step-wise megakernel loop on wide nodes in global memory (0 = chosen by the library,
  * 1 = 128-bit node loads, 2 = 256-bit node loads, 3 = 256-bit loads and one dependent fetch per step). Same results; A/B. */
 #define TRT_FLAG_STEP(n) (((n) & 3u) << 16)
+#define TRT_FLAG_NO_WIDE8 0x40000u  /* megakernel: walk the 4-wide nodes also where the scene has compressed 8-wide ones (built only when
+                                    * TRT_WIDE8=1 is in the environment at trt_scene_upload, for ordered trees that do not fit shared
+                                    * memory; DESIGN.md §4.5: measured slower on B200). Same results bit for bit; A/B and tests. */
 #define TRT_FLAG_BINARY_NODES 4u   /* tree kinds: walk the binary nodes instead of the 4-wide ones (same results; A/B and tests) */
 /* bits 8..15 of flags: megakernel tuning override, the number of lanes of a warp (1..32) that must have finished their ray
  * before the shade/regenerate block runs; 0 = chosen from the tree size (32 up to 4096 nodes, 16 above). Results do not

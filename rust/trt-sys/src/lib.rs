@@ -22,6 +22,7 @@ pub const TRT_FLAG_BINARY_NODES: u32 = 4;
 pub const TRT_FLAG_COUNT_WALKED: u32 = 8;
 pub const TRT_FLAG_INLINE_PRIMARY: u32 = 16;
 pub const TRT_FLAG_PRIMARY_PASS: u32 = 32;
+pub const TRT_FLAG_NO_WIDE8: u32 = 0x40000;
 pub const fn trt_flag_step(n: u32) -> u32 { (n & 3) << 16 }
 pub const fn trt_flag_regen_min(n: u32) -> u32 { (n & 0xFF) << 8 }
 

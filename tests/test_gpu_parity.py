@@ -974,3 +974,59 @@ def test_step_functions_of_the_step_wise_loop_agree(trt, orc, ctx, kind):
                 lin, u8, st = sc.render(ctx, cam, p)
                 assert (st.paths, st.rays) == (ost.paths, ost.rays), (desc.name, kind, step, regen, st.rays, ost.rays)
                 assert np.array_equal(bits(lin), bits(olin)), (desc.name, kind, step, regen, int((bits(lin) != bits(olin)).sum()))
+
+
+@pytest.mark.parametrize("kind", [1, 3])
+def test_compressed_wide8_walk_is_bit_identical_to_the_wide4_walk(trt, orc, ctx, kind):
+    """Round 2: ordered trees that do not fit shared memory can be walked on compressed 8-wide nodes (TRT_WIDE8=1 at upload; quantised
+    child boxes that only cull; a leaf's own box is rebuilt / fetched and tested exactly). TRT_FLAG_NO_WIDE8 keeps the 4-wide walk.
+    Images must be bit-identical to each other and to the oracle, ray counts equal, for the host SAH tree (kind 1; >= 65 536
+    primitives: wide records made on the device) and TRT_BVH_AUTO (kind 3; device-built tree from 65 536 primitives), on spheres
+    and on a mixed scene with quads, with the step-wise and the T-then-S loop; and the walk must really be the 8-wide one
+    (TRT_FLAG_COUNT_WALKED: fewer node records per ray than the 4-wide walk)."""
+    S = trt.scenes
+    cases = [S.random_spheres(70_000, 96, 54, 3, 50), S.random_mixed(3000, 17, 72, 40, 4, 12), S.random_mixed(70_000, 23, 64, 36, 2, 20)]
+    os.environ["TRT_WIDE8"] = "1"          # opt-in, read when the scene is uploaded (measured slower than the 4-wide walk on B200)
+    try:
+        scenes = []
+        for desc in cases:
+            sc = trt.Scene.from_desc(desc, kind)
+            sc.upload(ctx)
+            scenes.append(sc)
+    finally:
+        os.environ.pop("TRT_WIDE8", None)
+    for desc, sc in zip(cases, scenes):
+        osc, ocam, cam = both(trt, orc, desc)
+        _, op = params(trt, orc, desc)
+        olin, ou8, ost, _ = osc.render(ocam, op)
+        for regen in (0, 9):
+            out = {}
+            for name, flags in (("wide8", 2), ("wide4", 2 | trt._lib.FLAG_NO_WIDE8)):
+                p, _ = params(trt, orc, desc, flags=flags | (regen << 8))
+                out[name] = sc.render(ctx, cam, p)
+            for name, (lin, u8, st) in out.items():
+                assert (st.paths, st.rays) == (ost.paths, ost.rays), (desc.name, kind, regen, name, st.rays, ost.rays)
+                assert np.array_equal(bits(lin), bits(olin)), (desc.name, kind, regen, name, int((bits(lin) != bits(olin)).sum()))
+        walked = {}
+        for name, flags in (("wide8", 2 | 8), ("wide4", 2 | 8 | trt._lib.FLAG_NO_WIDE8)):
+            p, _ = params(trt, orc, desc, flags=flags | (9 << 8))
+            lin, u8, st = sc.render(ctx, cam, p)
+            assert np.array_equal(bits(lin), bits(olin)), (desc.name, kind, name)
+            walked[name] = st.node_visits / max(st.rays, 1)
+        assert 0 < walked["wide8"] < 0.9 * walked["wide4"], (desc.name, kind, walked)
+        # arbitrary and degenerate rays through trt_trace_rays (one thread per ray, the same wide-8 walk): exact zeros, negative
+        # zeros and axis-aligned directions cannot take the quantised-box test and must fall back to the reference-order walk;
+        # t_min = 0 and a negative t_min as well
+        rng = np.random.default_rng(11)
+        n = 60_000
+        lo = np.maximum(desc.prim_data[:, :3].min(0) - 3, -120); hi = np.minimum(desc.prim_data[:, :3].max(0) + 3, 120)
+        o = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+        d = rng.normal(size=(n, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+        d[:2000, 0] = 0.0; d[2000:4000, 1] = -0.0; d[4000:5000] = np.float32([0, 0, 1]); d[5000:6000] = np.float32([0, -1, 0])
+        o[6000:8000] = np.round(o[6000:8000])
+        osc_t = orc.Scene.from_desc(desc)
+        for t_min in (0.001, 0.0, -1.0):
+            prim, t = sc.trace_rays(ctx, o, d, t_min)
+            oprim, ot = osc_t.trace_rays(o, d, t_min, use_bvh=True)
+            assert np.array_equal(prim, oprim), (desc.name, kind, t_min, int((prim != oprim).sum()))
+            assert np.array_equal(bits(t), bits(ot)), (desc.name, kind, t_min)

@@ -16,6 +16,7 @@ FLAG_BINARY_NODES = 4
 FLAG_COUNT_WALKED = 8
 FLAG_INLINE_PRIMARY = 16
 FLAG_PRIMARY_PASS = 32
+FLAG_NO_WIDE8 = 0x40000
 
 
 def flag_step(n):

@@ -28,6 +28,7 @@ static int fail_cuda(const char* what, cudaError_t e) {
 
 struct DeviceCopy {
     uint64_t version = 0; void* buf = nullptr; size_t bytes = 0; trtk::SceneView view{}; uint32_t root_ref4 = 0; bool wide_ok = false;
+    void* buf8 = nullptr; size_t bytes8 = 0;      // compressed 8-wide nodes + quad boxes (scenes whose wide nodes do not fit shared memory)
 };
 struct trt_scene {
     trt::HostScene host;
@@ -122,7 +123,7 @@ int trt_scene_create(trt_scene** out) {
 }
 int trt_scene_destroy(trt_scene* s) {
     if (!s) return TRT_OK;
-    for (auto& kv : s->on_device) if (kv.second.buf) { cudaSetDevice(kv.first); cudaFree(kv.second.buf); }
+    for (auto& kv : s->on_device) if (kv.second.buf) { cudaSetDevice(kv.first); cudaFree(kv.second.buf); if (kv.second.buf8) cudaFree(kv.second.buf8); }
     delete s; return TRT_OK;
 }
 static int add_mat(trt_scene* s, uint32_t kind, const float rgb[3], float param, uint32_t* id, const char* who) {
@@ -278,6 +279,37 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
     for (int i = 0; i < 3; ++i) { v.root_min[i] = inf; v.root_max[i] = -inf; }
     for (const trt::HostPrim& p : s->host.prims)
         for (int i = 0; i < 3; ++i) { v.root_min[i] = fminf(v.root_min[i], p.bmin[i]); v.root_max[i] = fmaxf(v.root_max[i], p.bmax[i]); }
+    // Compressed 8-wide nodes (trt_lbvh.cu k_cw8_level) for ordered trees that are walked in global memory: built on
+    // the device from the binary records that are there anyway (uploaded SAH tree or device-built tree). OPT-IN (TRT_WIDE8=1 in the
+    // environment when the scene is uploaded): bit-identical results, a third fewer node fetches and 43 % fewer L1 sectors, but
+    // the decode makes the walk ALU-pipe-bound on B200 — 10^6 spheres 1 994 vs 2 317 Mrays/s on the 4-wide records
+    // (profiles/r2g_tree_c4_2spp_wide8 / _wide4_ld256) — so the 4-wide walk stays the default.
+    v.nodes8 = nullptr; v.n_nodes8 = 0; v.quad_box = nullptr; v.bound8 = -1.0f;
+    {
+        float bound = 0.f; bool finite = n_prims >= 2;
+        for (int i = 0; i < 3; ++i) { bound = fmaxf(bound, fmaxf(fabsf(v.root_min[i]), fabsf(v.root_max[i]))); if (!(fabsf(v.root_min[i]) <= 1073741824.0f && fabsf(v.root_max[i]) <= 1073741824.0f)) finite = false; }
+        const char* on8 = std::getenv("TRT_WIDE8");
+        const bool want8 = finite && v.kind == 1 && v.nodes4 && v.nodes_ref4 && trtk::scene_smem_bytes(v, 3) > 64 * 1024 && on8 && on8[0] == '1';
+        if (want8) {
+            const size_t nq = v.n_quads, node_bytes = align_up(96 * (n_prims - 1)), qb_bytes = align_up(32 * (nq ? nq : 1));
+            const size_t need = node_bytes + qb_bytes;
+            if (dc.buf8 && dc.bytes8 < need) { cudaFree(dc.buf8); dc.buf8 = nullptr; dc.bytes8 = 0; }
+            if (!dc.buf8) { CU(cudaMalloc(&dc.buf8, need)); dc.bytes8 = need; }
+            std::vector<trt_f4> qb(2 * nq);
+            for (const trt::HostPrim& p : s->host.prims) if (p.type == 1 && p.type_index < nq) {     // same slot as the quad's geometry (trt_scene.cpp)
+                qb[2 * (size_t)p.type_index] = trt_f4{p.bmin[0], p.bmin[1], p.bmin[2], 0.f}; qb[2 * (size_t)p.type_index + 1] = trt_f4{p.bmax[0], p.bmax[1], p.bmax[2], 0.f};
+            }
+            void* d_tmp8 = nullptr; uint32_t n8 = 0, levels8 = 0;
+            cudaError_t e = cudaSuccess;
+            if (nq) e = cudaMemcpyAsync((char*)dc.buf8 + node_bytes, qb.data(), 32 * nq, cudaMemcpyHostToDevice, c->stream);
+            if (e == cudaSuccess) e = cudaMalloc(&d_tmp8, trtk::cw8_tmp_bytes((uint32_t)n_prims));
+            if (e == cudaSuccess) e = trtk::build_cw8(v.nodes, (uint32_t)n_prims, v.root, dc.buf8, d_tmp8, &n8, &levels8, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (d_tmp8) cudaFree(d_tmp8);
+            if (e != cudaSuccess) return fail_cuda("trt_scene_upload: compressed 8-wide nodes", e);
+            v.nodes8 = dc.buf8; v.n_nodes8 = n8; v.quad_box = (char*)dc.buf8 + node_bytes; v.bound8 = bound;
+        }
+    }
     dc.version = s->host.version;
     return TRT_OK;
 }

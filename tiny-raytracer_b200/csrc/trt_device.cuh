@@ -132,6 +132,8 @@ struct DevScene {
     const float4* nodes_ref4; uint32_t n_nodes_ref4, root_ref4;   // ordered kinds: the REFERENCE-topology tree's wide nodes, for the rare replay (ordered_replay)
     const float4* g_spheres; const float4* g_quads;    // global-memory copies of spheres / quads (the staged scene overrides those two)
     const float4* flat_cbox; float flat_bound;  // TRT_BVH_FLAT: conservative centre/half-width boxes (phase A), largest |coordinate|
+    const float4* nodes8; uint32_t n_nodes8;    // ordered kinds in global memory: compressed 8-wide nodes (6 float4 each, root 0; trt_lbvh.cu k_cw8_level) or null
+    const float4* quad_box; float bound8;       // with nodes8: every quad's own padded box (2 float4), largest |coordinate| of the scene's boxes
     uint32_t root, n_nodes, n_spheres, n_quads, n_materials, ordered;
     float root_min[3], root_max[3];   // the root's own padded box (only consulted when counting events)
 };
@@ -352,6 +354,7 @@ struct Trav {
     float cur_s;        // ordered kinds: box entry of the child in `cur` (for a leaf: of the primitive's own box)
     bool best_anom;     // ordered kinds: the closest hit's t is smaller than its own box's entry
     bool replay;        // ordered kinds: this ray is being re-traced on the reference-topology tree (see needs_replay)
+    float e8;           // wide-8 walk: the margin E of the conservative quantised-box test for this ray (trav8_setup)
 };
 
 template <bool COUNT>
@@ -659,6 +662,150 @@ TRT_DEV void begin_replay(Trav& T, const DevScene& S) {
     T.replay = true; T.best_anom = false; T.cur = S.root_ref4; T.sp = 0;
     T.best.t = TRT_INF; T.best.ref = TRT_REF_INVALID;
 }
+// ------------------------------------------------------------------ traversal on compressed 8-wide nodes (round 2; ordered kinds in global memory)
+// Node format: trt_lbvh.cu k_cw8_level (96 bytes = three 256-bit loads for up to eight children, against 112 bytes = four loads
+// for four). The quantised child boxes only CULL: child k is skipped when the ray provably misses its quantised box, or provably
+// enters it beyond the closest hit; everything that decides the RESULT is unchanged — a leaf's own padded box is rebuilt from
+// the primitive with the host's operations (sphere, trt_scene.cpp add_sphere) or fetched (quad) and tested with the reference's
+// arithmetic, then the primitive, with trav4_step's acceptance and tie rules. The ordered walk's result does not depend on
+// the visiting order or on how much is culled, as long as nothing is culled that the exact walk would have to visit:
+//   per axis t = fma(q, 2^e * inv, (origin - o) * inv) is within 5 u (B + |o|) |inv| of the real crossing of the quantised
+//   plane (u = 2^-24, B = bound8), the reference's (b - o) * inv within 2 u (...) of the real crossing of the exact plane, and
+//   the quantised box contains the exact one, so: exact test passes (end > start) => far_q + 14 u X > near_q, and the exact
+//   entry s of ANY box inside child k satisfies s >= near_q - 7 u X, with X = max_axis (B + |o|) |inv|. The test uses the margin
+//   E = 2^-18 X = 64 u X (it also covers the 3 low bits of a stack entry, used for the slot number while the nearest is picked).
+// Only for rays without overflow or NaN (ray_is_flat_fast: |o| < 2^30, |1/d| < 2^64, no zero 1/d; scenes with B <= 2^30);
+// every other ray — and a ray whose stack would overflow — is traced in the reference's own order on the reference tree
+// (begin_replay), which is exact by construction. The nearest accepted child is entered; the others are pushed as they come.
+#define TRT_W8_EPS 3.8146973e-6f      /* 2^-18 */
+TRT_DEV bool ray_is_flat_fast(V3 o, V3 inv);
+TRT_DEV void trav8_setup(Trav& T, const DevScene& S) {          // right after trav_begin
+    if (T.cur == TRT_REF_INVALID) return;
+    const V3 o = T.o, inv = T.inv;
+    if (!(ray_is_flat_fast(o, inv) && S.bound8 >= 0.0f && T.t_min >= 0.0f)) { begin_replay(T, S); return; }
+    const float ex = (S.bound8 + fabsf(o.x)) * fabsf(inv.x), ey = (S.bound8 + fabsf(o.y)) * fabsf(inv.y), ez = (S.bound8 + fabsf(o.z)) * fabsf(inv.z);
+    T.e8 = fmaxf(fmaxf(ex, ey), ez) * TRT_W8_EPS + 1e-30f;
+    T.cur = 0u;                                                 // root of the wide-8 tree
+}
+TRT_DEV uint32_t pick8(uint32_t slot, const float4 lo, const float4 hi) {
+    const float a = (slot & 2u) ? ((slot & 1u) ? lo.w : lo.z) : ((slot & 1u) ? lo.y : lo.x);
+    const float b = (slot & 2u) ? ((slot & 1u) ? hi.w : hi.z) : ((slot & 1u) ? hi.y : hi.x);
+    return __float_as_uint((slot & 4u) ? b : a);
+}
+template <bool COUNT>
+TRT_DEV void trav8_step(Trav& T, const DevScene& S, float t_min, TravStack& K, EventCounters* ec = nullptr) {
+    uint32_t cur = T.cur;
+    const V3 o = T.o, d = T.d, inv = T.inv;
+    if (!(cur & TRT_REF_LEAF)) {
+        TRT_ASSERT(cur < S.n_nodes8);
+        if (T.sp + 7 > TRT_MAX_STACK) { begin_replay(T, S); return; }      // cannot happen on sane trees; exactness must not depend on it
+        if (COUNT) ec->node_visits += 1;
+        const float4* np = S.nodes8 + 6 * (size_t)cur;
+        const F4x2 h0 = ldg256(np), h1 = ldg256(np + 2), h2 = ldg256(np + 4);
+        const uint32_t eb = __float_as_uint(h0.a.w);
+        const float sx = __uint_as_float((eb & 0xFFu) << 23) * inv.x, sy = __uint_as_float(((eb >> 8) & 0xFFu) << 23) * inv.y, sz = __uint_as_float(((eb >> 16) & 0xFFu) << 23) * inv.z;
+        const float bx = (h0.a.x - o.x) * inv.x, by = (h0.a.y - o.y) * inv.y, bz = (h0.a.z - o.z) * inv.z;
+        const f32x2 sx2 = pk2(sx, sx), sy2 = pk2(sy, sy), sz2 = pk2(sz, sz), bx2 = pk2(bx, bx), by2 = pk2(by, by), bz2 = pk2(bz, bz);
+        const f32x2 two23 = pk2(8388608.0f, 8388608.0f);
+        // per axis: the plane words the ray meets first / last (children 0..3 in word 0, 4..7 in word 1)
+        const bool px = inv.x > 0.0f, py = inv.y > 0.0f, pz = inv.z > 0.0f;
+        const uint32_t lx0 = __float_as_uint(h0.b.x), lx1 = __float_as_uint(h0.b.y), ly0 = __float_as_uint(h0.b.z), ly1 = __float_as_uint(h0.b.w);
+        const uint32_t lz0 = __float_as_uint(h1.a.x), lz1 = __float_as_uint(h1.a.y), ux0 = __float_as_uint(h1.a.z), ux1 = __float_as_uint(h1.a.w);
+        const uint32_t uy0 = __float_as_uint(h1.b.x), uy1 = __float_as_uint(h1.b.y), uz0 = __float_as_uint(h1.b.z), uz1 = __float_as_uint(h1.b.w);
+        const uint32_t nx0 = px ? lx0 : ux0, nx1 = px ? lx1 : ux1, fx0 = px ? ux0 : lx0, fx1 = px ? ux1 : lx1;
+        const uint32_t ny0 = py ? ly0 : uy0, ny1 = py ? ly1 : uy1, fy0 = py ? uy0 : ly0, fy1 = py ? uy1 : ly1;
+        const uint32_t nz0 = pz ? lz0 : uz0, nz1 = pz ? lz1 : uz1, fz0 = pz ? uz0 : lz0, fz1 = pz ? uz1 : lz1;
+        const float E = T.e8, best = cull_limit(T.best.t);
+        uint32_t key[8];
+#define TRT_W8_CHILD(k, NX, FX, NY, FY, NZ, FZ, R) { \
+            const uint32_t sel_ = 0x7540u + ((k) & 3u); \
+            float tnx, tfx, tny, tfy, tnz, tfz; \
+            upk2(fma2(sub2(pk2(__uint_as_float(__byte_perm(NX, 0x4B000000u, sel_)), __uint_as_float(__byte_perm(FX, 0x4B000000u, sel_))), two23), sx2, bx2), &tnx, &tfx); \
+            upk2(fma2(sub2(pk2(__uint_as_float(__byte_perm(NY, 0x4B000000u, sel_)), __uint_as_float(__byte_perm(FY, 0x4B000000u, sel_))), two23), sy2, by2), &tny, &tfy); \
+            upk2(fma2(sub2(pk2(__uint_as_float(__byte_perm(NZ, 0x4B000000u, sel_)), __uint_as_float(__byte_perm(FZ, 0x4B000000u, sel_))), two23), sz2, bz2), &tnz, &tfz); \
+            const float nr_ = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, t_min)), fr_ = fminf(fminf(tfx, tfy), tfz); \
+            const float sp_ = nr_ - E; \
+            const bool ok_ = (fr_ + E > nr_) && !(best < sp_) && __float_as_uint(R) != TRT_REF_INVALID; \
+            key[k] = ok_ ? ((__float_as_uint(fmaxf(sp_, 0.0f)) & ~7u) | (uint32_t)(k)) : 0xFFFFFFFFu; }
+        TRT_W8_CHILD(0, nx0, fx0, ny0, fy0, nz0, fz0, h2.a.x) TRT_W8_CHILD(1, nx0, fx0, ny0, fy0, nz0, fz0, h2.a.y)
+        TRT_W8_CHILD(2, nx0, fx0, ny0, fy0, nz0, fz0, h2.a.z) TRT_W8_CHILD(3, nx0, fx0, ny0, fy0, nz0, fz0, h2.a.w)
+        TRT_W8_CHILD(4, nx1, fx1, ny1, fy1, nz1, fz1, h2.b.x) TRT_W8_CHILD(5, nx1, fx1, ny1, fy1, nz1, fz1, h2.b.y)
+        TRT_W8_CHILD(6, nx1, fx1, ny1, fy1, nz1, fz1, h2.b.z) TRT_W8_CHILD(7, nx1, fx1, ny1, fy1, nz1, fz1, h2.b.w)
+#undef TRT_W8_CHILD
+        const uint32_t kmin = min(min(min(key[0], key[1]), min(key[2], key[3])), min(min(key[4], key[5]), min(key[6], key[7])));
+        // stack entry: (ref, conservative entry distance = the key without its slot bits: rounded DOWN by < 8 ulp, covered by E)
+#define TRT_W8_PUSH(k, R) if (key[k] != 0xFFFFFFFFu && key[k] != kmin) { K.put(T.sp, __float_as_uint(R), __uint_as_float(key[k] & ~7u)); ++T.sp; }
+        TRT_W8_PUSH(0, h2.a.x) TRT_W8_PUSH(1, h2.a.y) TRT_W8_PUSH(2, h2.a.z) TRT_W8_PUSH(3, h2.a.w)
+        TRT_W8_PUSH(4, h2.b.x) TRT_W8_PUSH(5, h2.b.y) TRT_W8_PUSH(6, h2.b.z) TRT_W8_PUSH(7, h2.b.w)
+#undef TRT_W8_PUSH
+        cur = kmin != 0xFFFFFFFFu ? pick8(kmin & 7u, h2.a, h2.b) : TRT_REF_INVALID;
+    }
+    if (cur != TRT_REF_INVALID && (cur & TRT_REF_LEAF)) {
+        // the leaf's own padded box, exactly (bvh.rs:89): rebuilt (sphere.rs:17-18 + aabb.rs:13-20) or fetched (quad), then the primitive
+        const uint32_t idx = cur & TRT_REF_INDEX_MASK;
+        TRT_ASSERT(idx < ((cur & TRT_REF_QUAD) ? S.n_quads : S.n_spheres));
+        float mnx, mny, mnz, mxx, mxy, mxz; float4 g0;
+        if (cur & TRT_REF_QUAD) {
+            if (COUNT) ec->quad_tests += 1;
+            const F4x2 bb = ldg256(S.quad_box + 2 * (size_t)idx);
+            g0 = __ldg(S.quads + 4 * (size_t)idx);
+            mnx = bb.a.x; mny = bb.a.y; mnz = bb.a.z; mxx = bb.b.x; mxy = bb.b.y; mxz = bb.b.z;
+        } else {
+            if (COUNT) ec->sphere_tests += 1;
+            const F4x2 pr = ldg256(S.spheres + (idx & ~1u));          // the aligned pair that holds sphere idx (arrays are padded to 256 bytes)
+            g0 = (idx & 1u) ? pr.b : pr.a;
+            const float pad = 0.0001f / 2.0f;
+            const float lx = g0.x - g0.w, hx = g0.x + g0.w, ly = g0.y - g0.w, hy = g0.y + g0.w, lz = g0.z - g0.w, hz = g0.z + g0.w;
+            mnx = fminf(lx, hx) - pad; mxx = fmaxf(lx, hx) + pad; mny = fminf(ly, hy) - pad; mxy = fmaxf(ly, hy) + pad; mnz = fminf(lz, hz) - pad; mxz = fmaxf(lz, hz) + pad;
+        }
+        float s, e;
+        slab_tame(mnx, mny, mnz, mxx, mxy, mxz, o, inv, t_min, &s, &e);      // wide-8 rays are tame (trav8_setup)
+        if (e > s && !(cull_limit(T.best.t) < s)) {
+            float t; bool h;
+            if (cur & TRT_REF_QUAD) h = quad_hit_rec<false>(S.quads + 4 * (size_t)idx, g0, o, d, t_min, TRT_INF, T.best.t, &t);
+            else h = sphere_hit_rec(g0, o, d, t_min, TRT_INF, &t);
+            if (h) {
+                if (t < T.best.t) { T.best.t = t; T.best.ref = cur; T.best_anom = s > t; }
+                else if (t == T.best.t) {      // exact tie: the lower reference leaf rank wins
+                    const uint32_t rb = (T.best.ref & TRT_REF_QUAD) ? ld4ua(S.quad_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y
+                                                                    : ld4ua(S.sphere_meta + (T.best.ref & TRT_REF_INDEX_MASK)).y;
+                    const uint32_t rk = (cur & TRT_REF_QUAD) ? ld4ua(S.quad_meta + idx).y : ld4ua(S.sphere_meta + idx).y;
+                    if (rk < rb) { T.best.ref = cur; T.best_anom = s > t; }
+                }
+            }
+        }
+        cur = TRT_REF_INVALID;
+    }
+    while (cur == TRT_REF_INVALID && T.sp > 0) {
+        --T.sp;
+        uint32_t r; float s;
+        K.get(T.sp, &r, &s);
+        if (!(cull_limit(T.best.t) < s)) cur = r;
+    }
+    T.cur = cur;
+}
+template <bool COUNT>
+TRT_DEV void trav8_any_step(Trav& T, const DevScene& S, float t_min, TravStack& K, EventCounters* ec = nullptr) {
+    if (T.replay) {
+        DevScene R = S;
+        R.nodes4 = S.nodes_ref4; R.n_nodes4 = S.n_nodes_ref4; R.spheres = S.g_spheres; R.quads = S.g_quads;
+        trav4_step<false, false, COUNT, true>(T, R, t_min, K, ec);
+    } else trav8_step<COUNT>(T, S, t_min, K, ec);
+}
+
+template <bool COUNT>
+TRT_DEV Hit closest_hit8(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
+    Trav T;
+    trav_begin<false>(T, S, o, d, t_min, ec);
+    trav8_setup(T, S);
+    TravStack K;
+    for (;;) {
+        while (T.cur != TRT_REF_INVALID) trav8_any_step<COUNT>(T, S, t_min, K, ec);
+        if (!needs_replay(T, S)) break;
+        begin_replay(T, S);
+    }
+    return T.best;
+}
 template <bool ORDERED, bool SMEM, bool COUNT>
 TRT_DEV Hit closest_hit4(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
     Trav T;
@@ -947,10 +1094,12 @@ TRT_DEV Hit closest_hit_flat(const float4* __restrict__ CB, float bound, const F
 }
 
 // One whole path: CpuSampler::single_point_sampling, renderer/sampler/cpu.rs:39-65
-// KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH (binary nodes), 2 = TRT_BVH_FLAT, 3 / 4 = SAH / REFERENCE on their 4-wide nodes
+// KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH (binary nodes), 2 = TRT_BVH_FLAT, 3 / 4 = SAH / REFERENCE on their 4-wide nodes,
+// 5 = ordered tree on its compressed 8-wide nodes (global memory)
 template <int KIND, bool SMEM, bool COUNT>
 TRT_DEV Hit closest_hit_any(const DevScene& S, V3 o, V3 d, float t_min, EventCounters* ec) {
     if (KIND == 2) return closest_hit_flat<false>(S.flat_cbox, S.flat_bound, S.flat, S.n_flat, S.flat_qmask[0], S.flat_qmask[1], o, d, t_min);
+    if (KIND == 5) return closest_hit8<COUNT>(S, o, d, t_min, ec);
     if (KIND == 3 || KIND == 4) return closest_hit4<KIND == 3, SMEM, COUNT>(S, o, d, t_min, ec);
     return closest_hit<KIND == 1, SMEM, COUNT>(S, o, d, t_min, ec);
 }

@@ -15,6 +15,7 @@ inline DevScene dev_scene(const SceneView& v) {
     s.flat = (const FlatPrim*)v.flat; s.n_flat = v.n_flat; s.flat_cbox = (const float4*)v.flat_cbox; s.flat_bound = v.flat_bound; s.flat_qmask[0] = v.flat_qmask[0]; s.flat_qmask[1] = v.flat_qmask[1];
     s.nodes4 = (const float4*)v.nodes4; s.n_nodes4 = v.n_nodes4;
     s.nodes_ref4 = (const float4*)v.nodes_ref4; s.n_nodes_ref4 = v.n_nodes_ref4; s.root_ref4 = v.root_ref4; s.g_spheres = s.spheres; s.g_quads = s.quads;
+    s.nodes8 = (const float4*)v.nodes8; s.n_nodes8 = v.n_nodes8; s.quad_box = (const float4*)v.quad_box; s.bound8 = v.bound8;
     s.root = v.root; s.n_nodes = v.n_nodes; s.n_spheres = v.n_spheres; s.n_quads = v.n_quads; s.n_materials = v.n_materials;
     s.ordered = v.kind == 1 ? 1u : 0u;
     for (int i = 0; i < 3; ++i) { s.root_min[i] = v.root_min[i]; s.root_max[i] = v.root_max[i]; }

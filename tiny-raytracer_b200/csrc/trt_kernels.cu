@@ -274,7 +274,7 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
     const DevParams& P = A.p;
     const uint32_t lane = threadIdx.x & 31u;
     Trav T; T.cur = TRT_REF_INVALID; T.sp = 0; T.best.t = TRT_INF; T.best.ref = TRT_REF_INVALID;
-    T.o = mk(0, 0, 0); T.d = mk(0, 0, 1); T.inv = mk(0, 0, 1); T.t_min = P.t_min; T.tame = false;
+    T.o = mk(0, 0, 0); T.d = mk(0, 0, 1); T.inv = mk(0, 0, 1); T.t_min = P.t_min; T.tame = false; T.e8 = 0.f; T.replay = false; T.best_anom = false; T.cur_s = 0.f;
     TravStack K;
     V3 atten = mk(1, 1, 1), color = mk(0, 0, 0);
     uint32_t remain = 0, k = 0;
@@ -287,7 +287,11 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
     for (;;) {
         // ---- T: one step of cpu.rs:48 for every lane whose ray is in flight
         if (T.cur != TRT_REF_INVALID) {
-            if (KIND == 3 || KIND == 4) {
+            if (KIND == 5) {            // compressed 8-wide nodes (ordered; global memory)
+                trav8_any_step<COUNT>(T, S, P.t_min, K, &ec);
+                if (T.cur == TRT_REF_INVALID && needs_replay(T, S)) begin_replay(T, S);                    // rare: DESIGN.md §4.3
+            }
+            else if (KIND == 3 || KIND == 4) {
                 if (STEP == 3 && !SMEM) trav4_any_step_pipe<KIND == 3, COUNT>(T, S, P.t_min, K, &ec);
                 else trav4_any_step<KIND == 3, SMEM, COUNT, STEP == 2>(T, S, P.t_min, K, &ec);
                 if (KIND == 3 && T.cur == TRT_REF_INVALID && needs_replay(T, S)) begin_replay(T, S);     // rare: DESIGN.md §4.3
@@ -333,6 +337,7 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
                 V3 dir = scatter_direction(sf, rd, r);
                 atten = atten * sf.rgb; --remain;
                 trav_begin<COUNT && (KIND < 3)>(T, S, sf.point, normalized(dir), P.t_min, &ec);
+                if (KIND == 5) trav8_setup(T, S);
                 ++n_rays;
             }
         } else {
@@ -350,6 +355,7 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
                     atten = mk(1, 1, 1); color = mk(0, 0, 0); remain = P.max_bounces; alive = true;
                 }
                 trav_begin<COUNT && (KIND < 3)>(T, S, o, normalized(dir), P.t_min, &ec);      // Ray::new normalises, ray.rs:12-14 (root-box event only for the binary counts)
+                if (KIND == 5) trav8_setup(T, S);
                 ++n_rays;
                 // an empty scene (or, when counting, a ray that misses the root box) is finished at once: T.cur stays INVALID
                 // and the lane re-enters S on the next pass with T.best = miss.
@@ -368,7 +374,7 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
 // L1 capacity (10^6 spheres) or a whole CTA of occupancy (final scene), and the ray-swap block runs at low lane counts.
 template <int KIND, bool SMEM, bool COUNT, int MODE, bool PRIM>
 __global__ void __launch_bounds__(MEGA_THREADS, TRT_MEGA_MIN_BLOCKS) k_render_mega(const __grid_constant__ MegaArgs A) {
-    if (MODE == 0) mega_body<KIND, SMEM, COUNT, PRIM>(A, nullptr);
+    if constexpr (MODE == 0) mega_body<KIND, SMEM, COUNT, PRIM>(A, nullptr);
     else mega_body_async<KIND, SMEM, COUNT, PRIM, MODE>(A);
 }
 template <bool PRIM>
@@ -555,7 +561,13 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     const uint32_t step_req = (p.flags >> 16) & 3u;
     const int mega_mode = A.regen_min >= 32u ? 0 : (step_req ? (int)step_req : TRT_STEP_DEFAULT);
     const void* fn = nullptr; int blocks_per_sm = 0; cudaError_t e;
-    if (v.kind == 2) {
+    // ordered trees in global memory, step-wise loop: the compressed 8-wide nodes when the scene has them (trt_scene_upload builds
+    // them only on request, TRT_WIDE8=1: measured slower than the 4-wide walk on B200); TRT_FLAG_NO_WIDE8 keeps the 4-wide walk
+    // even then (same results; A/B, tests)
+    const bool use8 = kind == 3 && !use_smem && mega_mode != 0 && v.nodes8 && v.n_nodes8 && v.nodes_ref4 && !prim && !(p.flags & (1u | TRT_FLAG_NO_WIDE8));
+    if (use8) {
+        e = count ? mega_fn4<5, false, true, 2, false>(&fn, &blocks_per_sm, smem) : mega_fn4<5, false, false, 2, false>(&fn, &blocks_per_sm, smem);
+    } else if (v.kind == 2) {
         fn = prim ? (const void*)k_render_mega_flat<true> : (const void*)k_render_mega_flat<false>;
         if (smem > 48 * 1024) { e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, TRT_FLAT_THREADS, smem);
@@ -622,8 +634,13 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     return cudaLaunchKernel(fn, dim3(grid), dim3(MEGA_THREADS), args, smem, st);
 }
 
+// the one-thread-per-item kernels walk the compressed 8-wide nodes whenever the scene has them (never staged: global memory)
+static uint32_t item_walk_kind(const SceneView& v) {
+    const uint32_t k = walk_kind(v, false);
+    return (k == 3 && v.nodes8 && v.n_nodes8 && v.nodes_ref4) ? 5u : k;
+}
 #define TRT_KIND_LAUNCH(kern, kind, blocks, threads, st, A) \
-    do { if ((kind) == 2) kern<2><<<(blocks), (threads), 0, (st)>>>(A); else if ((kind) == 1) kern<1><<<(blocks), (threads), 0, (st)>>>(A); \
+    do { if ((kind) == 5) kern<5><<<(blocks), (threads), 0, (st)>>>(A); else if ((kind) == 2) kern<2><<<(blocks), (threads), 0, (st)>>>(A); else if ((kind) == 1) kern<1><<<(blocks), (threads), 0, (st)>>>(A); \
          else if ((kind) == 3) kern<3><<<(blocks), (threads), 0, (st)>>>(A); else if ((kind) == 4) kern<4><<<(blocks), (threads), 0, (st)>>>(A); else kern<0><<<(blocks), (threads), 0, (st)>>>(A); } while (0)
 
 cudaError_t launch_aov(const SceneView& v, const trt_camera& cam, const trt_params& p, uint32_t* d_prim, float* d_t,
@@ -634,7 +651,7 @@ cudaError_t launch_aov(const SceneView& v, const trt_camera& cam, const trt_para
     if (A.total == 0) return cudaSuccess;
     unsigned long long blocks = (A.total + 127) / 128;
     if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-    TRT_KIND_LAUNCH(k_aov, walk_kind(v, false), (unsigned)blocks, 128, st, A);
+    TRT_KIND_LAUNCH(k_aov, item_walk_kind(v), (unsigned)blocks, 128, st, A);
     return cudaGetLastError();
 }
 
@@ -644,7 +661,7 @@ cudaError_t launch_sample_batch(const SceneView& v, const trt_params& p, const t
     if (n == 0) return cudaSuccess;
     unsigned long long blocks = (n + 127) / 128;
     if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-    TRT_KIND_LAUNCH(k_sample_batch, walk_kind(v, false), (unsigned)blocks, 128, st, A);
+    TRT_KIND_LAUNCH(k_sample_batch, item_walk_kind(v), (unsigned)blocks, 128, st, A);
     return cudaGetLastError();
 }
 
@@ -654,7 +671,7 @@ cudaError_t launch_trace(const SceneView& v, const float* d_o, const float* d_d,
     if (n == 0) return cudaSuccess;
     unsigned long long blocks = (n + 127) / 128;
     if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
-    TRT_KIND_LAUNCH(k_trace, walk_kind(v, false), (unsigned)blocks, 128, st, A);
+    TRT_KIND_LAUNCH(k_trace, item_walk_kind(v), (unsigned)blocks, 128, st, A);
     return cudaGetLastError();
 }
 

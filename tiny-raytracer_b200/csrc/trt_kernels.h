@@ -20,6 +20,9 @@ struct SceneView {   // device copy of trt::FlatScene
     uint32_t n_flat;
     const void* nodes4; uint32_t n_nodes4;   // tree kinds: the tree collapsed to 4-wide nodes (8 float4 each) or null
     const void* nodes_ref4; uint32_t n_nodes_ref4, root_ref4;   // TRT_BVH_SAH: wide nodes of the reference-topology tree (replay of order-dependent rays) or null
+    const void* nodes8; uint32_t n_nodes8;   // ordered kinds in global memory: compressed 8-wide nodes (6 float4 each, root 0) or null
+    const void* quad_box;                    // with nodes8: every quad's own padded box, (min.xyz, 0), (max.xyz, 0)
+    float bound8;                            // with nodes8: largest |coordinate| of the scene's boxes
     uint32_t root, n_nodes, n_spheres, n_quads, n_materials;
     uint32_t kind;             // trt_bvh_kind after AUTO resolution: 0 reference, 1 SAH, 2 flat
     float root_min[3], root_max[3];
@@ -40,6 +43,10 @@ size_t lbvh_tmp_bytes(uint32_t n);
 // Builds the 64-byte node array (n - 1 nodes) and, if d_nodes4 is not null, its 4-wide form (128 bytes per node) on the device from per-primitive padded boxes (2 float4 each, leaf-ref bits in bmin.w).
 cudaError_t build_lbvh(const void* d_boxes, uint32_t n, void* d_nodes, void* d_nodes4, void* d_tmp, uint32_t* h_depth, float* h_ms, cudaStream_t st);
 cudaError_t collapse_lbvh4(const void* d_nodes, uint32_t n, void* d_nodes4, bool greedy, cudaStream_t st);
+// Compressed 8-wide nodes (trt_lbvh.cu k_cw8_level) of a binary node array with root `root`: 96 bytes per wide node into d_nodes8
+// (room for n - 1 of them), their number into *h_n_nodes8. Synchronises the stream.
+size_t cw8_tmp_bytes(uint32_t n);
+cudaError_t build_cw8(const void* d_nodes, uint32_t n, uint32_t root, void* d_nodes8, void* d_tmp, uint32_t* h_n_nodes8, uint32_t* h_levels, cudaStream_t st);
 size_t ref_order_tmp_bytes(uint32_t n);
 // Node::new (hittable/bvh.rs:42-84) on the device: the reference leaf rank of every primitive into meta.y and the wide nodes
 // of the reference-topology tree (8 float4 per node, n - 1 nodes, root index in *h_root) into d_nodes_ref4.

@@ -314,6 +314,85 @@ __global__ void k_ref_ranks(const float4* __restrict__ boxes, const uint32_t* __
     m->y = i;
 }
 
+
+// ------------------------------------------------------------------ compressed 8-wide nodes (round 2)
+// The walk of a tree that lives in L2 is bounded by the L1 data pipe (one wavefront per 32-byte sector per lane) and by the
+// number of dependent fetches per ray. A wide-8 node holds up to eight children — what is left after opening, six times, the
+// interior child with the largest surface area — with their boxes QUANTISED to 8 bits per plane on a per-node grid
+// (origin + q * 2^e per axis, min planes rounded down, max planes rounded up: the quantised box contains the exact one), in
+// 96 bytes = three 256-bit loads:
+//   [0] origin.xyz, (biased exponent bytes ex | ey << 8 | ez << 16)      [1] qlo_x[8], qlo_y[8]     [2] qlo_z[8], qhi_x[8]
+//   [3] qhi_y[8], qhi_z[8]                                               [4] child refs 0..3        [5] child refs 4..7
+// A child ref is a leaf ref (trt_layout.h) or the index of a wide-8 node; absent children are TRT_REF_INVALID. The quantised
+// boxes only CULL (conservatively); a leaf's own exact box is recomputed / fetched and tested with the reference's arithmetic
+// before its primitive is tested (trt_device.cuh trav8_step), so results stay bit-identical.
+// Built level by level from the binary records (the device-built tree or the uploaded SAH tree): one thread per wide node,
+// interior children get consecutive indices from an atomic counter, `bin_of_wide` maps a wide index to its binary node.
+__global__ void k_cw8_level(const float4* __restrict__ nodes, uint32_t* bin_of_wide, uint32_t begin, uint32_t end,
+                            unsigned int* counter, float4* nodes8) {
+    const uint32_t w = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= end) return;
+    float mn[8][3], mx[8][3]; uint32_t ref[8]; int nk = 0;
+    auto put = [&](int k, const float4* r, int side) {
+        const float4 a = r[0], b = r[1], c = r[2];
+        mn[k][0] = side ? a.y : a.x; mn[k][1] = side ? a.w : a.z; mn[k][2] = side ? b.y : b.x;
+        mx[k][0] = side ? b.w : b.z; mx[k][1] = side ? c.y : c.x; mx[k][2] = side ? c.w : c.z;
+        ref[k] = __float_as_uint(side ? r[3].y : r[3].x);
+    };
+    const float4* rec = nodes + 4 * (size_t)bin_of_wide[w];
+    put(0, rec, 0); nk = 1;
+    if (__float_as_uint(rec[3].y) != 0x7FFFFFFFu) { put(1, rec, 1); nk = 2; }
+    while (nk < 8) {
+        int best = -1; float ba = -1.f;
+        for (int k = 0; k < nk; ++k) if (!(ref[k] & 0x80000000u)) {
+            const float dx = mx[k][0] - mn[k][0], dy = mx[k][1] - mn[k][1], dz = mx[k][2] - mn[k][2];
+            const float a = dx * dy + dy * dz + dz * dx;
+            if (a > ba || best < 0) { ba = a; best = k; }
+        }
+        if (best < 0) break;
+        const float4* cr = nodes + 4 * (size_t)ref[best];
+        const bool two = __float_as_uint(cr[3].y) != 0x7FFFFFFFu;
+        if (two) { for (int k = nk; k > best + 1; --k) { for (int a = 0; a < 3; ++a) { mn[k][a] = mn[k - 1][a]; mx[k][a] = mx[k - 1][a]; } ref[k] = ref[k - 1]; } }
+        put(best, cr, 0);
+        if (two) { put(best + 1, cr, 1); ++nk; }
+    }
+    int ni = 0;
+    for (int k = 0; k < nk; ++k) if (!(ref[k] & 0x80000000u)) ++ni;
+    const uint32_t base = ni ? atomicAdd(counter, (unsigned)ni) : 0u;
+    for (int k = 0, j = 0; k < nk; ++k) if (!(ref[k] & 0x80000000u)) { bin_of_wide[base + j] = ref[k]; ref[k] = base + j; ++j; }
+    float org[3]; int ee[3]; uint32_t qlo[3][2] = {{0, 0}, {0, 0}, {0, 0}}, qhi[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    for (int a = 0; a < 3; ++a) {
+        float lo = mn[0][a], hi = mx[0][a];
+        for (int k = 1; k < nk; ++k) { lo = fminf(lo, mn[k][a]); hi = fmaxf(hi, mx[k][a]); }
+        org[a] = lo;
+        const double ext = (double)hi - (double)lo;
+        int e = -100;
+        if (ext > 0.0) { frexp(ext / 255.0, &e); }               // ext / 255 = m * 2^e, m in [0.5, 1): 255 * 2^e > ext
+        if (!(e >= -100)) e = -100;
+        if (e > 100) e = 100;                                     // (never with |coordinates| <= 2^30, the only scenes this walk is used for)
+        ee[a] = e;
+        const double inv_step = ldexp(1.0, -e), step = ldexp(1.0, e);
+        for (int k = 0; k < nk; ++k) {
+            double ql = floor(((double)mn[k][a] - (double)lo) * inv_step), qh = ceil(((double)mx[k][a] - (double)lo) * inv_step);
+            ql = fmin(fmax(ql, 0.0), 255.0); qh = fmin(fmax(qh, 0.0), 255.0);
+            while (ql > 0.0 && (double)lo + ql * step > (double)mn[k][a]) ql -= 1.0;       // containment, whatever the rounding above did
+            while (qh < 255.0 && (double)lo + qh * step < (double)mx[k][a]) qh += 1.0;
+            qlo[a][k >> 2] |= (uint32_t)ql << (8 * (k & 3));
+            qhi[a][k >> 2] |= (uint32_t)qh << (8 * (k & 3));
+        }
+    }
+    for (int k = nk; k < 8; ++k) ref[k] = 0x7FFFFFFFu;
+    float4* out = nodes8 + 6 * (size_t)w;
+    const uint32_t eb = (uint32_t)(ee[0] + 127) | ((uint32_t)(ee[1] + 127) << 8) | ((uint32_t)(ee[2] + 127) << 16);
+    out[0] = make_float4(org[0], org[1], org[2], __uint_as_float(eb));
+    out[1] = make_float4(__uint_as_float(qlo[0][0]), __uint_as_float(qlo[0][1]), __uint_as_float(qlo[1][0]), __uint_as_float(qlo[1][1]));
+    out[2] = make_float4(__uint_as_float(qlo[2][0]), __uint_as_float(qlo[2][1]), __uint_as_float(qhi[0][0]), __uint_as_float(qhi[0][1]));
+    out[3] = make_float4(__uint_as_float(qhi[1][0]), __uint_as_float(qhi[1][1]), __uint_as_float(qhi[2][0]), __uint_as_float(qhi[2][1]));
+    out[4] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), __uint_as_float(ref[2]), __uint_as_float(ref[3]));
+    out[5] = make_float4(__uint_as_float(ref[4]), __uint_as_float(ref[5]), __uint_as_float(ref[6]), __uint_as_float(ref[7]));
+}
+__global__ void k_cw8_init(uint32_t* bin_of_wide, unsigned int* counter, uint32_t root) { bin_of_wide[0] = root; *counter = 1u; }
+
 } // namespace
 
 namespace trtk {
@@ -372,6 +451,31 @@ cudaError_t build_lbvh(const void* d_boxes, uint32_t n, void* d_nodes, void* d_n
 cudaError_t collapse_lbvh4(const void* d_nodes, uint32_t n, void* d_nodes4, bool greedy, cudaStream_t st) {
     k_lbvh_collapse4<<<(n + 255) / 256, 256, 0, st>>>((const float4*)d_nodes, n, (float4*)d_nodes4, greedy ? 1 : 0);
     return cudaGetLastError();
+}
+
+
+// Compressed 8-wide nodes from a binary node array (n - 1 records of 64 bytes, root index `root`): d_nodes8 must hold
+// 96 * (n - 1) bytes (there are never more wide nodes than binary ones), d_tmp cw8_tmp_bytes(n). Synchronises the stream.
+size_t cw8_tmp_bytes(uint32_t n) { return al(4ull * n) + 256; }
+cudaError_t build_cw8(const void* d_nodes, uint32_t n, uint32_t root, void* d_nodes8, void* d_tmp, uint32_t* h_n_nodes8, uint32_t* h_levels, cudaStream_t st) {
+    if (n < 2) return cudaErrorInvalidValue;
+    uint32_t* bin_of_wide = (uint32_t*)d_tmp;
+    unsigned int* counter = (unsigned int*)((char*)d_tmp + al(4ull * n));
+    k_cw8_init<<<1, 1, 0, st>>>(bin_of_wide, counter, root);
+    uint32_t begin = 0, end = 1, levels = 0;
+    cudaError_t e = cudaSuccess;
+    while (begin < end) {
+        k_cw8_level<<<(end - begin + 127) / 128, 128, 0, st>>>((const float4*)d_nodes, bin_of_wide, begin, end, counter, (float4*)d_nodes8);
+        unsigned int total = 0;
+        e = cudaMemcpyAsync(&total, counter, sizeof total, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (total > n - 1 || total < end) return cudaErrorUnknown;
+        begin = end; end = total; ++levels;
+    }
+    *h_n_nodes8 = end; *h_levels = levels;
+    return cudaSuccess;
 }
 
 size_t ref_order_tmp_bytes(uint32_t n) {
