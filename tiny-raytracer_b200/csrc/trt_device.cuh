@@ -148,11 +148,18 @@ struct DevParams {
 // shared memory when they are small and stay in global memory (L1/L2) when staging them would cost occupancy.
 TRT_DEV float4 ld4a(const float4* p) { return *p; }
 TRT_DEV uint4 ld4ua(const uint4* p) { return *p; }
+#ifndef TRT_LD4_QUAL
+#define TRT_LD4_QUAL ""              /* A/B: cache qualifier (e.g. ".L1::no_allocate", see TRT_NODE_LD_QUAL) of the 128-bit loads of primitives / binary nodes in global memory */
+#endif
 // SMEM = scene staged in shared memory (small scenes): ld.shared.v4; otherwise read-only global path.
 template <bool SMEM> TRT_DEV float4 ld4(const float4* p) {
     if (SMEM) {
         float4 v; uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+        return v;
+    } else if (sizeof(TRT_LD4_QUAL) > 1) {
+        float4 v;
+        asm("ld.global.nc" TRT_LD4_QUAL ".v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
         return v;
     } else return __ldg(p);
 }
@@ -168,11 +175,25 @@ template <bool SMEM> TRT_DEV uint4 ld4u(const uint4* p) {
 // in its own cache line costs the L1 data pipe one wavefront per SECTOR it touches per instruction (10^6 spheres:
 // l1tex__data_pipe_lsu_wavefronts 92 % of peak, one per 16-byte lane access, profiles/r2d_tree_c4_64spp): fetching a wide node
 // as 3 x 32 B + 16 B instead of 7 x 16 B takes the same bytes through 4 instead of 7 of them.
+// Cache qualifier of the wide-node loads of trees in global memory. ".L1::no_allocate": the records still come through L1 but do
+// not displace what is there — on 10^6 spheres L1 then holds the traversal stacks and spills (local memory, whose misses sit
+// inside the pop chain) instead of node lines that are hardly ever reused by the same SM: 2 317 -> 2 511 Mrays/s (device-built
+// tree), 2 451 -> 2 689 (SAH). Measured and rejected (profiles/r2h_*): ".L1::evict_last" +-0; letting the first 2 / 4 node
+// fetches of every ray (the top of the tree) allocate -3 %; the same qualifier on the primitive loads -0.5 %; 5 CTAs per SM
+// -6 %; an L2 access-policy window (persisting set-aside of 32..79 MB) on the node array -2.5 %.
+#ifndef TRT_NODE_LD_QUAL
+#define TRT_NODE_LD_QUAL ".L1::no_allocate"
+#endif
 struct F4x2 { float4 a, b; };
 TRT_DEV F4x2 ldg256(const float4* p) {
     F4x2 v;
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm("ld.global.nc" TRT_NODE_LD_QUAL ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w) : "l"(p));
+    return v;
+}
+TRT_DEV float4 ldg128n(const float4* p) {      // the node's seventh float4, with the same qualifier
+    float4 v;
+    asm("ld.global.nc" TRT_NODE_LD_QUAL ".v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
 
@@ -478,7 +499,7 @@ template <bool SMEM, bool V256>
 TRT_DEV void load_wide_node(const float4* np, float4& a0, float4& a1, float4& a2, float4& b0, float4& b1, float4& b2, float4& rf) {
     if (!SMEM && V256) {
         const F4x2 p0 = ldg256(np), p1 = ldg256(np + 2), p2 = ldg256(np + 4);
-        a0 = p0.a; a1 = p0.b; a2 = p1.a; b0 = p1.b; b1 = p2.a; b2 = p2.b; rf = __ldg(np + 6);
+        a0 = p0.a; a1 = p0.b; a2 = p1.a; b0 = p1.b; b1 = p2.a; b2 = p2.b; rf = ldg128n(np + 6);
     } else {
         a0 = ld4<SMEM>(np); a1 = ld4<SMEM>(np + 1); a2 = ld4<SMEM>(np + 2);
         b0 = ld4<SMEM>(np + 3); b1 = ld4<SMEM>(np + 4); b2 = ld4<SMEM>(np + 5); rf = ld4<SMEM>(np + 6);
