@@ -292,6 +292,7 @@ def main():
     # ---- warm-up (>= 3), the first one also reads the ray / path counts of this rank's share
     st0 = step(want_stats=True)
     my_rays, my_paths = (int(st0.rays), int(st0.paths)) if st0 is not None else (0, 0)
+    render_launches = int(st0.launches) if st0 is not None and int(st0.launches) > 0 else 1   # 2 where the first-bounce pass runs (k_primary + path loop)
     for _ in range(max(args.warmup, 3) - 1):
         step()
     torch.cuda.synchronize()
@@ -414,6 +415,8 @@ def main():
         hits = per_ray["H"] if per_ray else (walked["rays"] - walked["paths"]) / max(walked["rays"], 1)
         walked["hits"] = hits
         walked["bytes"] = 112 * walked["wide_nodes"] + 16 * walked["spheres"] + 64 * walked["quads"] + 32 * hits + 16 * walked["paths"] / max(walked["rays"], 1)
+    if render_launches == 2 and variant == 0:
+        kernel_name = "k_primary + " + kernel_name       # the coherent first-bounce pass runs before the path loop; kernel_ms covers both
     roofline, other = rooflines(args, desc, per_ray, per_ray_src, walked, rays / world, kern_avg_ms, clk, kernel_name)
 
     out = {"metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -427,7 +430,7 @@ def main():
                    "ms_per_step": e2e_s * 1e3,
                    "what": ("trt_render (the C-ABI call behind Renderer::render): host BVH commit + scene upload + render + tone map + f32 and 8-bit image into pinned host buffers"
                             if world == 1 else "per rank: commit + upload scene, render share, NCCL reduce, tone map, rank 0 copies f32 + 8-bit image to pinned host memory")},
-           "gpu_launches": int(args.steps * (world + 1)),   # per step: one k_render_mega per rank + one k_finalize on rank 0
+           "gpu_launches": int(args.steps * (world * render_launches + 1)),   # per step: the render kernel(s) of every rank + one k_finalize on rank 0
            "wall_s_timed_region": wall_timed,
            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
     out.update(other)

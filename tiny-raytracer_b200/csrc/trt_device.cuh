@@ -495,6 +495,36 @@ TRT_DEV Hit closest_hit(const DevScene& S, V3 o, V3 d, float t_min, EventCounter
 #ifndef TRT_NODE_V256
 #define TRT_NODE_V256 true     /* wide nodes in global memory are fetched with 256-bit loads (see ldg256) */
 #endif
+// Pop: stack entries that the closest hit found meanwhile has cut off are skipped. With the stack in local memory every entry
+// is a DEPENDENT load, and on 10^6 spheres the one-at-a-time loop ran 2.8 times per node step with 2 of 32 lanes active — 31 % of
+// the kernel's long-scoreboard stalls (profiles/r2h_tree_c4_2spp): BATCH entries are therefore fetched together and the topmost
+// live one is taken. Same entries skipped, same entry taken: results unchanged.
+#ifndef TRT_POP_BATCH
+#define TRT_POP_BATCH 4      /* 10^6 spheres: 1 -> 2 479, 2 -> 2 482, 4 -> 2 498, 8 -> 2 424 Mrays/s: within noise of each other; 4 kept */
+#endif
+template <bool ORDERED, int BATCH>
+TRT_DEV uint32_t trav_pop(Trav& T, const TravStack& K) {
+    uint32_t cur = TRT_REF_INVALID;
+    while (cur == TRT_REF_INVALID && T.sp > 0) {
+        if (BATCH <= 1) {
+            --T.sp;
+            uint32_t r; float s;
+            K.get(T.sp, &r, &s);
+            if (ORDERED ? !(cull_limit(T.best.t) < s) : (T.best.t > s)) { cur = r; if (ORDERED) T.cur_s = s; }
+        } else {
+            const float lim = ORDERED ? cull_limit(T.best.t) : T.best.t;
+            uint32_t r[BATCH > 1 ? BATCH : 1]; float s[BATCH > 1 ? BATCH : 1];
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) { const int i = T.sp - 1 - j; K.get(i > 0 ? i : 0, &r[j], &s[j]); }
+            int used = T.sp < BATCH ? T.sp : BATCH;          // all of them cut off: drop them all
+#pragma unroll
+            for (int j = BATCH - 1; j >= 0; --j)
+                if (j < T.sp && (ORDERED ? !(lim < s[j]) : (lim > s[j]))) { cur = r[j]; if (ORDERED) T.cur_s = s[j]; used = j + 1; }
+            T.sp -= used;
+        }
+    }
+    return cur;
+}
 template <bool SMEM, bool V256>
 TRT_DEV void load_wide_node(const float4* np, float4& a0, float4& a1, float4& a2, float4& b0, float4& b1, float4& b2, float4& rf) {
     if (!SMEM && V256) {
@@ -570,12 +600,7 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, float t_min, TravStack& K, E
         }
         cur = TRT_REF_INVALID;
     }
-    while (cur == TRT_REF_INVALID && T.sp > 0) {
-        --T.sp;
-        uint32_t r; float s;
-        K.get(T.sp, &r, &s);
-        if (ORDERED ? !(cull_limit(T.best.t) < s) : (T.best.t > s)) { cur = r; if (ORDERED) T.cur_s = s; }
-    }
+    if (cur == TRT_REF_INVALID) cur = trav_pop<ORDERED, SMEM ? 1 : TRT_POP_BATCH>(T, K);
     T.cur = cur;
 }
 // One step of the wide walk, or — for a lane that is replaying its ray (needs_replay) — of the reference-order walk on the
@@ -662,12 +687,7 @@ TRT_DEV void trav4_step_pipe(Trav& T, const DevScene& S, float t_min, TravStack&
         }
         cur = TRT_REF_INVALID;
     }
-    while (cur == TRT_REF_INVALID && T.sp > 0) {
-        --T.sp;
-        uint32_t r; float s;
-        K.get(T.sp, &r, &s);
-        if (ORDERED ? !(cull_limit(T.best.t) < s) : (T.best.t > s)) { cur = r; if (ORDERED) T.cur_s = s; }
-    }
+    if (cur == TRT_REF_INVALID) cur = trav_pop<ORDERED, TRT_POP_BATCH>(T, K);
     T.cur = cur;
 }
 template <bool ORDERED, bool COUNT>
@@ -876,32 +896,46 @@ struct Surface { V3 point, normal; bool front; uint32_t kind; V3 rgb; float para
 // compute the geometric half once, for the lanes that really scatter:
 //   hit_material  material id -> (kind, rgb, param): what Material::emitted / scatter need to know (material/*.rs)
 //   hit_geometry  HitRecord::new (hittable/mod.rs:27-48): point = at(t), front_face, unit normal against the ray
-template <bool SMEM>
+// Scenes in global memory pay an L2 round trip for every DEPENDENT load of this block while the whole warp waits, so there the
+// two material float4 are fetched together (BOTH) and the primitive's first float4 is fetched before the material is known
+// (hit_prim_f4, passed to hit_geometry_f4): meta -> material -> primitive becomes (meta | primitive) -> material.
+template <bool SMEM, bool BOTH = !SMEM>
 TRT_DEV void hit_material(const DevScene& S, Hit h, Surface* sf) {
     const uint32_t idx = h.ref & TRT_REF_INDEX_MASK;
     const uint32_t mat = (h.ref & TRT_REF_QUAD) ? ld4ua(S.quad_meta + idx).x : ld4ua(S.sphere_meta + idx).x;
     const float4 m0 = ld4a(S.materials + 2 * (size_t)mat);
-    sf->kind = __float_as_uint(m0.w);
-    sf->rgb = mk(m0.x, m0.y, m0.z);
-    sf->param = (sf->kind == TRT_MAT_METAL || sf->kind == TRT_MAT_DIELECTRIC) ? ld4a(S.materials + 2 * (size_t)mat + 1).x : 0.0f;
+    if (BOTH) {
+        const float4 m1 = ld4a(S.materials + 2 * (size_t)mat + 1);
+        sf->kind = __float_as_uint(m0.w);
+        sf->rgb = mk(m0.x, m0.y, m0.z);
+        sf->param = (sf->kind == TRT_MAT_METAL || sf->kind == TRT_MAT_DIELECTRIC) ? m1.x : 0.0f;
+    } else {
+        sf->kind = __float_as_uint(m0.w);
+        sf->rgb = mk(m0.x, m0.y, m0.z);
+        sf->param = (sf->kind == TRT_MAT_METAL || sf->kind == TRT_MAT_DIELECTRIC) ? ld4a(S.materials + 2 * (size_t)mat + 1).x : 0.0f;
+    }
 }
 template <bool SMEM>
-TRT_DEV void hit_geometry(const DevScene& S, Hit h, V3 o, V3 d, Surface* sf) {
+TRT_DEV float4 hit_prim_f4(const DevScene& S, Hit h) {       // sphere: (centre, r); quad: (n, D)
+    const uint32_t idx = h.ref & TRT_REF_INDEX_MASK;
+    return (h.ref & TRT_REF_QUAD) ? ld4<SMEM>(S.quads + 4 * (size_t)idx) : ld4<SMEM>(S.spheres + idx);
+}
+TRT_DEV void hit_geometry_f4(const DevScene& S, Hit h, V3 o, V3 d, const float4 g0, Surface* sf) {
     const uint32_t idx = h.ref & TRT_REF_INDEX_MASK;
     sf->point = ray_at(o, d, h.t);
     V3 outward, nn;
     if (h.ref & TRT_REF_QUAD) {
-        const float4 q0 = ld4<SMEM>(S.quads + 4 * (size_t)idx);
-        outward = mk(q0.x, q0.y, q0.z);                                       // quad.rs:45: the unnormalised n
+        outward = mk(g0.x, g0.y, g0.z);                                       // quad.rs:45: the unnormalised n
         const float4 q = ld4a(S.quad_nn + idx); nn = mk(q.x, q.y, q.z);       // n / |n| never changes: host-side, same ops
     } else {
-        const float4 s = ld4<SMEM>(S.spheres + idx);
-        outward = sf->point - mk(s.x, s.y, s.z);                              // sphere.rs:46-50
+        outward = sf->point - mk(g0.x, g0.y, g0.z);                           // sphere.rs:46-50
         nn = normalized(outward);
     }
     sf->front = dot(d, outward) < 0.0f;
     sf->normal = sf->front ? nn : -nn;
 }
+template <bool SMEM>
+TRT_DEV void hit_geometry(const DevScene& S, Hit h, V3 o, V3 d, Surface* sf) { hit_geometry_f4(S, h, o, d, hit_prim_f4<SMEM>(S, h), sf); }
 template <bool SMEM>
 TRT_DEV Surface hit_record(const DevScene& S, Hit h, V3 o, V3 d) {
     Surface sf;

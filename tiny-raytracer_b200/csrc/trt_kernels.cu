@@ -308,10 +308,12 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
         sf.point = sf.normal = sf.rgb = mk(0, 0, 0);
         bool scatter = false;
         Hit h = T.best; V3 ro = T.o, rd = T.d;
+        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (in_s && alive) {
             if (KIND == 1 && needs_replay(T, S)) h = ordered_replay(S, T.o, T.d, P.t_min);   // rare: DESIGN.md §4.3 (binary walk)
             if (h.ref == TRT_REF_INVALID) color = color + atten * mk(P.bg[0], P.bg[1], P.bg[2]);
             else {
+                if (!SMEM && !PRIM) g0 = hit_prim_f4<SMEM>(S, h);      // global memory: fetched beside the meta record, not after the material
                 hit_material<SMEM>(S, h, &sf);
                 V3 emission = (sf.kind == TRT_MAT_LIGHT) ? sf.rgb : mk(0.0f, 0.0f, 0.0f);
                 color = color + atten * emission;
@@ -341,7 +343,7 @@ __device__ __forceinline__ void mega_body_async(const MegaArgs& A) {
                 ++n_rays;
             }
         } else {
-            if (scatter) hit_geometry<SMEM>(S, h, ro, rd, &sf);
+            if (scatter) { if (!SMEM) hit_geometry_f4(S, h, ro, rd, g0, &sf); else hit_geometry<SMEM>(S, h, ro, rd, &sf); }
             if (scatter || regen) {
                 uint32_t sample = P.sample_offset + I.s_cur;
                 if (scatter) ++k; else k = 0;
