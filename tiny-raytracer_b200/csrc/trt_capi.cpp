@@ -42,7 +42,10 @@ struct trt_ctx {
     unsigned long long* d_counters = nullptr;   // 8 x u64 (5 used) followed by the u32 work counter
     unsigned int* d_next_item = nullptr;
     // scratch reused across calls (grown on demand)
-    void* scratch[4] = {nullptr, nullptr, nullptr, nullptr}; size_t scratch_bytes[4] = {0, 0, 0, 0};
+    // slots: 0 f64 sums, 1 f32 image, 2 8-bit image (trt_render), 3 wavefront path pool, 4..7 temporaries of trt_scene_upload's device
+    // builds (primitive boxes, LBVH, reference order, wide-8 collapse) — kept, because cudaMalloc / cudaFree of ~200 MB per upload
+    // cost 30...400 ms of wall time on a 10^6-primitive scene (scripts/e2e_probe.py) against 5 ms for the builds themselves
+    void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     void* d_prim = nullptr; size_t prim_bytes = 0;   // records of the coherent first-bounce pass (one sample batch)
     char name[256];
 };
@@ -56,6 +59,19 @@ static int ensure_scratch(trt_ctx* c, int slot, size_t bytes, void** out) {
     }
     *out = c->scratch[slot];
     return TRT_OK;
+}
+
+// the same for code that carries a cudaError_t along (trt_scene_upload's device builds)
+static cudaError_t scratch_cu(trt_ctx* c, int slot, size_t bytes, void** out) {
+    if (bytes == 0) bytes = 16;
+    if (c->scratch_bytes[slot] < bytes) {
+        if (c->scratch[slot]) { cudaFree(c->scratch[slot]); c->scratch[slot] = nullptr; c->scratch_bytes[slot] = 0; }
+        cudaError_t e = cudaMalloc(&c->scratch[slot], bytes);
+        if (e != cudaSuccess) { c->scratch[slot] = nullptr; return e; }
+        c->scratch_bytes[slot] = bytes;
+    }
+    *out = c->scratch[slot];
+    return cudaSuccess;
 }
 
 extern "C" {
@@ -92,7 +108,7 @@ int trt_ctx_destroy(trt_ctx* c) {
     if (!c) return TRT_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (int i = 0; i < 4; ++i) if (c->scratch[i]) cudaFree(c->scratch[i]);
+    for (int i = 0; i < 8; ++i) if (c->scratch[i]) cudaFree(c->scratch[i]);
     if (c->d_prim) cudaFree(c->d_prim);
     if (c->d_counters) cudaFree(c->d_counters);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -218,9 +234,8 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
     // to the host for trt_scene_leaf_ranks), the reference tree's wide nodes into the buffer
     auto ref_order = [&](const void* d_boxes, float* ms_out) -> cudaError_t {
         void* d_tmp2 = nullptr; uint32_t root_ref = 0;
-        cudaError_t e = cudaMalloc(&d_tmp2, trtk::ref_order_tmp_bytes((uint32_t)n_prims));
+        cudaError_t e = scratch_cu(c, 6, trtk::ref_order_tmp_bytes((uint32_t)n_prims), &d_tmp2);
         if (e == cudaSuccess) e = trtk::build_reference_order(d_boxes, (uint32_t)n_prims, (char*)dc.buf + off[3], (char*)dc.buf + off[4], (char*)dc.buf + off[10], d_tmp2, &root_ref, ms_out, c->stream);
-        if (d_tmp2) cudaFree(d_tmp2);
         if (e != cudaSuccess) return e;
         dc.root_ref4 = root_ref;
         std::vector<trt_u4> meta(f.sphere_meta.size() + f.quad_meta.size());     // meta = (material, rank, prim_id, 0)
@@ -235,22 +250,20 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
     }
     if (f.ref_on_device) {
         void* d_boxes = nullptr; float ms_ref = 0.f;
-        cudaError_t e = cudaMalloc(&d_boxes, f.lbvh_boxes.size() * 16);
+        cudaError_t e = scratch_cu(c, 4, f.lbvh_boxes.size() * 16, &d_boxes);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_boxes, f.lbvh_boxes.data(), f.lbvh_boxes.size() * 16, cudaMemcpyHostToDevice, c->stream);
         if (e == cudaSuccess) e = ref_order(d_boxes, &ms_ref);
-        if (d_boxes) cudaFree(d_boxes);
         if (e != cudaSuccess) return fail_cuda("trt_scene_upload: device reference order", e);
         { std::lock_guard<std::mutex> lk(s->host_mutex); s->host.device_build_ms = ms_ref; }
     }
     if (device_build) {
         // the walked tree on the GPU: Morton codes + radix sort + Karras hierarchy + bottom-up boxes (trt_lbvh.cu)
         void *d_boxes = nullptr, *d_tmp = nullptr;
-        cudaError_t e = cudaMalloc(&d_boxes, f.lbvh_boxes.size() * 16);        // no early return below: both temporaries are freed on every path
-        if (e == cudaSuccess) e = cudaMalloc(&d_tmp, trtk::lbvh_tmp_bytes((uint32_t)n_prims));
+        cudaError_t e = scratch_cu(c, 4, f.lbvh_boxes.size() * 16, &d_boxes);   // pooled in the context: nothing to free on any path
+        if (e == cudaSuccess) e = scratch_cu(c, 5, trtk::lbvh_tmp_bytes((uint32_t)n_prims), &d_tmp);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_boxes, f.lbvh_boxes.data(), f.lbvh_boxes.size() * 16, cudaMemcpyHostToDevice, c->stream);
         uint32_t depth = 0; float ms = 0.f;
         if (e == cudaSuccess) e = trtk::build_lbvh(d_boxes, (uint32_t)n_prims, (char*)dc.buf + off[0], (char*)dc.buf + off[9], d_tmp, &depth, &ms, c->stream);
-        if (d_tmp) cudaFree(d_tmp);
         // the wide records: plain two-level collapse (opening the largest children instead, as the host does for the SAH tree,
         // measured no gain on the device-built tree: 10^6 spheres 2 100 vs 2 112 Mrays/s)
         const bool greedy4 = false;
@@ -259,7 +272,6 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
         // Node::new itself on the device: the reference leaf order (tie rule) and the reference tree's wide nodes (replay)
         float ms_ref = 0.f;
         if (e == cudaSuccess) e = ref_order(d_boxes, &ms_ref);
-        if (d_boxes) cudaFree(d_boxes);
         if (e != cudaSuccess) return fail_cuda("trt_scene_upload: device BVH build", e);
         { std::lock_guard<std::mutex> lk(s->host_mutex); s->host.flat.max_depth = depth; s->host.device_build_ms = ms + ms_ref; }
         if (depth > TRT_MAX_STACK) return fail(TRT_ERR_UNSUPPORTED, "trt_scene_upload: device-built tree deeper than the traversal stack; commit with TRT_BVH_SAH");
@@ -302,10 +314,9 @@ int trt_scene_upload(trt_ctx* c, trt_scene* s) {
             void* d_tmp8 = nullptr; uint32_t n8 = 0, levels8 = 0;
             cudaError_t e = cudaSuccess;
             if (nq) e = cudaMemcpyAsync((char*)dc.buf8 + node_bytes, qb.data(), 32 * nq, cudaMemcpyHostToDevice, c->stream);
-            if (e == cudaSuccess) e = cudaMalloc(&d_tmp8, trtk::cw8_tmp_bytes((uint32_t)n_prims));
+            if (e == cudaSuccess) e = scratch_cu(c, 7, trtk::cw8_tmp_bytes((uint32_t)n_prims), &d_tmp8);
             if (e == cudaSuccess) e = trtk::build_cw8(v.nodes, (uint32_t)n_prims, v.root, dc.buf8, d_tmp8, &n8, &levels8, c->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-            if (d_tmp8) cudaFree(d_tmp8);
             if (e != cudaSuccess) return fail_cuda("trt_scene_upload: compressed 8-wide nodes", e);
             v.nodes8 = dc.buf8; v.n_nodes8 = n8; v.quad_box = (char*)dc.buf8 + node_bytes; v.bound8 = bound;
         }

@@ -525,6 +525,37 @@ TRT_DEV uint32_t trav_pop(Trav& T, const TravStack& K) {
     }
     return cur;
 }
+// Four child boxes of a wide node STAGED IN SHARED MEMORY, for a tame ray: instead of computing both crossings of an axis and
+// ordering them with min / max (slab2_tame: 12 FMNMX per pair of boxes), the plane pair the ray meets FIRST and the one it meets
+// LAST are fetched through sign-dependent addresses (1/d > 0: the min planes first) — per axis a tame ray's crossings are ordered
+// by the sign alone ((mn - o) <= (mx - o) and a multiplication by a positive / negative number keeps / reverses the order, both
+// under round-to-nearest), so start and end are the SAME values slab2_tame computes, bit for bit; an absent child (box
+// +inf..-inf) comes out as start = +inf, end = -inf instead of a crossed box and is dropped either way (its ref is INVALID).
+// 12 LDS.64 + 6 address adds instead of 6 LDS.128, 24 FMNMX fewer per node. Record layout (trt_layout.h): pair group = 48
+// bytes: min x @0, min y @8, min z @16, max x @24, max y @32, max z @40; second group at +48.
+#ifndef TRT_SMEM_SIGN_SELECT
+#define TRT_SMEM_SIGN_SELECT 0      /* until measured */
+#endif
+TRT_DEV f32x2 lds64(uint32_t addr) { f32x2 v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr)); return v; }
+TRT_DEV void slab4_tame_signed(const float4* np, V3 o, V3 inv, float t_min, float* s0, float* e0, float* s1, float* e1,
+                               float* s2, float* e2, float* s3, float* e3) {
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(np);
+    const uint32_t kx = inv.x < 0.0f ? 24u : 0u, ky = inv.y < 0.0f ? 24u : 0u, kz = inv.z < 0.0f ? 24u : 0u;
+    const uint32_t nx = base + kx, fx = base + 24u - kx, ny = base + 8u + ky, fy = base + 32u - ky, nz = base + 16u + kz, fz = base + 40u - kz;
+    const f32x2 ox = pk2(o.x, o.x), oy = pk2(o.y, o.y), oz = pk2(o.z, o.z);
+    const f32x2 ix = pk2(inv.x, inv.x), iy = pk2(inv.y, inv.y), iz = pk2(inv.z, inv.z);
+    float nxl, nxr, fxl, fxr, nyl, nyr, fyl, fyr, nzl, nzr, fzl, fzr;
+    upk2(mul2(sub2(lds64(nx), ox), ix), &nxl, &nxr); upk2(mul2(sub2(lds64(fx), ox), ix), &fxl, &fxr);
+    upk2(mul2(sub2(lds64(ny), oy), iy), &nyl, &nyr); upk2(mul2(sub2(lds64(fy), oy), iy), &fyl, &fyr);
+    upk2(mul2(sub2(lds64(nz), oz), iz), &nzl, &nzr); upk2(mul2(sub2(lds64(fz), oz), iz), &fzl, &fzr);
+    *s0 = fmaxf(fmaxf(t_min, nxl), fmaxf(nyl, nzl)); *e0 = fminf(fminf(fxl, fyl), fzl);
+    *s1 = fmaxf(fmaxf(t_min, nxr), fmaxf(nyr, nzr)); *e1 = fminf(fminf(fxr, fyr), fzr);
+    upk2(mul2(sub2(lds64(nx + 48u), ox), ix), &nxl, &nxr); upk2(mul2(sub2(lds64(fx + 48u), ox), ix), &fxl, &fxr);
+    upk2(mul2(sub2(lds64(ny + 48u), oy), iy), &nyl, &nyr); upk2(mul2(sub2(lds64(fy + 48u), oy), iy), &fyl, &fyr);
+    upk2(mul2(sub2(lds64(nz + 48u), oz), iz), &nzl, &nzr); upk2(mul2(sub2(lds64(fz + 48u), oz), iz), &fzl, &fzr);
+    *s2 = fmaxf(fmaxf(t_min, nxl), fmaxf(nyl, nzl)); *e2 = fminf(fminf(fxl, fyl), fzl);
+    *s3 = fmaxf(fmaxf(t_min, nxr), fmaxf(nyr, nzr)); *e3 = fminf(fminf(fxr, fyr), fzr);
+}
 template <bool SMEM, bool V256>
 TRT_DEV void load_wide_node(const float4* np, float4& a0, float4& a1, float4& a2, float4& b0, float4& b1, float4& b2, float4& rf) {
     if (!SMEM && V256) {
@@ -544,16 +575,21 @@ TRT_DEV void trav4_step(Trav& T, const DevScene& S, float t_min, TravStack& K, E
         if (COUNT) ec->node_visits += 1;
         const float4* np = S.nodes4 + (size_t)(SMEM ? TRT_WIDE_SMEM_F4 : 8) * cur;
         float4 a0, a1, a2, b0, b1, b2, rf;
-        load_wide_node<SMEM, V256>(np, a0, a1, a2, b0, b1, b2, rf);
         float s0, e0, s1, e1, s2, e2, s3, e3;
-        if (T.tame) {
-            slab2_tame(a0, a1, a2, o, inv, t_min, &s0, &e0, &s1, &e1);
-            slab2_tame(b0, b1, b2, o, inv, t_min, &s2, &e2, &s3, &e3);
+        if (SMEM && TRT_SMEM_SIGN_SELECT && T.tame) {
+            slab4_tame_signed(np, o, inv, t_min, &s0, &e0, &s1, &e1, &s2, &e2, &s3, &e3);
+            rf = ld4<true>(np + 6);
         } else {
-            slab(a0.x, a0.z, a1.x, a1.z, a2.x, a2.z, o, inv, t_min, &s0, &e0);
-            slab(a0.y, a0.w, a1.y, a1.w, a2.y, a2.w, o, inv, t_min, &s1, &e1);
-            slab(b0.x, b0.z, b1.x, b1.z, b2.x, b2.z, o, inv, t_min, &s2, &e2);
-            slab(b0.y, b0.w, b1.y, b1.w, b2.y, b2.w, o, inv, t_min, &s3, &e3);
+            load_wide_node<SMEM, V256>(np, a0, a1, a2, b0, b1, b2, rf);
+            if (T.tame) {
+                slab2_tame(a0, a1, a2, o, inv, t_min, &s0, &e0, &s1, &e1);
+                slab2_tame(b0, b1, b2, o, inv, t_min, &s2, &e2, &s3, &e3);
+            } else {
+                slab(a0.x, a0.z, a1.x, a1.z, a2.x, a2.z, o, inv, t_min, &s0, &e0);
+                slab(a0.y, a0.w, a1.y, a1.w, a2.y, a2.w, o, inv, t_min, &s1, &e1);
+                slab(b0.x, b0.z, b1.x, b1.z, b2.x, b2.z, o, inv, t_min, &s2, &e2);
+                slab(b0.y, b0.w, b1.y, b1.w, b2.y, b2.w, o, inv, t_min, &s3, &e3);
+            }
         }
         uint32_t r0 = __float_as_uint(rf.x), r1 = __float_as_uint(rf.y), r2 = __float_as_uint(rf.z), r3 = __float_as_uint(rf.w);
         const float best = ORDERED ? cull_limit(T.best.t) : T.best.t;

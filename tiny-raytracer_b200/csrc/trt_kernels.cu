@@ -42,7 +42,7 @@ struct MegaArgs {
                                    // the remaining tiles as n_chunks items of `chunk` samples each (f64 atomicAdd): small
                                    // items at the end of the job, so that lanes do not idle behind the last whole pixel
     uint32_t regen_min;            // lanes that must be waiting before the shade/regenerate block runs (32 = T-then-S)
-    const float4* prim_a; const float4* prim_b;   // PRIM kernels: the records of k_primary for this launch's samples, [spp][H*W]
+    const float4* prim_a; const float4* prim_b;   // PRIM kernels: the records of k_primary for this launch's samples, [spp][H*W] x 2 float4 (prim_b unused)
 };
 #ifndef TRT_STEP_DEFAULT
 #define TRT_STEP_DEFAULT 2      /* measured on 10^6 spheres (B200): 1 -> 2 117, 2 -> 2 328, 3 -> 2 303 Mrays/s (device-built tree); 2 242 / 2 458 / 2 430 (SAH) */
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) k_primary(const __grid_constant__ PrimArg
             ra = make_float4(col.x, col.y, col.z, h.t); rb.w = __uint_as_float(TRT_REF_DONE);
         }
         const unsigned long long ri = (unsigned long long)s * npix + pixel;
-        __stcs(A.a + ri, ra); __stcs(A.b + ri, rb);
+        __stcs(A.a + 2 * ri, ra); __stcs(A.a + 2 * ri + 1, rb);       // one 32-byte record per path: the path loop reads it with ONE 256-bit load
     }
 }
 
@@ -158,7 +158,10 @@ __device__ __forceinline__ bool take_primary(const MegaArgs& A, ItemState& I, V3
 #pragma unroll 1
     for (int it = 0; it < TRT_PRIM_BURST && I.s_cur < I.s_end; ++it) {
         const size_t ri = (size_t)I.s_cur * npix + I.pixel;
-        const float4 ra = __ldcs(A.prim_a + ri), rb = __ldcs(A.prim_b + ri);
+        // written by k_primary, read-only here. ONE 32-byte record = one sector: with (a, b) in two arrays the final-scene frame read
+        // 67 GB from DRAM (profiles/r2j_tree_c2_500spp); interleaved: 131.1 -> 124.4 ms. Prefetching the pixel's next record into L2: +-0.
+        const F4x2 rec = ldg256(A.prim_a + 2 * ri);
+        const float4 ra = rec.a, rb = rec.b;
         ++*n_rays;
         const uint32_t ref = __float_as_uint(rb.w);
         if (ref != TRT_REF_DONE) { *o = mk(ra.x, ra.y, ra.z); *d = mk(rb.x, rb.y, rb.z); h->t = ra.w; h->ref = ref; return true; }
@@ -605,9 +608,15 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
         if (c < 4) c = 4;
         if (c < chunk) chunk = (uint32_t)c;
     } else if (p.spp >= 32 && !(p.flags & TRT_FLAG_NO_TAIL_SPLIT)) {
-        tiles_rest = (2 * resident + 31) / 32;                 // ~2 pixels per lane are handed out in pieces
+        // tuning overrides (development): TRT_TAIL_PX = pixels per lane handed out in pieces, TRT_TAIL_DIV = pieces per pixel, TRT_TAIL_MIN = samples per piece at least
+        double tail_px = 3.0; uint32_t tail_div = 32, tail_min = 4;      // measured (Cornell 1080p, 128 / 256 spp, profiles/r2j_probe_c3_tail_split.log): 3 pixels per lane -0.4 % against 2; 0.5...1.5 slower; 16...128 pieces +-0.2 %
+        if (const char* e = std::getenv("TRT_TAIL_PX")) { double x = std::atof(e); if (x >= 0.0 && x <= 64.0) tail_px = x; }
+        if (const char* e = std::getenv("TRT_TAIL_DIV")) { long x = std::atol(e); if (x >= 1 && x <= 4096) tail_div = (uint32_t)x; }
+        if (const char* e = std::getenv("TRT_TAIL_MIN")) { long x = std::atol(e); if (x >= 1 && x <= 4096) tail_min = (uint32_t)x; }
+        tiles_rest = (uint64_t)((tail_px * (double)resident + 31.0) / 32.0);                 // ~3 pixels per lane are handed out in pieces
         if (tiles_rest > n_tiles) tiles_rest = n_tiles;
-        chunk = (p.spp + 31) / 32; if (chunk < 4) chunk = 4;     // 1/32 of a pixel: the job ends within ~half a chunk per lane (1/8: -0.35 % at 1024 spp)
+        chunk = (p.spp + tail_div - 1) / tail_div; if (chunk < tail_min) chunk = tail_min;     // 1/32 of a pixel: the job ends within ~half a chunk per lane (1/8: -0.35 % at 1024 spp)
+        if (chunk > p.spp) chunk = p.spp;
     }
     A.chunk = chunk; A.n_chunks = p.spp ? (p.spp + chunk - 1) / chunk : 0;
     A.tiles_whole = (uint32_t)(n_tiles - tiles_rest);
