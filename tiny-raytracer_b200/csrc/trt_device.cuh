@@ -534,7 +534,7 @@ TRT_DEV uint32_t trav_pop(Trav& T, const TravStack& K) {
 // 12 LDS.64 + 6 address adds instead of 6 LDS.128, 24 FMNMX fewer per node. Record layout (trt_layout.h): pair group = 48
 // bytes: min x @0, min y @8, min z @16, max x @24, max y @32, max z @40; second group at +48.
 #ifndef TRT_SMEM_SIGN_SELECT
-#define TRT_SMEM_SIGN_SELECT 0      /* until measured */
+#define TRT_SMEM_SIGN_SELECT 1      /* final scene (B200): 8 588 -> 9 054 Mrays/s at 64 spp, 128.0 -> 120.6 ms at 500 spp; reference-topology tree 6 713 -> 7 023 (profiles/r2k_probe_c2_sign_select.log) */
 #endif
 TRT_DEV f32x2 lds64(uint32_t addr) { f32x2 v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr)); return v; }
 TRT_DEV void slab4_tame_signed(const float4* np, V3 o, V3 inv, float t_min, float* s0, float* e0, float* s1, float* e1,
