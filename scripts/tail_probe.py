@@ -12,7 +12,8 @@ cam = trt.make_camera(**desc.camera)
 sc = trt.Scene.from_desc(desc, trt.BVH_AUTO); sc.upload(ctx)
 acc = torch.zeros(h * w * 3, dtype=torch.float64, device="cuda:0"); torch.cuda.synchronize()
 settings = [(2, 32, 4), (1, 32, 4), (0.5, 32, 4), (4, 32, 4), (2, 16, 4), (2, 64, 4), (2, 64, 2), (2, 128, 1), (1, 64, 2), (1, 16, 8), (3, 32, 4), (1.5, 32, 4)]
-for spp in (128, 256):
+if len(sys.argv) > 2 and sys.argv[2] == "short": settings = [(2, 32, 4), (3, 32, 4), (2, 32, 4), (3, 32, 4), (4, 32, 4), (1, 32, 4)]
+for spp in ((128, 256) if not (len(sys.argv) > 3) else tuple(int(x) for x in sys.argv[3].split(","))):
     p = trt.make_params(w, h, spp, desc.max_bounces, desc.background, desc.seed, spp_total=spp)
     for px, div, mn in settings:
         os.environ["TRT_TAIL_PX"] = str(px); os.environ["TRT_TAIL_DIV"] = str(div); os.environ["TRT_TAIL_MIN"] = str(mn)

@@ -186,7 +186,11 @@ __device__ __forceinline__ void mega_stats(const MegaArgs& A, uint32_t lane, uin
 // still has work leaves S with a live ray, so T always runs with full lanes until the work counter runs dry).
 // KIND: 0 = TRT_BVH_REFERENCE, 1 = TRT_BVH_SAH, 2 = TRT_BVH_FLAT (U = the phase-A boxes in the constant bank),
 // 3 / 4 = TRT_BVH_SAH / TRT_BVH_REFERENCE walked on their 4-wide nodes. PRIM: paths start from the records of k_primary.
-template <int KIND, bool SMEM, bool COUNT, bool PRIM>
+// GEOM_EARLY (flat list only): HitRecord::new for every lane that hit, beside the material lookup (round-1 form), instead of later and
+// only for the lanes that scatter. Same operations per lane either way; which placement is faster depends on the scene — with
+// spheres in the list (their normal costs a square root and three divisions) early wins (glass Cornell 4K: 252.3 -> 248.4 ms), with
+// quads only (precomputed normals) late wins (Cornell 1080p: 52.77 vs 52.93 ms): the launcher picks (profiles/r2l_probe_flat_hit_geometry_placement.log).
+template <int KIND, bool SMEM, bool COUNT, bool PRIM, bool GEOM_EARLY = false>
 __device__ __forceinline__ void mega_body(const MegaArgs& A, const float4* U) {
     const DevScene S = stage_scene<SMEM, KIND>(A.scene);
     const DevParams& P = A.p;
@@ -214,6 +218,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& A, const float4* U) {
         if (alive) {
             if (h.ref == TRT_REF_INVALID) color = color + atten * mk(P.bg[0], P.bg[1], P.bg[2]);
             else {
+                if (KIND == 2 && !PRIM && GEOM_EARLY) hit_geometry<SMEM>(S, h, o, d, &sf);
                 hit_material<SMEM>(S, h, &sf);
                 V3 emission = (sf.kind == TRT_MAT_LIGHT) ? sf.rgb : mk(0.0f, 0.0f, 0.0f);
                 color = color + atten * emission;
@@ -242,7 +247,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& A, const float4* U) {
                 d = normalized(dir);                                                         // Ray::new, ray.rs:12-14
             }
         } else {
-            if (scatter) hit_geometry<SMEM>(S, h, o, d, &sf);
+            if (scatter && !(KIND == 2 && GEOM_EARLY)) hit_geometry<SMEM>(S, h, o, d, &sf);
             if (scatter || regen) {
                 uint32_t sample = P.sample_offset + I.s_cur;
                 if (scatter) ++k; else k = 0;
@@ -382,9 +387,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, TRT_MEGA_MIN_BLOCKS) k_render_me
     if constexpr (MODE == 0) mega_body<KIND, SMEM, COUNT, PRIM>(A, nullptr);
     else mega_body_async<KIND, SMEM, COUNT, PRIM, MODE>(A);
 }
-template <bool PRIM>
+template <bool PRIM, bool GEOM_EARLY = false>
 __global__ void __launch_bounds__(TRT_FLAT_THREADS, TRT_FLAT_MIN_BLOCKS) k_render_mega_flat(const __grid_constant__ MegaArgs A, const __grid_constant__ FlatList L) {
-    mega_body<2, true, false, PRIM>(A, L.cbox);
+    mega_body<2, true, false, PRIM, GEOM_EARLY>(A, L.cbox);
 }
 
 // ------------------------------------------------------------------ AOV / sample batch / trace
@@ -573,7 +578,7 @@ cudaError_t launch_render_mega(const SceneView& v, const trt_camera& cam, const 
     if (use8) {
         e = count ? mega_fn4<5, false, true, 2, false>(&fn, &blocks_per_sm, smem) : mega_fn4<5, false, false, 2, false>(&fn, &blocks_per_sm, smem);
     } else if (v.kind == 2) {
-        fn = prim ? (const void*)k_render_mega_flat<true> : (const void*)k_render_mega_flat<false>;
+        fn = prim ? (const void*)k_render_mega_flat<true> : (v.n_spheres > 0 ? (const void*)k_render_mega_flat<false, true> : (const void*)k_render_mega_flat<false, false>);
         if (smem > 48 * 1024) { e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, TRT_FLAT_THREADS, smem);
     } else if (kind == 3) {
