@@ -122,6 +122,24 @@ def test_rust_bindings_name_every_symbol():
     assert declared == bound, declared ^ bound
 
 
+def test_flag_constants_agree_across_bindings(trt):
+    """trt_params.flags switches (include/trt.h) as seen from Python (_lib.py) and Rust (trt-sys): same bits everywhere, and no
+    two single-bit switches share a bit with each other or with the two multi-bit fields (regen_min: bits 8..15, step: 16..17)."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "trt.h")).read()
+    rs = open(os.path.join(ROOT, "rust", "trt-sys", "src", "lib.rs")).read()
+    c_flags = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+TRT_FLAG_([A-Z0-9_]+)\s+(0x[0-9a-fA-F]+|\d+)u", hdr)}
+    assert {"COUNT_EVENTS", "NO_TAIL_SPLIT", "BINARY_NODES", "COUNT_WALKED", "INLINE_PRIMARY", "PRIMARY_PASS", "NO_WIDE8"} <= set(c_flags), c_flags
+    for name, bits in c_flags.items():
+        assert bits and bits & (bits - 1) == 0, (name, bits)                      # one bit each
+        assert not bits & 0x3FF00, (name, bits)                                   # outside the regen_min and step fields
+        assert getattr(trt._lib, "FLAG_" + name) == bits, name
+        m = re.search(r"pub const TRT_FLAG_%s: u32 = (0x[0-9a-fA-F]+|\d+);" % name, rs)
+        assert m and int(m.group(1), 0) == bits, name
+    assert len(set(c_flags.values())) == len(c_flags)
+    assert trt._lib.flag_step(3) == 3 << 16 and "((n) & 3u) << 16" in hdr and "(n & 3) << 16" in rs
+
+
 def test_rust_build_lists_every_translation_unit():
     """rust/trt-sys/build.rs had its own source list and missed trt_lbvh.cu. Both builds now read
     csrc/sources.txt; that file must name every .cu / .cpp under csrc/ and neither build script may name one itself."""
